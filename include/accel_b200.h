@@ -1,0 +1,160 @@
+/*
+ * accel_b200.h - C ABI of the B200-native ACCEL-v1 hot path (libaccel_b200.so).
+ *
+ * Drop-in boundary for the reference's BSR-INT8 path.  The reference itself has no FFI
+ * (SURVEY.md 8b): its boundary is a set of Python call signatures plus the C++ host class.
+ * Every entry point below names the reference interface it stands in for (file:line under
+ * the reference root).  All `*_dev` / unqualified data pointers are DEVICE pointers owned by
+ * the caller (PyTorch allocates; this library never allocates device memory); `*_host`
+ * pointers are host pointers.  Functions return 0 or a negative accel_status that mirrors
+ * AcceleratorError::Code (hw/sim/cpp/include/accelerator_driver.hpp:337-345).
+ * Calls are asynchronous on `stream` unless stated otherwise.  No CPU fallback exists.
+ */
+#ifndef ACCEL_B200_H
+#define ACCEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ACCEL_API __attribute__((visibility("default")))
+#else
+#define ACCEL_API
+#endif
+
+typedef void* accel_stream_t; /* cudaStream_t */
+
+typedef enum accel_status {
+  ACCEL_OK = 0,
+  ACCEL_INIT_FAILED = -1,     /* AcceleratorError::INIT_FAILED    */
+  ACCEL_TIMEOUT = -2,         /* AcceleratorError::TIMEOUT        */
+  ACCEL_DMA_ERROR = -3,       /* AcceleratorError::DMA_ERROR      (CUDA runtime error) */
+  ACCEL_ILLEGAL_COMMAND = -4, /* AcceleratorError::ILLEGAL_COMMAND */
+  ACCEL_INVALID_CONFIG = -5,  /* AcceleratorError::INVALID_CONFIG (bad sizes / BSR structure) */
+  ACCEL_MEMORY_ERROR = -6,    /* AcceleratorError::MEMORY_ERROR   (workspace too small / misaligned) */
+  ACCEL_NOT_READY = -7        /* AcceleratorError::NOT_READY      (plan not uploaded) */
+} accel_status;
+
+/* Epilogue flags (golden_models.cpp:298-303, :378-411, :465-490). */
+enum {
+  ACCEL_RELU = 1 << 0,      /* relu_int32 on the accumulator before scaling            */
+  ACCEL_OUT_I8 = 1 << 1,    /* per-channel requant -> int8 (needs chan_scale)          */
+  ACCEL_OUT_I32 = 1 << 2,   /* raw INT32 accumulator (+bias, +relu)                    */
+  ACCEL_OUT_F32 = 1 << 3    /* float32(acc) * chan_scale[c]  (de-quantised logits)     */
+};
+
+/* Where activation row m, output channel c lands:
+ *   out[(m / rows_per_image) * image_stride + c * chan_stride + (m % rows_per_image) * row_stride]
+ * Row-major [M, ld]:  rows_per_image = M, image_stride = 0, chan_stride = 1, row_stride = ld.
+ * NCHW conv output:   rows_per_image = Ho*Wo, image_stride = Cout*Ho*Wo, chan_stride = Ho*Wo, row_stride = 1. */
+typedef struct accel_out_layout {
+  int64_t rows_per_image;
+  int64_t image_stride;
+  int64_t chan_stride;
+  int64_t row_stride;
+} accel_out_layout;
+
+typedef struct accel_epilogue {
+  int32_t flags;             /* ACCEL_RELU | one ACCEL_OUT_*                                   */
+  int32_t n_channels;        /* channels actually written (<= n_block_rows*14)                  */
+  const float* chan_scale;   /* [n_channels] float32 requant factor sf[c]; may be NULL for I32  */
+  const int32_t* bias;       /* [n_channels] INT32 bias added to the accumulator; may be NULL   */
+  const int8_t* residual;    /* same layout as out (int8); NULL = no residual add               */
+  float res_scale_main;      /* add_residual_int8(main, res, s_main, s_res, s_out)              */
+  float res_scale_res;
+  float res_scale_out;
+  unsigned long long* sat_count; /* device counter += #values clipped by the int8 requant; may be NULL */
+  int32_t* chan_absmax;      /* device [n_channels], atomicMax of |acc| per channel; may be NULL */
+} accel_epilogue;
+
+/* Convolution geometry: input int8 NCHW, weights viewed [Cout, Cin*k*k] with K index
+ * (c_in, kh, kw) exactly as im2col_int8 orders it (golden_models.cpp:801-842). */
+typedef struct accel_conv_geom {
+  int32_t batch, c_in, h, w;
+  int32_t ksize, stride, pad;
+} accel_conv_geom;
+
+typedef struct accel_plan accel_plan; /* opaque: host-side schedule of one BSR weight matrix */
+
+/* --- library ---------------------------------------------------------------------------- */
+ACCEL_API const char* accel_last_error_string(void);
+ACCEL_API const char* accel_version(void);
+/* 0 if a sm_100 device is current and the tcgen05 path can run, else ACCEL_INIT_FAILED. */
+ACCEL_API int accel_device_check(void);
+
+/* --- weight plan: replaces AccelDriver.load_sparse_weights (sw/host/accel.py:177-236) and
+ *     AcceleratorDriver::set_layer_weights / load_weights_bsr (accelerator_driver.cpp:643-760).
+ * Validates the structure with the rules of validate_bsr (bsr_packer.hpp:364-436), builds the
+ * MMA schedule on the host and reports the device workspace it needs.  Convention B:
+ * block-rows = output channels, col_idx = K tile.  block must be 14 (the tensor-core path). */
+ACCEL_API int accel_plan_create(const int32_t* row_ptr_host, const int32_t* col_idx_host, int32_t n_block_rows,
+                      int32_t n_block_cols, int32_t block, int32_t group_rows_hint /* 0 = default (32) */,
+                      accel_plan** plan_out, size_t* workspace_bytes);
+/* Repack the 14x14 blocks (`blocks_dev`, nnz*196 int8, reference layout) into 16-aligned MMA
+ * tiles inside `workspace_dev` (>= workspace_bytes, 256-byte aligned) and upload the schedule. */
+ACCEL_API int accel_plan_upload(accel_plan* plan, const int8_t* blocks_dev, void* workspace_dev, size_t workspace_bytes,
+                      accel_stream_t stream);
+ACCEL_API void accel_plan_destroy(accel_plan* plan);
+ACCEL_API int64_t accel_plan_num_blocks(const accel_plan* plan);
+ACCEL_API int64_t accel_plan_num_mma(const accel_plan* plan); /* tcgen05.mma instructions per 128-row tile */
+/* Schedule read-out for tests / tooling: writes up to `cap` records of 8 int32
+ * {group, first_block_row, local_row, k_chunk, window_tile, block_lo, block_hi, batch} and returns the op count. */
+ACCEL_API int64_t accel_plan_export_ops(const accel_plan* plan, int32_t* records, int64_t cap);
+
+/* --- K1+K3: block-sparse GEMM, tcgen05 kind::i8, fused epilogue.
+ * Replaces gemm_bsr_int8_golden (sw/golden/golden_fc1_test.py:49-108), AccelDriver.run_inference
+ * (sw/host/accel.py:279-342) and AcceleratorDriver::run_layer (accelerator_driver.cpp:435-496).
+ * act: int8 [M, K] row-major with leading dimension lda (K may be the unpadded width). */
+ACCEL_API int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64_t M, int64_t K, int64_t lda,
+                      const accel_epilogue* epi, void* out, const accel_out_layout* layout, accel_stream_t stream);
+
+/* --- K2+K1+K3: implicit-im2col BSR convolution (conv2d_int8_im2col, golden_models.cpp:883-933,
+ * with the BSR weights of export_bsr_14x14.py).  Output NCHW through `layout`. */
+ACCEL_API int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const accel_conv_geom* geom,
+                      const accel_epilogue* epi, void* out, const accel_out_layout* layout, accel_stream_t stream);
+
+/* --- reference-shaped CUDA-core kernels: any block size (4/8/14/16 fixtures), Convention B or A.
+ * Same arithmetic as above, used for the generic-block path and as an on-device cross-check.
+ * orient 0 = Convention B (golden_fc1_test.py), 1 = Convention A (golden_models.cpp:187-255). */
+ACCEL_API int accel_bsr_gemm_generic(const int8_t* act, int64_t M, int64_t K, int64_t lda, const int32_t* row_ptr,
+                           const int32_t* col_idx, const int8_t* blocks, int32_t n_block_rows, int32_t block_h,
+                           int32_t block_w, int32_t orient, int64_t n_out, int32_t* out, int64_t ldo,
+                           accel_stream_t stream);
+
+/* --- K4: GPU packer / pruner (export_bsr_14x14.py:406-484, export_bsr.py:76-153,
+ * blocksparse_train.py:93-138).  Two phases so that the caller owns every allocation. */
+/* per-block statistics of a dense [rows, cols] matrix: int8 -> L1 sums (int32), float -> L2 norms (float32) */
+ACCEL_API int accel_block_l1_i8(const int8_t* w, int64_t rows, int64_t cols, int64_t ld, int32_t block, int32_t* l1_out,
+                      accel_stream_t stream);
+ACCEL_API int accel_block_l2_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, int32_t bh, int32_t bw, float* l2_out,
+                       accel_stream_t stream);
+/* keep[i] (uint8, [nbr*nbc]) -> row_ptr [nbr+1] (int32) and per-block output slot (int32, -1 = dropped) */
+ACCEL_API int accel_bsr_scan(const uint8_t* keep, int32_t nbr, int32_t nbc, int32_t* row_ptr, int32_t* slot,
+                   accel_stream_t stream);
+/* gather kept blocks: col_idx [nnz], blocks [nnz, block, block] (zero padded at the edges) */
+ACCEL_API int accel_bsr_gather_i8(const int8_t* w, int64_t rows, int64_t cols, int64_t ld, int32_t block, const int32_t* slot,
+                        int32_t nbr, int32_t nbc, int32_t* col_idx, int8_t* blocks, accel_stream_t stream);
+/* per-row symmetric quantisation q = clip(rint(w / scale[row]), -128, 127) (quantize.py:71-98) */
+ACCEL_API int accel_quantize_rows_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, const float* scales, int8_t* q,
+                            accel_stream_t stream);
+ACCEL_API int accel_row_absmax_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, float* absmax,
+                         accel_stream_t stream);
+
+/* --- K5 + stand-alone epilogue pieces (golden_models.cpp:378-411, :465-490, :534-628) */
+ACCEL_API int accel_requant_i32_i8(const int32_t* acc, int8_t* out, int64_t n_outer, int64_t n_chan, int64_t n_inner,
+                         const float* chan_scale, const int32_t* bias, int32_t relu, unsigned long long* sat_count,
+                         accel_stream_t stream);
+ACCEL_API int accel_add_residual_i8(const int8_t* main_, const int8_t* res, int8_t* out, int64_t n, float s_main, float s_res,
+                          float s_out, accel_stream_t stream);
+ACCEL_API int accel_maxpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, int32_t pool,
+                     int32_t stride, int32_t pad, accel_stream_t stream);
+ACCEL_API int accel_avgpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, accel_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACCEL_B200_H */

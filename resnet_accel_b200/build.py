@@ -1,0 +1,53 @@
+"""In-tree build of libaccel_b200.so with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m resnet_accel_b200.build [--force]
+
+The .so lands next to the sources (resnet_accel_b200/libaccel_b200.so): it is git-ignored but
+travels to the GPU box with the snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libaccel_b200.so")
+SOURCES = ["api.cu", "plan.cpp"]
+DEPS = ["api.cu", "plan.cpp", "plan.h", "ptx.cuh", "bsr_tc.cuh", "simple_kernels.cuh",
+        os.path.join("..", "..", "include", "accel_b200.h")]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libaccel_b200.so")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "--fmad=false",
+           "-Xptxas", "-v" if verbose else "-O3",
+           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,373 @@
+// C ABI of libaccel_b200.so (declared in include/accel_b200.h).  Thin: validate, fill the kernel
+// parameter block, launch on the caller's stream.  No device allocation, no CPU arithmetic.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/accel_b200.h"
+#include "bsr_tc.cuh"
+#include "plan.h"
+#include "simple_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(ACCEL_DMA_ERROR, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                            \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
+  } while (0)
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+// grid for grid-stride kernels: a multiple of the SM count, capped by the work
+int grid_for(int64_t work_items, int threads, int per_sm = 8) {
+  const int64_t need = (work_items + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
+  int64_t g = need < cap ? need : cap;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+std::once_flag g_attr_once;
+cudaError_t g_attr_err = cudaSuccess;
+void set_kernel_attrs() {
+  g_attr_err = cudaFuncSetAttribute(accel::bsr_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    accel::kSmemBytes);
+  if (g_attr_err == cudaSuccess)
+    g_attr_err = cudaFuncSetAttribute(accel::bsr_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      accel::kSmemBytes);
+}
+
+int check_epilogue(const accel_epilogue* epi, const accel_out_layout* lay, const void* out, int32_t max_channels) {
+  if (!epi || !lay || !out) return fail(ACCEL_INVALID_CONFIG, "null epilogue / layout / output");
+  const int kinds = (epi->flags & ACCEL_OUT_I8 ? 1 : 0) + (epi->flags & ACCEL_OUT_I32 ? 1 : 0) +
+                    (epi->flags & ACCEL_OUT_F32 ? 1 : 0);
+  if (kinds != 1) return fail(ACCEL_INVALID_CONFIG, "exactly one of ACCEL_OUT_I8 / I32 / F32 must be set");
+  if ((epi->flags & (ACCEL_OUT_I8 | ACCEL_OUT_F32)) && !epi->chan_scale)
+    return fail(ACCEL_INVALID_CONFIG, "chan_scale required for int8 / float32 output");
+  if (epi->residual && !(epi->flags & ACCEL_OUT_I8))
+    return fail(ACCEL_INVALID_CONFIG, "residual add is defined on the int8 output only");
+  if (epi->n_channels < 0 || epi->n_channels > max_channels)
+    return fail(ACCEL_INVALID_CONFIG, "n_channels exceeds n_block_rows*14");
+  if (lay->rows_per_image <= 0) return fail(ACCEL_INVALID_CONFIG, "rows_per_image must be positive");
+  return ACCEL_OK;
+}
+
+int launch_tc(const accel::Plan* P, accel::TcParams& prm, bool conv, cudaStream_t st) {
+  std::call_once(g_attr_once, set_kernel_attrs);
+  if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(smem)");
+  const int n_groups = static_cast<int>(P->groups.size());
+  const int64_t m_tiles = (prm.M + accel::kTileM - 1) / accel::kTileM;
+  if (n_groups == 0 || m_tiles == 0) return ACCEL_OK;
+  const int64_t ctas = m_tiles * n_groups;
+  if (ctas > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "grid too large");
+  prm.ws = P->ws_dev + P->off_blob;
+  prm.batches = reinterpret_cast<const accel::BatchInfo*>(P->ws_dev + P->off_batches);
+  prm.groups = reinterpret_cast<const accel::GroupInfo*>(P->ws_dev + P->off_groups);
+  prm.n_groups = n_groups;
+  if (conv)
+    accel::bsr_tc_kernel<true><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemBytes, st>>>(prm);
+  else
+    accel::bsr_tc_kernel<false><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemBytes, st>>>(prm);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+}  // namespace
+
+struct accel_plan {
+  accel::Plan p;
+};
+
+extern "C" {
+
+const char* accel_last_error_string(void) { return g_err.c_str(); }
+const char* accel_version(void) { return "accel_b200 0.1 (sm_100a, tcgen05 kind::i8)"; }
+
+int accel_device_check(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return fail(ACCEL_INIT_FAILED, "no CUDA device");
+  if (prop.major != 10) return fail(ACCEL_INIT_FAILED, "device is not sm_100 (tcgen05 kind::i8 needs a B200)");
+  return ACCEL_OK;
+}
+
+int accel_plan_create(const int32_t* row_ptr_host, const int32_t* col_idx_host, int32_t n_block_rows,
+                      int32_t n_block_cols, int32_t block, int32_t group_rows_hint, accel_plan** plan_out,
+                      size_t* workspace_bytes) {
+  if (!row_ptr_host || !plan_out || !workspace_bytes) return fail(ACCEL_INVALID_CONFIG, "null argument");
+  if (block != accel::kBlock) return fail(ACCEL_INVALID_CONFIG, "Block size must be 14");  // accel.py:196
+  if (n_block_rows < 0 || n_block_cols < 0) return fail(ACCEL_INVALID_CONFIG, "negative block grid");
+  if (row_ptr_host[n_block_rows] > 0 && !col_idx_host) return fail(ACCEL_INVALID_CONFIG, "null col_idx");
+  accel_plan* pl = new accel_plan();
+  pl->p.group_rows = group_rows_hint;
+  const std::string msg = accel::build_plan(row_ptr_host, col_idx_host, n_block_rows, n_block_cols, &pl->p);
+  if (!msg.empty()) {
+    delete pl;
+    return fail(ACCEL_INVALID_CONFIG, msg);
+  }
+  *plan_out = pl;
+  *workspace_bytes = pl->p.ws_bytes;
+  return ACCEL_OK;
+}
+
+int accel_plan_upload(accel_plan* plan, const int8_t* blocks_dev, void* workspace_dev, size_t workspace_bytes,
+                      accel_stream_t stream) {
+  if (!plan || !workspace_dev) return fail(ACCEL_INVALID_CONFIG, "null plan / workspace");
+  accel::Plan& P = plan->p;
+  if (workspace_bytes < P.ws_bytes) return fail(ACCEL_MEMORY_ERROR, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace_dev) & 255) return fail(ACCEL_MEMORY_ERROR, "workspace not 256-byte aligned");
+  if (P.nnz > 0 && !blocks_dev) return fail(ACCEL_INVALID_CONFIG, "null blocks");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    return bytes ? cudaMemcpyAsync(ws + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  };
+  CU(up(P.off_batches, P.batches.data(), P.batches.size() * sizeof(accel::BatchInfo)));
+  CU(up(P.off_groups, P.groups.data(), P.groups.size() * sizeof(accel::GroupInfo)));
+  CU(up(P.off_opsrc, P.op_src.data(), P.op_src.size() * sizeof(accel::OpSrc)));
+  CU(up(P.off_opoff, P.op_blob_off.data(), P.op_blob_off.size() * sizeof(uint32_t)));
+  CU(up(P.off_opmoff, P.op_meta_off.data(), P.op_meta_off.size() * sizeof(uint32_t)));
+  CU(up(P.off_opmeta, P.op_meta.data(), P.op_meta.size() * sizeof(uint16_t)));
+  if (P.n_ops > 0) {
+    accel::repack_blocks_kernel<<<static_cast<unsigned>(P.n_ops), 128, 0, st>>>(
+        blocks_dev, ws + P.off_blob, reinterpret_cast<const accel::OpSrc*>(ws + P.off_opsrc),
+        reinterpret_cast<const uint32_t*>(ws + P.off_opoff), reinterpret_cast<const uint32_t*>(ws + P.off_opmoff),
+        reinterpret_cast<const uint16_t*>(ws + P.off_opmeta), P.n_ops);
+    CU(cudaGetLastError());
+  }
+  // the host vectors are pageable: make sure the copies have consumed them before returning
+  CU(cudaStreamSynchronize(st));
+  P.ws_dev = ws;
+  P.uploaded = true;
+  return ACCEL_OK;
+}
+
+void accel_plan_destroy(accel_plan* plan) { delete plan; }
+int64_t accel_plan_num_blocks(const accel_plan* plan) { return plan ? plan->p.nnz : 0; }
+int64_t accel_plan_num_mma(const accel_plan* plan) { return plan ? plan->p.n_ops : 0; }
+
+int64_t accel_plan_export_ops(const accel_plan* plan, int32_t* rec, int64_t cap) {
+  if (!plan) return 0;
+  const accel::Plan& P = plan->p;
+  int64_t op = 0;
+  for (size_t gi = 0; gi < P.groups.size(); ++gi) {
+    const accel::GroupInfo& G = P.groups[gi];
+    for (int32_t b = G.batch_begin; b < G.batch_end; ++b)
+      for (int i = 0; i < P.batches[b].n_ops; ++i, ++op) {
+        if (rec && op < cap) {
+          int32_t* r = rec + op * 8;
+          r[0] = static_cast<int32_t>(gi); r[1] = G.br0; r[2] = P.op_meta[op] & 31; r[3] = P.batches[b].chunk;
+          r[4] = P.op_meta[op] >> 5; r[5] = P.op_src[op].blk_lo; r[6] = P.op_src[op].blk_hi; r[7] = b;
+        }
+      }
+  }
+  return op;
+}
+
+int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64_t M, int64_t K, int64_t lda,
+                      const accel_epilogue* epi, void* out, const accel_out_layout* layout, accel_stream_t stream) {
+  if (!plan) return fail(ACCEL_INVALID_CONFIG, "null plan");
+  if (!plan->p.uploaded) return fail(ACCEL_NOT_READY, "Weights not loaded");  // accel.py:296
+  if (M < 0 || K < 0 || lda < K) return fail(ACCEL_INVALID_CONFIG, "bad activation shape");
+  if (M > 0 && !act) return fail(ACCEL_INVALID_CONFIG, "Activations not loaded");  // accel.py:297
+  if (K > INT_MAX / 2) return fail(ACCEL_INVALID_CONFIG, "K too large");
+  // accumulator overflow guard (SURVEY.md hard part 7): |acc| <= K*128*128 must stay below 2^31
+  if (K >= 131072) return fail(ACCEL_INVALID_CONFIG, "K >= 131072 could overflow the INT32 accumulator");
+  int rc = check_epilogue(epi, layout, out, plan->p.nbr * accel::kBlock);
+  if (rc) return rc;
+  accel::TcParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.x = act; prm.M = M; prm.K = static_cast<int32_t>(K); prm.lda = lda;
+  prm.x_align2 = ((reinterpret_cast<uintptr_t>(act) | static_cast<uintptr_t>(lda)) & 1) == 0;
+  prm.epi = *epi; prm.out = out; prm.lay = *layout;
+  return launch_tc(&plan->p, prm, false, static_cast<cudaStream_t>(stream));
+}
+
+int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const accel_conv_geom* g,
+                      const accel_epilogue* epi, void* out, const accel_out_layout* layout, accel_stream_t stream) {
+  if (!plan || !g) return fail(ACCEL_INVALID_CONFIG, "null plan / geometry");
+  if (!plan->p.uploaded) return fail(ACCEL_NOT_READY, "Weights not loaded");
+  if (g->batch < 0 || g->c_in <= 0 || g->h <= 0 || g->w <= 0 || g->ksize <= 0 || g->stride <= 0 || g->pad < 0)
+    return fail(ACCEL_INVALID_CONFIG, "bad convolution geometry");
+  if (g->h + 2 * g->pad < g->ksize || g->w + 2 * g->pad < g->ksize)
+    return fail(ACCEL_INVALID_CONFIG, "kernel larger than padded input");
+  const int64_t K = static_cast<int64_t>(g->c_in) * g->ksize * g->ksize;
+  if (K >= 131072) return fail(ACCEL_INVALID_CONFIG, "K >= 131072 could overflow the INT32 accumulator");
+  if ((K + accel::kBlock - 1) / accel::kBlock > plan->p.nbc)
+    return fail(ACCEL_INVALID_CONFIG, "Cin*k*k does not match the plan's K tiles");
+  if (g->batch > 0 && !input_nchw) return fail(ACCEL_INVALID_CONFIG, "Activations not loaded");
+  int rc = check_epilogue(epi, layout, out, plan->p.nbr * accel::kBlock);
+  if (rc) return rc;
+  accel::TcParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.Ho = (g->h + 2 * g->pad - g->ksize) / g->stride + 1;
+  prm.Wo = (g->w + 2 * g->pad - g->ksize) / g->stride + 1;
+  prm.x = input_nchw; prm.M = static_cast<int64_t>(g->batch) * prm.Ho * prm.Wo; prm.K = static_cast<int32_t>(K);
+  prm.C = g->c_in; prm.H = g->h; prm.W = g->w; prm.ksz = g->ksize; prm.stride = g->stride; prm.pad = g->pad;
+  prm.epi = *epi; prm.out = out; prm.lay = *layout;
+  return launch_tc(&plan->p, prm, true, static_cast<cudaStream_t>(stream));
+}
+
+int accel_bsr_gemm_generic(const int8_t* act, int64_t M, int64_t K, int64_t lda, const int32_t* row_ptr,
+                           const int32_t* col_idx, const int8_t* blocks, int32_t n_block_rows, int32_t block_h,
+                           int32_t block_w, int32_t orient, int64_t n_out, int32_t* out, int64_t ldo,
+                           accel_stream_t stream) {
+  if (M < 0 || K < 0 || n_out < 0 || block_h <= 0 || block_w <= 0 || n_block_rows < 0 || ldo < n_out)
+    return fail(ACCEL_INVALID_CONFIG, "bad shape");
+  if (M == 0 || n_out == 0) return ACCEL_OK;
+  if (!act || !row_ptr || !out) return fail(ACCEL_INVALID_CONFIG, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(M * n_out, 256, 16);
+  if (orient == 0)
+    accel::bsr_gemm_generic_b_kernel<<<grid, 256, 0, st>>>(act, M, K, lda, row_ptr, col_idx, blocks, n_block_rows,
+                                                           block_h, block_w, n_out, out, ldo);
+  else
+    accel::bsr_gemm_generic_a_kernel<<<grid, 256, 0, st>>>(act, M, K, lda, row_ptr, col_idx, blocks, n_block_rows,
+                                                           block_h, block_w, n_out, out, ldo);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+// ----------------------------------------------------------------------------------- packer
+static int grid_dims(int64_t rows, int64_t cols, int32_t bh, int32_t bw, int32_t* nbr, int32_t* nbc) {
+  if (rows < 0 || cols < 0 || bh <= 0 || bw <= 0) return fail(ACCEL_INVALID_CONFIG, "bad matrix / block shape");
+  *nbr = static_cast<int32_t>((rows + bh - 1) / bh);
+  *nbc = static_cast<int32_t>((cols + bw - 1) / bw);
+  return ACCEL_OK;
+}
+
+int accel_block_l1_i8(const int8_t* w, int64_t rows, int64_t cols, int64_t ld, int32_t block, int32_t* l1_out,
+                      accel_stream_t stream) {
+  int32_t nbr, nbc;
+  if (int rc = grid_dims(rows, cols, block, block, &nbr, &nbc)) return rc;
+  if (!nbr || !nbc) return ACCEL_OK;
+  accel::block_l1_i8_kernel<<<grid_for(static_cast<int64_t>(nbr) * nbc * 32, 256), 256, 0,
+                              static_cast<cudaStream_t>(stream)>>>(w, rows, cols, ld, block, nbr, nbc, l1_out);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_block_l2_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, int32_t bh, int32_t bw, float* l2_out,
+                       accel_stream_t stream) {
+  int32_t nbr, nbc;
+  if (int rc = grid_dims(rows, cols, bh, bw, &nbr, &nbc)) return rc;
+  if (!nbr || !nbc) return ACCEL_OK;
+  accel::block_l2_f32_kernel<<<grid_for(static_cast<int64_t>(nbr) * nbc * 32, 256), 256, 0,
+                               static_cast<cudaStream_t>(stream)>>>(w, rows, cols, ld, bh, bw, nbr, nbc, l2_out);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_bsr_scan(const uint8_t* keep, int32_t nbr, int32_t nbc, int32_t* row_ptr, int32_t* slot,
+                   accel_stream_t stream) {
+  if (nbr < 0 || nbc < 0 || !row_ptr) return fail(ACCEL_INVALID_CONFIG, "bad block grid");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nbr == 0 || nbc == 0) {
+    CU(cudaMemsetAsync(row_ptr, 0, sizeof(int32_t) * (static_cast<size_t>(nbr) + 1), st));
+    return ACCEL_OK;
+  }
+  if (!keep || !slot) return fail(ACCEL_INVALID_CONFIG, "null keep / slot");
+  // slot[0..nbr) (it has nbr*nbc >= nbr entries) holds the per-row counts until the scan consumed them
+  accel::bsr_row_count_kernel<<<grid_for(static_cast<int64_t>(nbr) * 32, 256), 256, 0, st>>>(keep, nbr, nbc, slot);
+  CU(cudaGetLastError());
+  accel::bsr_row_scan_kernel<<<1, 1024, 0, st>>>(slot, nbr, row_ptr);
+  CU(cudaGetLastError());
+  if (nbc > 0) {
+    accel::bsr_slot_kernel<<<grid_for(static_cast<int64_t>(nbr) * 32, 256), 256, 0, st>>>(keep, nbr, nbc, row_ptr, slot);
+    CU(cudaGetLastError());
+  }
+  return ACCEL_OK;
+}
+
+int accel_bsr_gather_i8(const int8_t* w, int64_t rows, int64_t cols, int64_t ld, int32_t block, const int32_t* slot,
+                        int32_t nbr, int32_t nbc, int32_t* col_idx, int8_t* blocks, accel_stream_t stream) {
+  if (!nbr || !nbc) return ACCEL_OK;
+  accel::bsr_gather_i8_kernel<<<grid_for(static_cast<int64_t>(nbr) * nbc * 32, 256), 256, 0,
+                                static_cast<cudaStream_t>(stream)>>>(w, rows, cols, ld, block, slot, nbr, nbc, col_idx,
+                                                                     blocks);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_quantize_rows_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, const float* scales, int8_t* q,
+                            accel_stream_t stream) {
+  if (rows <= 0 || cols <= 0) return ACCEL_OK;
+  accel::quantize_rows_f32_kernel<<<grid_for(rows * cols, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, rows, cols, ld, scales, q);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_row_absmax_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, float* absmax,
+                         accel_stream_t stream) {
+  if (rows <= 0) return ACCEL_OK;
+  accel::row_absmax_f32_kernel<<<grid_for(rows * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, rows, cols,
+                                                                                                       ld, absmax);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+// ----------------------------------------------------------------------------------- epilogue pieces / pools
+int accel_requant_i32_i8(const int32_t* acc, int8_t* out, int64_t n_outer, int64_t n_chan, int64_t n_inner,
+                         const float* chan_scale, const int32_t* bias, int32_t relu, unsigned long long* sat_count,
+                         accel_stream_t stream) {
+  const int64_t total = n_outer * n_chan * n_inner;
+  if (total <= 0) return ACCEL_OK;
+  if (!chan_scale) return fail(ACCEL_INVALID_CONFIG, "chan_scale required");
+  accel::requant_i32_i8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc, out, n_outer, n_chan, n_inner, chan_scale, bias, relu, sat_count);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_add_residual_i8(const int8_t* main_, const int8_t* res, int8_t* out, int64_t n, float s_main, float s_res,
+                          float s_out, accel_stream_t stream) {
+  if (n <= 0) return ACCEL_OK;
+  accel::add_residual_i8_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(main_, res, out, n,
+                                                                                                 s_main, s_res, s_out);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_maxpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, int32_t pool,
+                     int32_t stride, int32_t pad, accel_stream_t stream) {
+  if (pool <= 0 || stride <= 0 || pad < 0 || h + 2 * pad < pool || w + 2 * pad < pool)
+    return fail(ACCEL_INVALID_CONFIG, "bad pooling geometry");
+  const int32_t Ho = (h + 2 * pad - pool) / stride + 1, Wo = (w + 2 * pad - pool) / stride + 1;
+  const int64_t total = n_planes * Ho * Wo;
+  if (total <= 0) return ACCEL_OK;
+  accel::maxpool_i8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, out, n_planes, h, w, pool, stride, pad, Ho, Wo);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_avgpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, accel_stream_t stream) {
+  if (n_planes <= 0) return ACCEL_OK;
+  accel::avgpool_i8_kernel<<<grid_for(n_planes * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out,
+                                                                                                        n_planes, h * w);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+}  // extern "C"

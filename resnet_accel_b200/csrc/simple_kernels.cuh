@@ -1,0 +1,265 @@
+// CUDA-core kernels: generic-block BSR GEMM (both conventions), GPU packer / pruner pieces,
+// stand-alone epilogue pieces and pools.  HBM-bound byte/integer work: coalesced, grid-stride,
+// sized in multiples of the SM count by the launchers in api.cu.
+#pragma once
+#include <cstdint>
+
+namespace accel {
+
+// ------------------------------------------------------------------ generic BSR GEMM (any block)
+// Convention B (sw/golden/golden_fc1_test.py:78-106): one thread per (m, output column n).
+__global__ void bsr_gemm_generic_b_kernel(const int8_t* __restrict__ X, int64_t M, int64_t K, int64_t lda,
+                                          const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                          const int8_t* __restrict__ blocks, int32_t nbr, int32_t bh, int32_t bw,
+                                          int64_t n_out, int32_t* __restrict__ Y, int64_t ldo) {
+  const int64_t total = M * n_out;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = idx / n_out, n = idx - m * n_out;
+    const int32_t br = static_cast<int32_t>(n / bh), h = static_cast<int32_t>(n - static_cast<int64_t>(br) * bh);
+    uint32_t acc = 0;  // wraps like the hardware accumulator (mac8.sv:392-399)
+    if (br < nbr) {
+      const int8_t* x = X + m * lda;
+      for (int32_t j = row_ptr[br]; j < row_ptr[br + 1]; ++j) {
+        const int64_t k0 = static_cast<int64_t>(col_idx[j]) * bw;
+        const int8_t* wrow = blocks + (static_cast<int64_t>(j) * bh + h) * bw;
+        const int lim = static_cast<int>(min(static_cast<int64_t>(bw), K - k0));
+        int32_t s = 0;
+        for (int w = 0; w < lim; ++w) s += static_cast<int32_t>(x[k0 + w]) * static_cast<int32_t>(wrow[w]);
+        acc += static_cast<uint32_t>(s);
+      }
+    }
+    Y[m * ldo + n] = static_cast<int32_t>(acc);
+  }
+}
+
+// Convention A (hw/sim/cpp/src/golden_models.cpp:187-255): B[K, N], block-rows over K, col_idx = N tile.
+__global__ void bsr_gemm_generic_a_kernel(const int8_t* __restrict__ A, int64_t M, int64_t K, int64_t lda,
+                                          const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                          const int8_t* __restrict__ blocks, int32_t nbr, int32_t bh, int32_t bw,
+                                          int64_t N, int32_t* __restrict__ C, int64_t ldo) {
+  const int64_t total = M * N;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = idx / N, n = idx - m * N;
+    const int32_t bc = static_cast<int32_t>(n / bw), jj = static_cast<int32_t>(n - static_cast<int64_t>(bc) * bw);
+    uint32_t acc = 0;
+    for (int32_t br = 0; br < nbr; ++br) {
+      int32_t lo = row_ptr[br], hi = row_ptr[br + 1];
+      while (lo < hi) {  // col_idx is strictly increasing inside a block-row (validate_bsr)
+        const int32_t mid = (lo + hi) >> 1;
+        if (col_idx[mid] < bc) lo = mid + 1; else hi = mid;
+      }
+      if (lo < row_ptr[br + 1] && col_idx[lo] == bc) {
+        const int8_t* blk = blocks + static_cast<int64_t>(lo) * bh * bw;
+        int32_t s = 0;
+        for (int i = 0; i < bh; ++i) {
+          const int64_t k = static_cast<int64_t>(br) * bh + i;
+          if (k < K) s += static_cast<int32_t>(A[m * lda + k]) * static_cast<int32_t>(blk[i * bw + jj]);
+        }
+        acc += static_cast<uint32_t>(s);
+      }
+    }
+    C[m * ldo + n] = static_cast<int32_t>(acc);
+  }
+}
+
+// ------------------------------------------------------------------ packer: block statistics
+// One warp per block; lanes stride over the block's elements (rows of `bw` contiguous bytes).
+__global__ void block_l1_i8_kernel(const int8_t* __restrict__ w, int64_t rows, int64_t cols, int64_t ld, int32_t b,
+                                   int32_t nbr, int32_t nbc, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t blk = warp0; blk < static_cast<int64_t>(nbr) * nbc; blk += nwarps) {
+    const int64_t r0 = (blk / nbc) * b, c0 = (blk % nbc) * b;
+    int32_t s = 0;
+    for (int e = lane; e < b * b; e += 32) {
+      const int64_t r = r0 + e / b, c = c0 + e % b;
+      if (r < rows && c < cols) { const int v = w[r * ld + c]; s += v < 0 ? -v : v; }
+    }
+    s = __reduce_add_sync(0xffffffffu, s);
+    if (lane == 0) out[blk] = s;
+  }
+}
+
+__global__ void block_l2_f32_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld, int32_t bh,
+                                    int32_t bw, int32_t nbr, int32_t nbc, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t blk = warp0; blk < static_cast<int64_t>(nbr) * nbc; blk += nwarps) {
+    const int64_t r0 = (blk / nbc) * bh, c0 = (blk % nbc) * bw;
+    double s = 0.0;
+    for (int e = lane; e < bh * bw; e += 32) {
+      const int64_t r = r0 + e / bw, c = c0 + e % bw;
+      if (r < rows && c < cols) { const double v = w[r * ld + c]; s += v * v; }
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[blk] = static_cast<float>(sqrt(s));
+  }
+}
+
+// ------------------------------------------------------------------ packer: scan + compaction
+// keep[nbr*nbc] -> per-row counts (one warp per block-row, ballot popcount)
+__global__ void bsr_row_count_kernel(const uint8_t* __restrict__ keep, int32_t nbr, int32_t nbc,
+                                     int32_t* __restrict__ row_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t br = warp0; br < nbr; br += nwarps) {
+    int32_t cnt = 0;
+    for (int32_t c = lane; c < nbc; c += 32) cnt += keep[br * nbc + c] ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) row_cnt[br] = cnt;
+  }
+}
+// exclusive scan of row counts into row_ptr[0..nbr] (single CTA, chunked warp scans)
+__global__ void bsr_row_scan_kernel(const int32_t* __restrict__ row_cnt, int32_t nbr, int32_t* __restrict__ row_ptr) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) { carry = 0; row_ptr[0] = 0; }
+  __syncthreads();
+  for (int32_t base = 0; base < nbr; base += blockDim.x) {
+    const int32_t i = base + threadIdx.x;
+    int32_t v = i < nbr ? row_cnt[i] : 0, incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t t = lane < nw ? warp_tot[lane] : 0, ti = t;
+      for (int o = 1; o < 32; o <<= 1) { const int32_t u = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += u; }
+      warp_tot[lane] = ti - t;  // exclusive offsets per warp
+      if (lane == 31) warp_tot[31] = ti - t;
+    }
+    __syncthreads();
+    const int32_t total_prev = carry;
+    if (i < nbr) row_ptr[i + 1] = total_prev + warp_tot[warp] + incl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = total_prev + warp_tot[warp] + incl;
+    __syncthreads();
+  }
+}
+// slot[br*nbc+c] = output index of a kept block (row-major scan order == reference loop order), -1 = dropped
+__global__ void bsr_slot_kernel(const uint8_t* __restrict__ keep, int32_t nbr, int32_t nbc,
+                                const int32_t* __restrict__ row_ptr, int32_t* __restrict__ slot) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t br = warp0; br < nbr; br += nwarps) {
+    int32_t base = row_ptr[br];
+    for (int32_t c0 = 0; c0 < nbc; c0 += 32) {
+      const int32_t c = c0 + lane;
+      const bool k = c < nbc && keep[br * nbc + c];
+      const uint32_t bal = __ballot_sync(0xffffffffu, k);
+      if (c < nbc) slot[br * nbc + c] = k ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
+      base += __popc(bal);
+    }
+  }
+}
+// one warp per kept block: copy (zero padded) b x b bytes, record its column
+__global__ void bsr_gather_i8_kernel(const int8_t* __restrict__ w, int64_t rows, int64_t cols, int64_t ld, int32_t b,
+                                     const int32_t* __restrict__ slot, int32_t nbr, int32_t nbc,
+                                     int32_t* __restrict__ col_idx, int8_t* __restrict__ blocks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t blk = warp0; blk < static_cast<int64_t>(nbr) * nbc; blk += nwarps) {
+    const int32_t s = slot[blk];
+    if (s < 0) continue;
+    const int64_t r0 = (blk / nbc) * b, c0 = (blk % nbc) * b;
+    for (int e = lane; e < b * b; e += 32) {
+      const int64_t r = r0 + e / b, c = c0 + e % b;
+      blocks[static_cast<int64_t>(s) * b * b + e] = (r < rows && c < cols) ? w[r * ld + c] : static_cast<int8_t>(0);
+    }
+    if (lane == 0) col_idx[s] = static_cast<int32_t>(blk % nbc);
+  }
+}
+
+// ------------------------------------------------------------------ quantiser (quantize.py:71-98)
+__global__ void row_absmax_f32_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld,
+                                      float* __restrict__ absmax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    float m = 0.f;
+    for (int64_t c = lane; c < cols; c += 32) m = fmaxf(m, fabsf(w[r * ld + c]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) absmax[r] = m;
+  }
+}
+__global__ void quantize_rows_f32_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld,
+                                         const float* __restrict__ scales, int8_t* __restrict__ q) {
+  const int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / cols, c = idx - r * cols;
+    const float v = rintf(__fdiv_rn(w[r * ld + c], scales[r]));   // np.rint(x / scale), float32
+    q[idx] = static_cast<int8_t>(fminf(127.f, fmaxf(-128.f, v)));
+  }
+}
+
+// ------------------------------------------------------------------ stand-alone epilogue pieces
+__global__ void requant_i32_i8_kernel(const int32_t* __restrict__ acc, int8_t* __restrict__ out, int64_t n_outer,
+                                      int64_t n_chan, int64_t n_inner, const float* __restrict__ sf,
+                                      const int32_t* __restrict__ bias, int32_t relu,
+                                      unsigned long long* __restrict__ sat_count) {
+  const int64_t total = n_outer * n_chan * n_inner;
+  uint32_t sat = 0;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t c = (idx / n_inner) % n_chan;
+    int a = acc[idx];
+    if (bias) a += bias[c];
+    if (relu) a = max(a, 0);
+    int q = __float2int_rn(__fmul_rn(__int2float_rn(a), sf[c]));
+    if (q > 127) { q = 127; ++sat; } else if (q < -128) { q = -128; ++sat; }
+    out[idx] = static_cast<int8_t>(q);
+  }
+  if (sat_count) {
+    sat = __reduce_add_sync(0xffffffffu, sat);
+    if ((threadIdx.x & 31) == 0 && sat) atomicAdd(sat_count, static_cast<unsigned long long>(sat));
+  }
+}
+__global__ void add_residual_i8_kernel(const int8_t* __restrict__ a, const int8_t* __restrict__ b,
+                                       int8_t* __restrict__ out, int64_t n, float sa, float sb, float so) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float x = __fmul_rn(__int2float_rn(a[i]), sa), y = __fmul_rn(__int2float_rn(b[i]), sb);
+    const int q = __float2int_rn(__fdiv_rn(__fadd_rn(x, y), so));
+    out[i] = static_cast<int8_t>(min(127, max(-128, q)));
+  }
+}
+__global__ void maxpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out, int64_t n_planes, int32_t H,
+                                  int32_t W, int32_t pool, int32_t stride, int32_t pad, int32_t Ho, int32_t Wo) {
+  const int64_t total = n_planes * Ho * Wo;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ow = static_cast<int>(idx % Wo), oh = static_cast<int>((idx / Wo) % Ho);
+    const int64_t pl = idx / (static_cast<int64_t>(Wo) * Ho);
+    int best = -128;
+    for (int ph = 0; ph < pool; ++ph)
+      for (int pw = 0; pw < pool; ++pw) {
+        const int ih = oh * stride + ph - pad, iw = ow * stride + pw - pad;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) best = max(best, static_cast<int>(x[(pl * H + ih) * W + iw]));
+      }
+    out[idx] = static_cast<int8_t>(best);
+  }
+}
+// one warp per plane: (sum + HW/2) / HW with C truncating division (golden_models.cpp:619)
+__global__ void avgpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out, int64_t n_planes,
+                                  int32_t hw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t pl = warp0; pl < n_planes; pl += nwarps) {
+    int s = 0;
+    for (int i = lane; i < hw; i += 32) s += x[pl * hw + i];
+    s = __reduce_add_sync(0xffffffffu, s);
+    if (lane == 0) out[pl] = static_cast<int8_t>(min(127, max(-128, (s + hw / 2) / hw)));
+  }
+}
+
+}  // namespace accel

@@ -1,0 +1,271 @@
+"""Torch-facing wrappers over the C ABI: device memory and streams come from PyTorch, every
+byte of arithmetic happens in libaccel_b200.so.  No fallbacks: without CUDA these raise."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AcceleratorError, ConvGeom, Epilogue, OutLayout, check
+
+BLOCK = 14
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise AcceleratorError(_lib.INIT_FAILED, "no CUDA device: resnet_accel_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def to_device(a, dtype: torch.dtype, device=None) -> torch.Tensor:
+    """numpy / torch (any device) -> contiguous CUDA tensor of `dtype` (zero-copy when already there)."""
+    device = device or _require_cuda()
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.uint16:
+            a = a.astype(np.int32)
+        elif a.dtype == np.uint32:
+            a = a.astype(np.int64)
+        t = torch.from_numpy(a)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=False).contiguous()
+
+
+class BsrPlan:
+    """A BSR weight matrix (Convention B, 14x14) resident on the GPU in MMA-tile form.
+
+    Mirrors what ``AccelDriver.load_sparse_weights`` does for the FPGA (sw/host/accel.py:177-236):
+    takes ``row_ptr`` / ``col_idx`` / ``blocks[nnz,14,14]`` exactly as the exporters write them.
+    """
+
+    def __init__(self, row_ptr, col_idx, blocks, n_block_cols: Optional[int] = None, group_rows: int = 0):
+        self.device = _require_cuda()
+        L = _lib.lib()
+        rp = np.ascontiguousarray(_host(row_ptr), dtype=np.int32)
+        ci = np.ascontiguousarray(_host(col_idx), dtype=np.int32)
+        if rp.ndim != 1 or rp.size < 1:
+            raise AcceleratorError(_lib.INVALID_CONFIG, "row_ptr must be 1-D with >= 1 entry")
+        self.n_block_rows = int(rp.size - 1)
+        if n_block_cols is None:
+            n_block_cols = int(ci.max()) + 1 if ci.size else 0
+        self.n_block_cols = int(n_block_cols)
+        if int(rp[-1]) != ci.size:
+            raise AcceleratorError(_lib.INVALID_CONFIG, f"col_idx size mismatch: expected {int(rp[-1])}, got {ci.size}")
+        blk = to_device(blocks, torch.int8, self.device) if not _is_cuda(blocks) else blocks.contiguous()
+        if blk.numel() != ci.size * BLOCK * BLOCK:
+            raise AcceleratorError(_lib.INVALID_CONFIG,
+                                   f"data size mismatch: expected {ci.size * 196}, got {blk.numel()}")
+        handle = C.c_void_p()
+        ws_bytes = C.c_size_t()
+        check(L.accel_plan_create(rp.ctypes.data, ci.ctypes.data if ci.size else None, self.n_block_rows,
+                                  self.n_block_cols, BLOCK, int(group_rows), C.byref(handle), C.byref(ws_bytes)))
+        self._h = handle
+        self.workspace = torch.empty(max(int(ws_bytes.value), 256) + 256, dtype=torch.uint8, device=self.device)
+        off = (-self.workspace.data_ptr()) % 256
+        self._ws_ptr = self.workspace.data_ptr() + off
+        check(L.accel_plan_upload(self._h, _ptr(blk) if ci.size else None, self._ws_ptr, int(ws_bytes.value), _stream()))
+        self.num_blocks = int(L.accel_plan_num_blocks(self._h))
+        self.num_mma = int(L.accel_plan_num_mma(self._h))
+        self.row_ptr, self.col_idx = rp, ci
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().accel_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def n_out_padded(self) -> int:
+        return self.n_block_rows * BLOCK
+
+    # ------------------------------------------------------------------------------------
+    def _epilogue(self, out_kind: str, n_channels: int, chan_scale, bias, relu: bool, residual, res_scales,
+                  sat_count, chan_absmax) -> Tuple[Epilogue, list]:
+        keep = []
+        flags = {"i8": _lib.OUT_I8, "i32": _lib.OUT_I32, "f32": _lib.OUT_F32}[out_kind] | (_lib.RELU if relu else 0)
+        e = Epilogue()
+        e.flags, e.n_channels = flags, int(n_channels)
+        for name, val, dt in (("chan_scale", chan_scale, torch.float32), ("bias", bias, torch.int32),
+                              ("residual", residual, torch.int8)):
+            if val is not None:
+                t = val if _is_cuda(val) and val.dtype == dt and val.is_contiguous() else to_device(val, dt, self.device)
+                if name != "residual" and t.numel() < n_channels:
+                    raise AcceleratorError(_lib.INVALID_CONFIG, f"{name} has {t.numel()} entries, need {n_channels}")
+                keep.append(t)
+                setattr(e, name, t.data_ptr())
+        s = res_scales or (1.0, 1.0, 1.0)
+        e.res_scale_main, e.res_scale_res, e.res_scale_out = float(s[0]), float(s[1]), float(s[2])
+        if sat_count is not None:
+            e.sat_count = sat_count.data_ptr()
+        if chan_absmax is not None:
+            e.chan_absmax = chan_absmax.data_ptr()
+        return e, keep
+
+    def gemm(self, x: torch.Tensor, out_kind: str = "i32", n_channels: Optional[int] = None, chan_scale=None,
+             bias=None, relu: bool = False, residual=None, res_scales=None, out: Optional[torch.Tensor] = None,
+             sat_count: Optional[torch.Tensor] = None, chan_absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Y = epilogue(X @ W^T).  x int8 [M, K] (CUDA, row stride may exceed K) -> [M, n_channels]."""
+        if x.dtype != torch.int8 or x.dim() != 2 or not x.is_cuda:
+            raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 2-D INT8 CUDA tensor")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        M, K = x.shape
+        n_channels = self.n_out_padded if n_channels is None else int(n_channels)
+        dt = {"i8": torch.int8, "i32": torch.int32, "f32": torch.float32}[out_kind]
+        if out is None:
+            out = torch.empty((M, n_channels), dtype=dt, device=x.device)
+        e, keep = self._epilogue(out_kind, n_channels, chan_scale, bias, relu, residual, res_scales, sat_count,
+                                 chan_absmax)
+        lay = OutLayout(max(M, 1), 0, 1, out.stride(0) if M else n_channels)
+        check(_lib.lib().accel_bsr_gemm_i8(self._h, _ptr(x), M, K, x.stride(0) if M else K, C.byref(e), _ptr(out),
+                                           C.byref(lay), _stream()))
+        return out
+
+    def conv(self, x: torch.Tensor, ksize: int, stride: int, pad: int, c_out: int, out_kind: str = "i8",
+             chan_scale=None, bias=None, relu: bool = False, residual=None, res_scales=None,
+             out: Optional[torch.Tensor] = None, sat_count: Optional[torch.Tensor] = None,
+             chan_absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Implicit-im2col BSR convolution.  x int8 NCHW (CUDA) -> [B, c_out, Ho, Wo]."""
+        if x.dtype != torch.int8 or x.dim() != 4 or not x.is_cuda:
+            raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 4-D INT8 CUDA tensor (NCHW)")
+        x = x.contiguous()
+        B, Cin, H, W = x.shape
+        Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+        dt = {"i8": torch.int8, "i32": torch.int32, "f32": torch.float32}[out_kind]
+        if out is None:
+            out = torch.empty((B, c_out, Ho, Wo), dtype=dt, device=x.device)
+        if residual is not None and tuple(residual.shape) != tuple(out.shape):
+            raise AcceleratorError(_lib.INVALID_CONFIG, "residual shape must equal the output shape")
+        e, keep = self._epilogue(out_kind, c_out, chan_scale, bias, relu, residual, res_scales, sat_count, chan_absmax)
+        g = ConvGeom(B, Cin, H, W, ksize, stride, pad)
+        P = max(Ho * Wo, 1)
+        lay = OutLayout(P, c_out * Ho * Wo, Ho * Wo, 1)
+        check(_lib.lib().accel_conv_bsr_i8(self._h, _ptr(x), C.byref(g), C.byref(e), _ptr(out), C.byref(lay), _stream()))
+        return out
+
+
+def _is_cuda(a) -> bool:
+    return isinstance(a, torch.Tensor) and a.is_cuda
+
+
+def _host(a) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+# ---------------------------------------------------------------------------------------- generic block sizes
+def bsr_gemm_generic(x: torch.Tensor, row_ptr, col_idx, blocks, n_out: int, orient: int = 0) -> torch.Tensor:
+    """CUDA-core BSR GEMM for any block size; orient 0 = Convention B, 1 = Convention A."""
+    dev = _require_cuda()
+    x = to_device(x, torch.int8, dev)
+    rp = to_device(row_ptr, torch.int32, dev)
+    ci = to_device(col_idx, torch.int32, dev)
+    blk = to_device(blocks, torch.int8, dev)
+    bh, bw = (int(blk.shape[1]), int(blk.shape[2])) if blk.dim() == 3 and blk.shape[0] else (BLOCK, BLOCK)
+    M, K = x.shape
+    out = torch.empty((M, n_out), dtype=torch.int32, device=dev)
+    check(_lib.lib().accel_bsr_gemm_generic(_ptr(x), M, K, x.stride(0) if M else K, _ptr(rp), _ptr(ci) if ci.numel() else None,
+                                            _ptr(blk) if blk.numel() else None, rp.numel() - 1, bh, bw, orient, n_out,
+                                            _ptr(out), n_out, _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------- packer / pruner (K4)
+def block_l1_i8(w: torch.Tensor, block: int = BLOCK) -> torch.Tensor:
+    rows, cols = w.shape
+    nbr, nbc = -(-rows // block), -(-cols // block)
+    out = torch.empty((nbr, nbc), dtype=torch.int32, device=w.device)
+    check(_lib.lib().accel_block_l1_i8(_ptr(w), rows, cols, w.stride(0), block, _ptr(out), _stream()))
+    return out
+
+
+def block_l2_f32(w: torch.Tensor, bh: int, bw: int) -> torch.Tensor:
+    rows, cols = w.shape
+    nbr, nbc = -(-rows // bh), -(-cols // bw)
+    out = torch.empty((nbr, nbc), dtype=torch.float32, device=w.device)
+    check(_lib.lib().accel_block_l2_f32(_ptr(w), rows, cols, w.stride(0), bh, bw, _ptr(out), _stream()))
+    return out
+
+
+def pack_bsr_i8(w: torch.Tensor, keep: torch.Tensor, block: int = BLOCK):
+    """dense int8 [rows, cols] + keep mask [nbr, nbc] -> (row_ptr i32, col_idx i32, blocks i8 [nnz,b,b])."""
+    rows, cols = w.shape
+    nbr, nbc = keep.shape
+    keep8 = keep.to(torch.uint8).contiguous()
+    row_ptr = torch.empty(nbr + 1, dtype=torch.int32, device=w.device)
+    slot = torch.empty(max(nbr * nbc, 1), dtype=torch.int32, device=w.device)
+    check(_lib.lib().accel_bsr_scan(_ptr(keep8), nbr, nbc, _ptr(row_ptr), _ptr(slot), _stream()))
+    nnz = int(row_ptr[-1].item())
+    col_idx = torch.empty(nnz, dtype=torch.int32, device=w.device)
+    blocks = torch.empty((nnz, block, block), dtype=torch.int8, device=w.device)
+    if nnz:
+        check(_lib.lib().accel_bsr_gather_i8(_ptr(w), rows, cols, w.stride(0), block, _ptr(slot), nbr, nbc,
+                                             _ptr(col_idx), _ptr(blocks), _stream()))
+    return row_ptr, col_idx, blocks
+
+
+def row_absmax_f32(w: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
+    check(_lib.lib().accel_row_absmax_f32(_ptr(w), w.shape[0], w.shape[1], w.stride(0), _ptr(out), _stream()))
+    return out
+
+
+def quantize_rows_f32(w: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
+    q = torch.empty(w.shape, dtype=torch.int8, device=w.device)
+    check(_lib.lib().accel_quantize_rows_f32(_ptr(w), w.shape[0], w.shape[1], w.stride(0), _ptr(scales), _ptr(q), _stream()))
+    return q
+
+
+# ---------------------------------------------------------------------------------------- epilogue pieces / pools
+def requant_i32_i8(acc: torch.Tensor, chan_scale: torch.Tensor, chan_dim: int, bias=None, relu=False,
+                   sat_count: Optional[torch.Tensor] = None) -> torch.Tensor:
+    acc = acc.contiguous()
+    n_chan = acc.shape[chan_dim]
+    n_outer = int(np.prod(acc.shape[:chan_dim])) if chan_dim else 1
+    n_inner = int(np.prod(acc.shape[chan_dim + 1:])) if chan_dim + 1 < acc.dim() else 1
+    out = torch.empty(acc.shape, dtype=torch.int8, device=acc.device)
+    check(_lib.lib().accel_requant_i32_i8(_ptr(acc), _ptr(out), n_outer, n_chan, n_inner, _ptr(chan_scale), _ptr(bias),
+                                          int(relu), _ptr(sat_count), _stream()))
+    return out
+
+
+def add_residual_i8(a: torch.Tensor, b: torch.Tensor, s_main: float, s_res: float, s_out: float) -> torch.Tensor:
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty_like(a)
+    check(_lib.lib().accel_add_residual_i8(_ptr(a), _ptr(b), _ptr(out), a.numel(), s_main, s_res, s_out, _stream()))
+    return out
+
+
+def maxpool_i8(x: torch.Tensor, pool: int, stride: int, pad: int = 0) -> torch.Tensor:
+    x = x.contiguous()
+    H, W = x.shape[-2:]
+    Ho, Wo = (H + 2 * pad - pool) // stride + 1, (W + 2 * pad - pool) // stride + 1
+    out = torch.empty(x.shape[:-2] + (Ho, Wo), dtype=torch.int8, device=x.device)
+    check(_lib.lib().accel_maxpool_i8(_ptr(x), _ptr(out), x.numel() // (H * W), H, W, pool, stride, pad, _stream()))
+    return out
+
+
+def avgpool_i8(x: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous()
+    H, W = x.shape[-2:]
+    out = torch.empty(x.shape[:-2], dtype=torch.int8, device=x.device)
+    check(_lib.lib().accel_avgpool_i8(_ptr(x), _ptr(out), x.numel() // (H * W), H, W, _stream()))
+    return out

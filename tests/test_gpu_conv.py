@@ -1,0 +1,66 @@
+"""GPU parity: implicit-im2col BSR convolution (C ABI) vs the oracle and the C++-golden fixtures. Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import bsr_oracle as O
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _plan(bsr):
+    from resnet_accel_b200.ops import BsrPlan
+    return BsrPlan(bsr["indptr"], bsr["indices"], bsr["data"], n_block_cols=bsr["num_block_cols"])
+
+
+def test_cpp_golden_conv_cases(golden):
+    """conv2d_int8_im2col outputs recorded from the reference C++ golden (INT32, with bias)."""
+    import torch
+    c = golden("cpp_golden_cases.npz")
+    for i in range(5):
+        x, w, bias, ref = c[f"conv{i}_x"], c[f"conv{i}_w"], c[f"conv{i}_bias"], c[f"conv{i}_out"]
+        k, s, p = c[f"conv{i}_geom"].tolist()
+        bsr = O.build_bsr_14x14_int8_direct(w.reshape(w.shape[0], -1))
+        out = _plan(bsr).conv(torch.from_numpy(x[None]).cuda(), k, s, p, w.shape[0], out_kind="i32",
+                              bias=bias).cpu().numpy()
+        assert np.array_equal(out[0], ref), i
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k,s,p,density", [
+    (2, 3, 20, 20, 16, 7, 2, 3, 1.0),      # ResNet stem shape family
+    (3, 16, 14, 14, 32, 3, 1, 1, 0.5),
+    (2, 32, 15, 13, 20, 3, 2, 1, 0.3),
+    (5, 64, 7, 7, 64, 3, 1, 1, 0.3),        # 49 positions per image: tiles straddle images
+    (2, 64, 9, 9, 128, 1, 2, 0, 0.5),       # 1x1 stride-2 downsample
+    (1, 1, 28, 28, 32, 3, 1, 0, 1.0),       # MNIST conv1
+    (2, 40, 12, 12, 30, 3, 1, 1, 0.0),      # no stored blocks at all
+])
+def test_conv_layer_vs_oracle(B, Cin, H, W, Cout, k, s, p, density):
+    import torch
+    rng = np.random.default_rng(B * 7 + Cin + Cout + k)
+    K = Cin * k * k
+    Wm = rng.integers(-128, 128, (Cout, K), dtype=np.int8)
+    nbr, nbc = -(-Cout // 14), -(-K // 14)
+    keep = rng.random((nbr, nbc)) < density
+    Wm = Wm * np.repeat(np.repeat(keep, 14, 0), 14, 1)[:Cout, :K].astype(np.int8)
+    bsr = O.build_bsr_14x14_int8_direct(Wm)
+    x = rng.integers(-128, 128, (B, Cin, H, W), dtype=np.int8)
+    bias = rng.integers(-1000, 1000, Cout, dtype=np.int32)
+    sf = rng.uniform(1e-4, 2e-3, Cout).astype(np.float32)
+    Ho, Wo = O.conv_out_hw(H, W, k, s, p)
+    res = rng.integers(-128, 128, (B, Cout, Ho, Wo), dtype=np.int8)
+    plan = _plan(bsr)
+    xd = torch.from_numpy(x).cuda()
+    # int8, relu, bias, residual
+    ref, sat = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, k, s, p, bias=bias,
+                                       relu=True, sf=sf, residual=res, res_scales=(0.05, 0.02, 0.04))
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out = plan.conv(xd, k, s, p, Cout, out_kind="i8", chan_scale=sf, bias=bias, relu=True,
+                    residual=torch.from_numpy(res).cuda(), res_scales=(0.05, 0.02, 0.04), sat_count=cnt).cpu().numpy()
+    assert out.shape == ref.shape
+    assert np.array_equal(out, ref)
+    assert int(cnt.item()) == sat
+    # int32 against the NumPy oracle (independent of the C port)
+    ref32, _ = O.conv2d_bsr_layer(x[:1], bsr["indptr"], bsr["indices"], bsr["data"], Cout, k, s, p, bias=bias)
+    out32 = plan.conv(xd[:1], k, s, p, Cout, out_kind="i32", bias=bias).cpu().numpy()
+    assert np.array_equal(out32, ref32)
