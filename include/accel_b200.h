@@ -44,7 +44,8 @@ enum {
   ACCEL_RELU = 1 << 0,      /* relu_int32 on the accumulator before scaling            */
   ACCEL_OUT_I8 = 1 << 1,    /* per-channel requant -> int8 (needs chan_scale)          */
   ACCEL_OUT_I32 = 1 << 2,   /* raw INT32 accumulator (+bias, +relu)                    */
-  ACCEL_OUT_F32 = 1 << 3    /* float32(acc) * chan_scale[c]  (de-quantised logits)     */
+  ACCEL_OUT_F32 = 1 << 3,   /* float32(acc) * chan_scale[c]  (de-quantised logits)     */
+  ACCEL_RELU_OUT = 1 << 4   /* relu_int8 on the final int8 value (after the residual add, golden_models.cpp:278) */
 };
 
 /* Where activation row m, output channel c lands:
@@ -138,9 +139,14 @@ ACCEL_API int accel_bsr_scan(const uint8_t* keep, int32_t nbr, int32_t nbc, int3
 /* gather kept blocks: col_idx [nnz], blocks [nnz, block, block] (zero padded at the edges) */
 ACCEL_API int accel_bsr_gather_i8(const int8_t* w, int64_t rows, int64_t cols, int64_t ld, int32_t block, const int32_t* slot,
                         int32_t nbr, int32_t nbc, int32_t* col_idx, int8_t* blocks, accel_stream_t stream);
+ACCEL_API int accel_bsr_gather_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, int32_t bh, int32_t bw,
+                                   const int32_t* slot, int32_t nbr, int32_t nbc, int32_t* col_idx, float* blocks,
+                                   accel_stream_t stream);
 /* per-row symmetric quantisation q = clip(rint(w / scale[row]), -128, 127) (quantize.py:71-98) */
 ACCEL_API int accel_quantize_rows_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, const float* scales, int8_t* q,
                             accel_stream_t stream);
+/* scales[i] = max(absmax[i] / 127, 1e-12) in float32 (quantize.py:86) */
+ACCEL_API int accel_symmetric_scales_f32(const float* absmax, int64_t n, float* scales, accel_stream_t stream);
 ACCEL_API int accel_row_absmax_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, float* absmax,
                          accel_stream_t stream);
 

@@ -16,7 +16,7 @@ OK, INIT_FAILED, TIMEOUT, DMA_ERROR, ILLEGAL_COMMAND, INVALID_CONFIG, MEMORY_ERR
 STATUS_NAMES = {0: "OK", -1: "INIT_FAILED", -2: "TIMEOUT", -3: "DMA_ERROR", -4: "ILLEGAL_COMMAND",
                 -5: "INVALID_CONFIG", -6: "MEMORY_ERROR", -7: "NOT_READY"}
 
-RELU, OUT_I8, OUT_I32, OUT_F32 = 1, 2, 4, 8
+RELU, OUT_I8, OUT_I32, OUT_F32, RELU_OUT = 1, 2, 4, 8, 16
 
 
 class AcceleratorError(RuntimeError):
@@ -62,7 +62,9 @@ SYMBOLS = {
     "accel_block_l2_f32": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32, _P, _P]),
     "accel_bsr_scan": (C.c_int, [_P, _I32, _I32, _P, _P, _P]),
     "accel_bsr_gather_i8": (C.c_int, [_P, _I64, _I64, _I64, _I32, _P, _I32, _I32, _P, _P, _P]),
+    "accel_bsr_gather_f32": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32, _P, _I32, _I32, _P, _P, _P]),
     "accel_quantize_rows_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P]),
+    "accel_symmetric_scales_f32": (C.c_int, [_P, _I64, _P, _P]),
     "accel_row_absmax_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
     "accel_requant_i32_i8": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I32, _P, _P]),
     "accel_add_residual_i8": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, _P]),

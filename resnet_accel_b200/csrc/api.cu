@@ -309,11 +309,29 @@ int accel_bsr_gather_i8(const int8_t* w, int64_t rows, int64_t cols, int64_t ld,
   return ACCEL_OK;
 }
 
+int accel_bsr_gather_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, int32_t bh, int32_t bw,
+                         const int32_t* slot, int32_t nbr, int32_t nbc, int32_t* col_idx, float* blocks,
+                         accel_stream_t stream) {
+  if (!nbr || !nbc) return ACCEL_OK;
+  accel::bsr_gather_f32_kernel<<<grid_for(static_cast<int64_t>(nbr) * nbc * 32, 256), 256, 0,
+                                 static_cast<cudaStream_t>(stream)>>>(w, rows, cols, ld, bh, bw, slot, nbr, nbc,
+                                                                      col_idx, blocks);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
 int accel_quantize_rows_f32(const float* w, int64_t rows, int64_t cols, int64_t ld, const float* scales, int8_t* q,
                             accel_stream_t stream) {
   if (rows <= 0 || cols <= 0) return ACCEL_OK;
   accel::quantize_rows_f32_kernel<<<grid_for(rows * cols, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, rows, cols, ld, scales, q);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_symmetric_scales_f32(const float* absmax, int64_t n, float* scales, accel_stream_t stream) {
+  if (n <= 0) return ACCEL_OK;
+  accel::symmetric_scales_f32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(absmax, n, scales);
   CU(cudaGetLastError());
   return ACCEL_OK;
 }

@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) bsr_tc_kernel(const __grid_consta
             const int z = __float2int_rn(__fdiv_rn(__fadd_rn(a, r), p.epi.res_scale_out));
             q8 = static_cast<int8_t>(min(127, max(-128, z)));
           }
+          if ((flags & ACCEL_RELU_OUT) && q8 < 0) q8 = 0;   // relu_int8, golden_models.cpp:278-283
           reinterpret_cast<int8_t*>(p.out)[o] = q8;
         }
       }
@@ -283,16 +284,30 @@ __global__ void __launch_bounds__(kThreads, 1) bsr_tc_kernel(const __grid_consta
       const uint8_t* wst = smem + kSmemW + ws_i * ((kWStageBytes + 127) / 128 * 128);
       const uint32_t x_addr = smem_u32(smem + kSmemX + xs * kXStageBytes);
       const uint32_t w_addr = smem_u32(wst);
-      const uint16_t* meta = reinterpret_cast<const uint16_t*>(wst + bi.n_ops * kBTileBytes);
-      if (lane == 0) {
-        for (int i = 0; i < bi.n_ops; ++i) {
-          const uint32_t mt = meta[i];
-          const uint32_t g = mt & 31u, win = mt >> 5;
-          const uint64_t adesc = smem_desc_kmajor(x_addr + win * kXTileStride, kXTileStride, 128);
-          const uint64_t bdesc = smem_desc_kmajor(w_addr + i * kBTileBytes, 256, 128);
-          mma_i8_ss(tmem_base + g * kTile, adesc, bdesc, idesc, (inited >> g) & 1u);
-          inited |= 1u << g;
+      // Lane-parallel decode: lane i owns op i of the batch.  Everything that depends on the op's
+      // metadata is computed once, in vector registers, for all ops at the same time; the issue loop
+      // below only broadcasts one packed word per op (shfl -> warp-uniform -> uniform registers).
+      const int n_ops = bi.n_ops;
+      uint32_t mt = 0;
+      if (lane < n_ops) mt = reinterpret_cast<const uint16_t*>(wst + n_ops * kBTileBytes)[lane];
+      const uint32_t g = mt & 31u, win = mt >> 5;
+      const uint32_t same = __match_any_sync(0xffffffffu, lane < n_ops ? g : 32u + lane);
+      const uint32_t acc = ((inited >> g) & 1u) | ((same & ((1u << lane) - 1u)) != 0u ? 1u : 0u);
+      // packed: bits 0..13 A start address >> 4, bits 14..22 D column, bit 23 accumulate
+      const uint32_t packed = (((x_addr + win * kXTileStride) >> 4) & 0x3FFFu) | ((g * kTile) << 14) | (acc << 23);
+      inited |= __reduce_or_sync(0xffffffffu, lane < n_ops ? (1u << g) : 0u);
+      const uint64_t adesc_hi = smem_desc_kmajor(0, kXTileStride, 128);
+      const uint64_t bdesc0 = smem_desc_kmajor(w_addr, 256, 128);
+#pragma unroll
+      for (int i = 0; i < kOpsPerBatch; ++i) {
+        if (i < n_ops) {                                   // warp-uniform
+          const uint32_t pk = __shfl_sync(0xffffffffu, packed, i);
+          const uint64_t adesc = adesc_hi | static_cast<uint64_t>(pk & 0x3FFFu);
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((i * kBTileBytes) >> 4);
+          if (elect_one()) mma_i8_ss(tmem_base + ((pk >> 14) & 0x1FFu), adesc, bdesc, idesc, (pk >> 23) & 1u);
         }
+      }
+      if (elect_one()) {
         mma_commit(&w_empty[ws_i]);
         if (bi.flags & 2) mma_commit(&x_empty[xs]);
         if (b == G.batch_end - 1) mma_commit(acc_full);

@@ -37,7 +37,7 @@ std::string build_plan(const int32_t* row_ptr, const int32_t* col_idx, int32_t n
   p->nbc = nbc;
   p->nnz = nnz;
   p->n_chunks = (nbc + kChunkTiles - 1) / kChunkTiles;
-  int32_t want = p->group_rows > 0 ? std::min(p->group_rows, kMaxGroupRows) : kMaxGroupRows;
+  int32_t want = p->group_rows > 0 ? std::min(p->group_rows, kMaxGroupRows) : kDefaultGroupRows;
   const int32_t n_groups = nbr > 0 ? (nbr + want - 1) / want : 0;
   const int32_t rows_per = n_groups ? (nbr + n_groups - 1) / n_groups : 0;  // balanced split
   p->group_rows = rows_per;
@@ -80,35 +80,49 @@ std::string build_plan(const int32_t* row_ptr, const int32_t* col_idx, int32_t n
           p->op_meta_off[p->op_meta_off.size() - ops_in_batch + i] = static_cast<uint32_t>(base + tiles + 2 * i);
         blob_bytes = base + tiles + kBatchMetaBytes;
       };
-      bool any = false;
+      // Per block-row op lists of this chunk, then emitted round-robin across block-rows: consecutive
+      // tcgen05.mma instructions then target different TMEM accumulators, so the small N=16 MMAs do not
+      // serialise on the accumulate dependency of a single block-row.
+      struct PendingOp { OpSrc src; int32_t win; };
+      std::vector<std::vector<PendingOp>> per_row(G.n_rows);
       for (int g = 0; g < G.n_rows; ++g) {
         const int32_t end = row_ptr[G.br0 + g + 1];
         int32_t j = cursor[g];
         while (j < end && col_idx[j] < t_hi) {
+          const int32_t t = col_idx[j] - t_lo;  // tile inside the chunk
+          PendingOp op{{-1, -1}, 0};
+          if (j + 1 < end && col_idx[j + 1] == col_idx[j] + 1 && col_idx[j + 1] < t_hi) {
+            op.src.blk_lo = j; op.src.blk_hi = j + 1; op.win = t; j += 2;   // adjacent pair: one MMA
+          } else if (t + 1 < kChunkTiles) {
+            op.src.blk_lo = j; op.win = t; j += 1;                          // lone block in K slot 0
+          } else {
+            op.src.blk_hi = j; op.win = t - 1; j += 1;                      // last tile of the chunk: K slot 1
+          }
+          per_row[g].push_back(op);
+        }
+        cursor[g] = j;
+      }
+      bool any = false;
+      for (size_t depth = 0;; ++depth) {
+        bool found = false;
+        for (int g = 0; g < G.n_rows; ++g) {
+          if (depth >= per_row[g].size()) continue;
+          found = true;
           if (!any || ops_in_batch == kOpsPerBatch) {
             if (any) close_batch();
             open_batch();
             any = true;
           }
-          const int32_t t = col_idx[j] - t_lo;  // tile inside the chunk
-          OpSrc src{-1, -1};
-          int32_t win;
-          if (j + 1 < end && col_idx[j + 1] == col_idx[j] + 1 && col_idx[j + 1] < t_hi) {
-            src.blk_lo = j; src.blk_hi = j + 1; win = t; j += 2;          // adjacent pair: one MMA
-          } else if (t + 1 < kChunkTiles) {
-            src.blk_lo = j; win = t; j += 1;                              // lone block in slot 0
-          } else {
-            src.blk_hi = j; win = t - 1; j += 1;                          // last tile of the chunk: slot 1
-          }
+          const PendingOp& op = per_row[g][depth];
           const BatchInfo& b = p->batches.back();
-          p->op_src.push_back(src);
-          p->op_meta.push_back(static_cast<uint16_t>((g & 31) | (win << 5)));
+          p->op_src.push_back(op.src);
+          p->op_meta.push_back(static_cast<uint16_t>((g & 31) | (op.win << 5)));
           p->op_blob_off.push_back(static_cast<uint32_t>(static_cast<size_t>(b.blob_off16) * 16 +
                                                          static_cast<size_t>(ops_in_batch) * kBTileBytes));
           p->op_meta_off.push_back(0);
           ++ops_in_batch;
         }
-        cursor[g] = j;
+        if (!found) break;
       }
       if (any) {
         close_batch();

@@ -18,6 +18,7 @@ constexpr int kBlock = 14;           // reference block size (export_bsr_14x14.p
 constexpr int kTile = 16;            // padded K slot / padded block-row height
 constexpr int kChunkTiles = 16;      // K tiles staged per activation stage
 constexpr int kMaxGroupRows = 32;    // block-rows per CTA (32 x 16 = 512 TMEM columns)
+constexpr int kDefaultGroupRows = 16;  // 256 TMEM columns: two CTAs can share an SM
 constexpr int kOpsPerBatch = 16;     // B tiles per weight stage
 constexpr int kBTileBytes = 512;     // 16 rows x 32 bytes
 constexpr int kBatchMetaBytes = 32;  // kOpsPerBatch x u16

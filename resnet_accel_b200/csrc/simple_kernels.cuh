@@ -177,6 +177,24 @@ __global__ void bsr_gather_i8_kernel(const int8_t* __restrict__ w, int64_t rows,
   }
 }
 
+__global__ void bsr_gather_f32_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld, int32_t bh,
+                                      int32_t bw, const int32_t* __restrict__ slot, int32_t nbr, int32_t nbc,
+                                      int32_t* __restrict__ col_idx, float* __restrict__ blocks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t blk = warp0; blk < static_cast<int64_t>(nbr) * nbc; blk += nwarps) {
+    const int32_t s = slot[blk];
+    if (s < 0) continue;
+    const int64_t r0 = (blk / nbc) * bh, c0 = (blk % nbc) * bw;
+    for (int e = lane; e < bh * bw; e += 32) {
+      const int64_t r = r0 + e / bw, c = c0 + e % bw;
+      blocks[static_cast<int64_t>(s) * bh * bw + e] = (r < rows && c < cols) ? w[r * ld + c] : 0.f;
+    }
+    if (lane == 0) col_idx[s] = static_cast<int32_t>(blk % nbc);
+  }
+}
+
 // ------------------------------------------------------------------ quantiser (quantize.py:71-98)
 __global__ void row_absmax_f32_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld,
                                       float* __restrict__ absmax) {
@@ -189,6 +207,11 @@ __global__ void row_absmax_f32_kernel(const float* __restrict__ w, int64_t rows,
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) absmax[r] = m;
   }
+}
+__global__ void symmetric_scales_f32_kernel(const float* __restrict__ absmax, int64_t n, float* __restrict__ scales) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    scales[i] = fmaxf(__fdiv_rn(absmax[i], 127.0f), 1e-12f);
 }
 __global__ void quantize_rows_f32_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld,
                                          const float* __restrict__ scales, int8_t* __restrict__ q) {

@@ -1,0 +1,250 @@
+"""Layer objects, layer tables and the network runner for the BSR-INT8 path.
+
+* ``ConvSpec`` / ``resnet18_specs`` - the reference's ResNet-18 layer table
+  (hw/sim/cpp/src/resnet_inference.cpp:61-127) with the three 1x1 downsample convolutions the
+  reference only flags (``export_resnet18_bsr.py:72,79,86``) written out as layers of their own,
+  plus the 3x3/2 stem max-pool the table omits.
+* ``synthetic_conv_weights`` - the reference's synthetic-weight recipe (He init of
+  ``create_conv_weights`` sw/exporters/export_conv.py:17-40, block mask of ``create_sparse_mask``
+  with one seed per layer as ``BlockSparsePruner._create_masks`` train_resnet18.py:163-184,
+  per-channel INT8 quantisation quantize.py:71-98) with 14x14 blocks throughout.
+* ``BsrConv`` / ``BsrLinear`` / ``BsrNetwork`` - device-resident layers that call the C ABI, and a
+  runner that replays the whole network as one CUDA graph (``ResNetInference::run_inference``
+  resnet_inference.hpp:180-271 is the reference-side shape of that API).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import exporters, ops
+from .host import channel_scale_factors
+
+
+@dataclass
+class ConvSpec:
+    name: str
+    c_in: int
+    c_out: int
+    h: int            # input height
+    w: int            # input width
+    k: int
+    stride: int
+    pad: int
+    relu: bool = True           # ReLU on the INT32 accumulator (no residual) / on the int8 sum (residual)
+    residual: Optional[str] = None   # name of the tensor added after requant ("input of the block" or a downsample)
+    src: Optional[str] = None        # input tensor name (default: previous layer's output)
+    kind: str = "conv"               # conv | maxpool | avgpool | fc
+
+    @property
+    def h_out(self) -> int:
+        return (self.h + 2 * self.pad - self.k) // self.stride + 1
+
+    @property
+    def w_out(self) -> int:
+        return (self.w + 2 * self.pad - self.k) // self.stride + 1
+
+    @property
+    def K(self) -> int:
+        return self.c_in * self.k * self.k
+
+
+def resnet18_specs(image: int = 224, num_classes: int = 1000) -> List[ConvSpec]:
+    s: List[ConvSpec] = []
+    h = image
+    s.append(ConvSpec("conv1", 3, 64, h, h, 7, 2, 3))
+    h = s[-1].h_out
+    s.append(ConvSpec("maxpool", 64, 64, h, h, 3, 2, 1, kind="maxpool"))
+    h = s[-1].h_out
+    c = 64
+    for stage, width in enumerate((64, 128, 256, 512), start=1):
+        for blk in range(2):
+            stride = 2 if (stage > 1 and blk == 0) else 1
+            block_in = s[-1].name
+            pre = f"layer{stage}.{blk}"
+            s.append(ConvSpec(f"{pre}.conv1", c, width, h, h, 3, stride, 1, src=block_in))
+            h_out = s[-1].h_out
+            ident = block_in
+            if stride != 1 or c != width:
+                s.append(ConvSpec(f"{pre}.downsample", c, width, h, h, 1, stride, 0, relu=False, src=block_in))
+                ident = s[-1].name
+            s.append(ConvSpec(f"{pre}.conv2", width, width, h_out, h_out, 3, 1, 1, residual=ident,
+                              src=f"{pre}.conv1"))
+            h, c = h_out, width
+    s.append(ConvSpec("avgpool", c, c, h, h, h, 1, 0, kind="avgpool"))
+    s.append(ConvSpec("fc", c, num_classes, 1, 1, 1, 1, 0, relu=False, kind="fc"))
+    return s
+
+
+def resnet50_specs(image: int = 224, num_classes: int = 1000) -> List[ConvSpec]:
+    """torchvision resnet50 (v1.5: stride on the 3x3), SURVEY.md A.9."""
+    s: List[ConvSpec] = []
+    h = image
+    s.append(ConvSpec("conv1", 3, 64, h, h, 7, 2, 3))
+    h = s[-1].h_out
+    s.append(ConvSpec("maxpool", 64, 64, h, h, 3, 2, 1, kind="maxpool"))
+    h = s[-1].h_out
+    c = 64
+    for stage, (width, n) in enumerate(((64, 3), (128, 4), (256, 6), (512, 3)), start=1):
+        for blk in range(n):
+            stride = 2 if (stage > 1 and blk == 0) else 1
+            block_in = s[-1].name
+            pre = f"layer{stage}.{blk}"
+            s.append(ConvSpec(f"{pre}.conv1", c, width, h, h, 1, 1, 0, src=block_in))
+            s.append(ConvSpec(f"{pre}.conv2", width, width, h, h, 3, stride, 1))
+            h_out = s[-1].h_out
+            ident = block_in
+            if stride != 1 or c != 4 * width:
+                s.append(ConvSpec(f"{pre}.downsample", c, 4 * width, h, h, 1, stride, 0, relu=False, src=block_in))
+                ident = s[-1].name
+            s.append(ConvSpec(f"{pre}.conv3", width, 4 * width, h_out, h_out, 1, 1, 0, residual=ident,
+                              src=f"{pre}.conv2"))
+            h, c = h_out, 4 * width
+    s.append(ConvSpec("avgpool", c, c, h, h, h, 1, 0, kind="avgpool"))
+    s.append(ConvSpec("fc", c, num_classes, 1, 1, 1, 1, 0, relu=False, kind="fc"))
+    return s
+
+
+# Synthetic quantisation constants of SURVEY.md 8d: fixed activation scales so that requant saturates sometimes.
+S_ACT_IN = 0.02
+S_ACT_OUT = 0.05
+
+
+def synthetic_conv_weights(spec: ConvSpec, sparsity_pct: float, layer_idx: int, bias_range: int = 0) -> Dict:
+    """FP32 He weights -> 14x14 block mask -> per-channel INT8 (host RNG streams as the reference)."""
+    seed = 42 + layer_idx
+    np.random.seed(seed)
+    scale = np.sqrt(2.0 / (spec.c_in * spec.k * spec.k))
+    w4 = np.random.randn(spec.c_out, spec.c_in, spec.k, spec.k).astype(np.float32) * scale
+    w2 = w4.reshape(spec.c_out, -1)
+    mask = exporters.create_sparse_mask(w2.shape, sparsity_pct, block_size=exporters.BLOCK_SIZE, seed=seed)
+    w2 = (w2 * mask).astype(np.float32)
+    bias = None
+    if bias_range:
+        bias = np.random.default_rng(seed).integers(-bias_range, bias_range + 1, spec.c_out).astype(np.int32)
+    return {"w2": w2, "bias": bias}
+
+
+class BsrLayer:
+    """One BSR weight matrix on the device + its epilogue constants."""
+
+    def __init__(self, spec: ConvSpec, w_fp32_2d=None, *, bsr: Optional[Dict] = None, w_scales=None, bias=None,
+                 s_in: float = S_ACT_IN, s_out: float = S_ACT_OUT, group_rows: int = 0):
+        self.spec = spec
+        if bsr is None:
+            q, w_scales = exporters.quantize_symmetric_per_channel(w_fp32_2d, device=True)
+            bsr = exporters.build_bsr_14x14_int8_direct(q, device=True)
+        self.bsr = bsr
+        self.plan = ops.BsrPlan(bsr["indptr"], bsr["indices"], bsr["data"], n_block_cols=bsr["num_block_cols"],
+                                group_rows=group_rows)
+        ws = w_scales.cpu().numpy() if isinstance(w_scales, torch.Tensor) else np.asarray(w_scales, np.float32)
+        self.w_scales = ws.astype(np.float32)
+        self.s_in, self.s_out = float(s_in), float(s_out)
+        self.sf = torch.from_numpy(channel_scale_factors(s_in, self.w_scales, s_out)).cuda()
+        self.bias = None if bias is None else torch.as_tensor(bias, dtype=torch.int32).cuda()
+
+    # algorithmic work of one call
+    def useful_ops(self, M: int) -> int:
+        return 2 * M * self.plan.num_blocks * 196
+
+    def weight_bytes(self) -> int:
+        return self.plan.num_blocks * 200 + 4 * (self.plan.n_block_rows + 1) + 4 * self.spec.c_out
+
+
+class BsrNetwork:
+    """A chain of BSR conv / pool / fc layers on one GPU.  ``forward`` enqueues every layer on the current
+    stream; ``capture`` records it once into a CUDA graph for replay (launch-latency-bound tails)."""
+
+    def __init__(self, specs: List[ConvSpec], sparsity_pct: float, batch: int, bias_range: int = 0,
+                 layers: Optional[Dict[str, BsrLayer]] = None):
+        self.specs, self.batch, self.sparsity_pct = specs, batch, sparsity_pct
+        self.layers: Dict[str, BsrLayer] = layers or {}
+        if not self.layers:
+            idx = 0
+            for sp in specs:
+                if sp.kind in ("conv", "fc"):
+                    syn = synthetic_conv_weights(sp, sparsity_pct, idx, bias_range)
+                    self.layers[sp.name] = BsrLayer(sp, syn["w2"], bias=syn["bias"],
+                                                    group_rows=(8 if sp.kind == "fc" else 0))
+                    idx += 1
+        self.buffers: Dict[str, torch.Tensor] = {}
+        self.sat = torch.zeros(1, dtype=torch.int64, device="cuda")
+        for sp in specs:
+            if sp.kind == "fc":
+                self.buffers[sp.name] = torch.empty((batch, sp.c_out), dtype=torch.int32, device="cuda")
+            elif sp.kind == "avgpool":
+                self.buffers[sp.name] = torch.empty((batch, sp.c_out), dtype=torch.int8, device="cuda")
+            else:
+                self.buffers[sp.name] = torch.empty((batch, sp.c_out, sp.h_out, sp.w_out), dtype=torch.int8, device="cuda")
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.static_in: Optional[torch.Tensor] = None
+        self.n_launches = sum(1 for _ in specs)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        prev = "input"
+        t: Dict[str, torch.Tensor] = {"input": x}
+        t.update(self.buffers)
+        for sp in self.specs:
+            src = t[sp.src] if sp.src else t[prev]
+            out = self.buffers[sp.name]
+            if sp.kind == "conv":
+                L = self.layers[sp.name]
+                if sp.residual:
+                    # conv -> requant -> + identity -> ReLU on the int8 sum
+                    L.plan.conv(src, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=L.sf, bias=L.bias, relu=False,
+                                residual=t[sp.residual], res_scales=(L.s_out, S_ACT_OUT, S_ACT_OUT), out=out,
+                                sat_count=self.sat, relu_out=True)
+                else:
+                    L.plan.conv(src, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=L.sf, bias=L.bias,
+                                relu=sp.relu, out=out, sat_count=self.sat)
+            elif sp.kind == "maxpool":
+                ops.maxpool_i8(src, sp.k, sp.stride, sp.pad, out=out)
+            elif sp.kind == "avgpool":
+                ops.avgpool_i8(src, out=out)
+            elif sp.kind == "fc":
+                L = self.layers[sp.name]
+                L.plan.gemm(src.reshape(src.shape[0], -1), "i32", n_channels=sp.c_out, bias=L.bias, out=out)
+            prev = sp.name
+        return self.buffers[self.specs[-1].name]
+
+    def capture(self, x: torch.Tensor) -> None:
+        self.static_in = x.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.forward(self.static_in)          # warm-up (also sets the kernels' smem attributes)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward(self.static_in)
+        self.graph = g
+
+    def replay(self, x: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x is not None:
+            self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.buffers[self.specs[-1].name]
+
+    # ------------------------------------------------------------------ accounting
+    def work(self) -> Dict:
+        ops_total, bytes_total, per_layer = 0, 0, []
+        B = self.batch
+        for sp in self.specs:
+            in_bytes = B * sp.c_in * sp.h * sp.w
+            if sp.kind in ("conv", "fc"):
+                L = self.layers[sp.name]
+                M = B * sp.h_out * sp.w_out
+                o = L.useful_ops(M)
+                out_bytes = M * sp.c_out * (4 if sp.kind == "fc" else 1)
+                b = in_bytes + L.weight_bytes() + out_bytes + (M * sp.c_out if sp.residual else 0)
+            else:
+                o = 0
+                b = in_bytes + B * sp.c_out * (sp.h_out * sp.w_out if sp.kind == "maxpool" else 1)
+            ops_total += o
+            bytes_total += b
+            per_layer.append({"name": sp.name, "ops": o, "bytes": b})
+        return {"ops": ops_total, "bytes": bytes_total, "layers": per_layer}

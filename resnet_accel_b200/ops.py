@@ -97,9 +97,11 @@ class BsrPlan:
 
     # ------------------------------------------------------------------------------------
     def _epilogue(self, out_kind: str, n_channels: int, chan_scale, bias, relu: bool, residual, res_scales,
-                  sat_count, chan_absmax) -> Tuple[Epilogue, list]:
+                  sat_count, chan_absmax, relu_out: bool = False) -> Tuple[Epilogue, list]:
         keep = []
         flags = {"i8": _lib.OUT_I8, "i32": _lib.OUT_I32, "f32": _lib.OUT_F32}[out_kind] | (_lib.RELU if relu else 0)
+        if relu_out:
+            flags |= _lib.RELU_OUT
         e = Epilogue()
         e.flags, e.n_channels = flags, int(n_channels)
         for name, val, dt in (("chan_scale", chan_scale, torch.float32), ("bias", bias, torch.int32),
@@ -120,7 +122,8 @@ class BsrPlan:
 
     def gemm(self, x: torch.Tensor, out_kind: str = "i32", n_channels: Optional[int] = None, chan_scale=None,
              bias=None, relu: bool = False, residual=None, res_scales=None, out: Optional[torch.Tensor] = None,
-             sat_count: Optional[torch.Tensor] = None, chan_absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+             sat_count: Optional[torch.Tensor] = None, chan_absmax: Optional[torch.Tensor] = None,
+             relu_out: bool = False) -> torch.Tensor:
         """Y = epilogue(X @ W^T).  x int8 [M, K] (CUDA, row stride may exceed K) -> [M, n_channels]."""
         if x.dtype != torch.int8 or x.dim() != 2 or not x.is_cuda:
             raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 2-D INT8 CUDA tensor")
@@ -132,7 +135,7 @@ class BsrPlan:
         if out is None:
             out = torch.empty((M, n_channels), dtype=dt, device=x.device)
         e, keep = self._epilogue(out_kind, n_channels, chan_scale, bias, relu, residual, res_scales, sat_count,
-                                 chan_absmax)
+                                 chan_absmax, relu_out)
         lay = OutLayout(max(M, 1), 0, 1, out.stride(0) if M else n_channels)
         check(_lib.lib().accel_bsr_gemm_i8(self._h, _ptr(x), M, K, x.stride(0) if M else K, C.byref(e), _ptr(out),
                                            C.byref(lay), _stream()))
@@ -141,7 +144,7 @@ class BsrPlan:
     def conv(self, x: torch.Tensor, ksize: int, stride: int, pad: int, c_out: int, out_kind: str = "i8",
              chan_scale=None, bias=None, relu: bool = False, residual=None, res_scales=None,
              out: Optional[torch.Tensor] = None, sat_count: Optional[torch.Tensor] = None,
-             chan_absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+             chan_absmax: Optional[torch.Tensor] = None, relu_out: bool = False) -> torch.Tensor:
         """Implicit-im2col BSR convolution.  x int8 NCHW (CUDA) -> [B, c_out, Ho, Wo]."""
         if x.dtype != torch.int8 or x.dim() != 4 or not x.is_cuda:
             raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 4-D INT8 CUDA tensor (NCHW)")
@@ -153,7 +156,8 @@ class BsrPlan:
             out = torch.empty((B, c_out, Ho, Wo), dtype=dt, device=x.device)
         if residual is not None and tuple(residual.shape) != tuple(out.shape):
             raise AcceleratorError(_lib.INVALID_CONFIG, "residual shape must equal the output shape")
-        e, keep = self._epilogue(out_kind, c_out, chan_scale, bias, relu, residual, res_scales, sat_count, chan_absmax)
+        e, keep = self._epilogue(out_kind, c_out, chan_scale, bias, relu, residual, res_scales, sat_count, chan_absmax,
+                                 relu_out)
         g = ConvGeom(B, Cin, H, W, ksize, stride, pad)
         P = max(Ho * Wo, 1)
         lay = OutLayout(P, c_out * Ho * Wo, Ho * Wo, 1)
@@ -222,9 +226,32 @@ def pack_bsr_i8(w: torch.Tensor, keep: torch.Tensor, block: int = BLOCK):
     return row_ptr, col_idx, blocks
 
 
+def pack_bsr_f32(w: torch.Tensor, keep: torch.Tensor, bh: int, bw: int):
+    """float32 flavour of :func:`pack_bsr_i8` (generic block shape)."""
+    rows, cols = w.shape
+    nbr, nbc = keep.shape
+    keep8 = keep.to(torch.uint8).contiguous()
+    row_ptr = torch.empty(nbr + 1, dtype=torch.int32, device=w.device)
+    slot = torch.empty(max(nbr * nbc, 1), dtype=torch.int32, device=w.device)
+    check(_lib.lib().accel_bsr_scan(_ptr(keep8), nbr, nbc, _ptr(row_ptr), _ptr(slot), _stream()))
+    nnz = int(row_ptr[-1].item())
+    col_idx = torch.empty(nnz, dtype=torch.int32, device=w.device)
+    blocks = torch.empty((nnz, bh, bw), dtype=torch.float32, device=w.device)
+    if nnz:
+        check(_lib.lib().accel_bsr_gather_f32(_ptr(w), rows, cols, w.stride(0), bh, bw, _ptr(slot), nbr, nbc,
+                                              _ptr(col_idx), _ptr(blocks), _stream()))
+    return row_ptr, col_idx, blocks
+
+
 def row_absmax_f32(w: torch.Tensor) -> torch.Tensor:
     out = torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
     check(_lib.lib().accel_row_absmax_f32(_ptr(w), w.shape[0], w.shape[1], w.stride(0), _ptr(out), _stream()))
+    return out
+
+
+def symmetric_scales_f32(absmax: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(absmax)
+    check(_lib.lib().accel_symmetric_scales_f32(_ptr(absmax), absmax.numel(), _ptr(out), _stream()))
     return out
 
 
@@ -254,18 +281,20 @@ def add_residual_i8(a: torch.Tensor, b: torch.Tensor, s_main: float, s_res: floa
     return out
 
 
-def maxpool_i8(x: torch.Tensor, pool: int, stride: int, pad: int = 0) -> torch.Tensor:
+def maxpool_i8(x: torch.Tensor, pool: int, stride: int, pad: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     x = x.contiguous()
     H, W = x.shape[-2:]
     Ho, Wo = (H + 2 * pad - pool) // stride + 1, (W + 2 * pad - pool) // stride + 1
-    out = torch.empty(x.shape[:-2] + (Ho, Wo), dtype=torch.int8, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape[:-2] + (Ho, Wo), dtype=torch.int8, device=x.device)
     check(_lib.lib().accel_maxpool_i8(_ptr(x), _ptr(out), x.numel() // (H * W), H, W, pool, stride, pad, _stream()))
     return out
 
 
-def avgpool_i8(x: torch.Tensor) -> torch.Tensor:
+def avgpool_i8(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     x = x.contiguous()
     H, W = x.shape[-2:]
-    out = torch.empty(x.shape[:-2], dtype=torch.int8, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape[:-2], dtype=torch.int8, device=x.device)
     check(_lib.lib().accel_avgpool_i8(_ptr(x), _ptr(out), x.numel() // (H * W), H, W, _stream()))
     return out
