@@ -48,12 +48,13 @@ int grid_for(int64_t work_items, int threads, int per_sm = 8) {
 
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
+constexpr int kMaxHaloBytes = 28 * 1024;   // per producer half; keeps two CTAs (2 x ~106 KB) on one SM
 void set_kernel_attrs() {
   g_attr_err = cudaFuncSetAttribute(accel::bsr_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    accel::kSmemBytes);
+                                    accel::kSmemHalo);
   if (g_attr_err == cudaSuccess)
     g_attr_err = cudaFuncSetAttribute(accel::bsr_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      accel::kSmemBytes);
+                                      accel::kSmemHalo + 2 * kMaxHaloBytes);
 }
 
 int check_epilogue(const accel_epilogue* epi, const accel_out_layout* lay, const void* out, int32_t max_channels) {
@@ -84,9 +85,9 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, bool conv, cudaStream_
   prm.groups = reinterpret_cast<const accel::GroupInfo*>(P->ws_dev + P->off_groups);
   prm.n_groups = n_groups;
   if (conv)
-    accel::bsr_tc_kernel<true><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemBytes, st>>>(prm);
+    accel::bsr_tc_kernel<true><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemHalo + 2 * prm.halo_bytes, st>>>(prm);
   else
-    accel::bsr_tc_kernel<false><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemBytes, st>>>(prm);
+    accel::bsr_tc_kernel<false><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemHalo, st>>>(prm);
   CU(cudaGetLastError());
   return ACCEL_OK;
 }
@@ -176,8 +177,8 @@ int64_t accel_plan_export_ops(const accel_plan* plan, int32_t* rec, int64_t cap)
       for (int i = 0; i < P.batches[b].n_ops; ++i, ++op) {
         if (rec && op < cap) {
           int32_t* r = rec + op * 8;
-          r[0] = static_cast<int32_t>(gi); r[1] = G.br0; r[2] = P.op_meta[op] & 31; r[3] = P.batches[b].chunk;
-          r[4] = P.op_meta[op] >> 5; r[5] = P.op_src[op].blk_lo; r[6] = P.op_src[op].blk_hi; r[7] = b;
+          r[0] = static_cast<int32_t>(gi); r[1] = G.br0; r[2] = P.op_meta[op] & 15; r[3] = P.batches[b].chunk;
+          r[4] = P.op_meta[op] >> 4; r[5] = P.op_src[op].blk_lo; r[6] = P.op_src[op].blk_hi; r[7] = b;
         }
       }
   }
@@ -225,6 +226,15 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
   prm.x = input_nchw; prm.M = static_cast<int64_t>(g->batch) * prm.Ho * prm.Wo; prm.K = static_cast<int32_t>(K);
   prm.C = g->c_in; prm.H = g->h; prm.W = g->w; prm.ksz = g->ksize; prm.stride = g->stride; prm.pad = g->pad;
   prm.epi = *epi; prm.out = out; prm.lay = *layout;
+  if (g->ksize == 3 && g->pad <= 3) {
+    // shared-memory staging of the input rows one 14-channel stage needs: [14][halo_rows][3][pitch]
+    const int rows = (accel::kTileM - 1) / prm.Wo + 2;
+    const int pitch = ((g->w + 3) / 4) * 4 + 8;             // 4 zero bytes left, >= 4 right (pad <= 3)
+    const int bytes = ((14 * rows * 3 * pitch + 127) / 128) * 128;
+    if (rows <= accel::kMaxHaloRows && bytes <= kMaxHaloBytes) {   // else: the general gather path
+      prm.halo_rows = rows; prm.halo_pitch = pitch; prm.halo_bytes = bytes;
+    }
+  }
   return launch_tc(&plan->p, prm, true, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,23 +1,29 @@
-// Block-sparse INT8 GEMM / implicit-im2col convolution on tcgen05 (sm_100a).
+// Block-sparse INT8 GEMM / implicit-im2col convolution on tcgen05 (sm_100a) - activation-stationary design.
 //
 //   Y[m, br*14+h] = sum over stored blocks (br, bc) of  sum_w X[m, bc*14+w] * blk[h][w]
 //   (sw/golden/golden_fc1_test.py:78-106), then the fused epilogue of SURVEY.md A.3.
 //
-// One CTA owns 128 activation rows x one group of block-rows (<= 32 -> 512 TMEM columns, one
-// 16-column INT32 accumulator per block-row).  Every stored block is a true dense contraction:
-// it is issued as (half of) a tcgen05.mma.kind::i8 with M=128 (activation rows), N=16 (the
-// block-row, 14 channels + 2 zero rows), K=32 bytes (two 16-byte K slots = two adjacent K tiles).
+// One CTA owns 128 activation rows (= 128 TMEM lanes) x one group of <= 11 block-rows.  Its 256 TMEM
+// columns hold BOTH operands of the hot loop:
+//     columns [0, 176)        one 16-column INT32 accumulator per block-row (zeroed up front)
+//     columns [176, 248)      two activation stages of 9 K-tiles (16 bytes = 4 columns per tile, 14 data + 2 zero)
+// so two CTAs share an SM and overlap each other's prologue / epilogue.  Every stored block is a true
+// dense contraction, issued as (half of) one  tcgen05.mma.kind::i8  with A = activations FROM TMEM
+// (M=128), B = the block-row's 16x32 weight tile from shared memory (N=16, K=32 = two adjacent K tiles).
+// Measured on B200 (tools/probe): an SS-mode N=16 MMA is bound by the 4 KB shared-memory read of A
+// (~45 cycles); with A in TMEM and several issuing warps the same MMA sustains ~16 cycles.
 //
-// Warp roles (192 threads):
-//   warps 0-3  activation producers: gather a [128 x 16 K-tiles] stage (GEMM rows or im2col
-//              patches, reference K order) into the canonical K-major core-matrix layout,
-//              re-striding 14 -> 16; afterwards the same four warps run the epilogue, one TMEM
-//              lane (= activation row) per thread.
-//   warp 4     MMA issuer (one elected lane) + TMEM allocation.
-//   warp 5     weight loader: cp.async.bulk of pre-packed B-tile batches into a ring.
-// Pipelines are mbarrier rings: x_full/x_empty (producers <-> MMA), w_full/w_empty (loader <-> MMA),
-// acc_full (MMA -> epilogue).  tcgen05.commit releases the rings.
+// Warp roles:
+//   warps 0-7   activation producers, thread = activation row (TMEM lane), two halves of 4 warps that own
+//               alternating stages.  GEMM: re-stride 14 -> 16 from the row-major activations.
+//               Conv: implicit im2col in the reference K order (c, kh, kw) - the input rows a stage needs
+//               are staged once in shared memory (coalesced, zero padded), then each thread walks its
+//               patch with a compile-time (3x3) or incremental (general) pattern and writes 16-byte
+//               tiles straight into TMEM with tcgen05.st.  Afterwards the same warps run the epilogue.
+//   warps 8..   MMA issuers (kIssuers warps, ops dealt round-robin) + TMEM allocation.
+//   last warp   weight loader: cp.async.bulk of pre-packed B-tile batches into a ring.
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 
@@ -27,17 +33,22 @@
 
 namespace accel {
 
+constexpr int kTileM = 128;
+constexpr int kProducerWarps = 8;
+constexpr int kIssuers = 4;
+constexpr int kThreads = (kProducerWarps + kIssuers + 1) * 32;
 constexpr int kXStages = 2;
 constexpr int kWStages = 3;
-constexpr int kTileM = 128;
-constexpr int kXTileStride = kTileM * kTile + 16;             // 2064: +16 B skews banks between K tiles
-constexpr int kXStageBytes = kChunkTiles * kXTileStride;      // 33024
-constexpr int kWStageBytes = kBatchBytes;                     // 8224
-constexpr int kSmemX = 0;
-constexpr int kSmemW = kSmemX + kXStages * kXStageBytes;
-constexpr int kSmemBar = kSmemW + kWStages * ((kWStageBytes + 127) / 128 * 128);
-constexpr int kSmemBytes = kSmemBar + 256;
-constexpr int kThreads = 192;
+constexpr int kAccCols = kMaxGroupRows * kTile;                 // 176
+constexpr int kXStageCols = kChunkTiles * 4;                    // 36
+constexpr int kTmemCols = 256;
+static_assert(kAccCols + kXStages * kXStageCols <= kTmemCols, "TMEM budget");
+constexpr int kWStageBytes = (kBatchBytes + 127) / 128 * 128;
+constexpr int kSmemW = 0;
+constexpr int kSmemBar = kSmemW + kWStages * kWStageBytes;
+constexpr int kSmemTab = kSmemBar + 128;                        // per-halo-row (image, first input row) tables
+constexpr int kMaxHaloRows = 40;
+constexpr int kSmemHalo = kSmemBar + 128 + 2 * kMaxHaloRows * 4 + 64;   // two halo buffers follow (conv only)
 
 struct TcParams {
   // activation source
@@ -48,6 +59,7 @@ struct TcParams {
   int32_t x_align2;  // GEMM: base pointer and lda are even -> 16-bit loads
   // conv geometry (conv mode only)
   int32_t C, H, W, ksz, stride, pad, Ho, Wo;
+  int32_t halo_pitch, halo_rows, halo_bytes;   // per producer half: [14 ch][halo_rows][ksz][halo_pitch]
   // plan
   const uint8_t* ws;
   const BatchInfo* batches;
@@ -86,16 +98,44 @@ __device__ __forceinline__ int8_t sat8_count(int v, uint32_t& sat) {
   if (v < -128) { ++sat; return -128; }
   return static_cast<int8_t>(v);
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 3x3 fast path: one stage = 9 K tiles = 126 k = exactly 14 input channels x 9 taps, so the (channel, tap) ->
+// (tile, byte) map is a compile-time pattern.  `rowp` points at this thread's patch origin inside the halo.
+__device__ __forceinline__ void gather3x3_to_tmem(const uint8_t* rowp, int chan_stride, int pitch, uint32_t tcol) {
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int c = 0; c < 14; ++c) {
+    const uint8_t* pc = rowp + c * chan_stride;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const uint8_t* pr = pc + kh * pitch;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int kl = c * 9 + kh * 3 + kw;        // compile-time
+        const int i = kl % 14;
+        const uint32_t b = pr[kw];
+        if ((i & 3) == 0) w[i >> 2] = b; else w[i >> 2] |= b << ((i & 3) * 8);
+        if (i == 13) {
+          tmem_st4(tcol + (kl / 14) * 4, w[0], w[1], w[2], w[3]);
+          w[3] = 0u;
+        }
+      }
+    }
+  }
+}
 
 template <bool kConv>
-__global__ void __launch_bounds__(kThreads, 1) bsr_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
-  uint64_t* x_full = bars;                 // [kXStages]
-  uint64_t* x_empty = bars + kXStages;     // [kXStages]
-  uint64_t* w_full = bars + 2 * kXStages;  // [kWStages]
-  uint64_t* w_empty = w_full + kWStages;   // [kWStages]
-  uint64_t* acc_full = w_empty + kWStages; // [1]
+  uint64_t* x_full = bars;                 // [2]  count 128 (one producer half)
+  uint64_t* x_empty = bars + 2;            // [2]  count kIssuers
+  uint64_t* w_full = bars + 4;             // [kWStages] count 1 (+tx bytes)
+  uint64_t* w_empty = w_full + kWStages;   // [kWStages] count kIssuers
+  uint64_t* acc_full = w_empty + kWStages; // [1]  count kIssuers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -106,82 +146,144 @@ __global__ void __launch_bounds__(kThreads, 1) bsr_tc_kernel(const __grid_consta
   const int64_t m0 = mtile * kTileM;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kXStages; ++s) { mbar_init(&x_full[s], 128); mbar_init(&x_empty[s], 1); }
-    for (int s = 0; s < kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 128); mbar_init(&x_empty[s], kIssuers); }
+    for (int s = 0; s < kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kIssuers); }
+    mbar_init(acc_full, kIssuers);
     fence_mbar_init();
   }
-  if (warp == 4) {
-    tmem_alloc_dyn(tmem_slot, static_cast<uint32_t>(G.tmem_cols));
+  if (warp == kProducerWarps) {
+    tmem_alloc_dyn(tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  int* tab_n = reinterpret_cast<int*>(smem + kSmemTab);        // image index of halo row rr (-1: past the batch)
+  int* tab_ih0 = tab_n + kMaxHaloRows;                          // first input row (oh*stride - pad) of halo row rr
+  if (kConv) {  // halo pads (left/right columns, rows never written) must read as zero
+    uint32_t* h = reinterpret_cast<uint32_t*>(smem + kSmemHalo);
+    for (int i = threadIdx.x; i < (2 * p.halo_bytes) / 4; i += kThreads) h[i] = 0u;
+    if (threadIdx.x < p.halo_rows) {
+      const int Rg = static_cast<int>(m0 / p.Wo) + threadIdx.x;
+      const int n = Rg / p.Ho;
+      tab_n[threadIdx.x] = (static_cast<int64_t>(n) * p.Ho * p.Wo < p.M) ? n : -1;
+      tab_ih0[threadIdx.x] = (Rg - n * p.Ho) * p.stride - p.pad;
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {  // zero the accumulators: every MMA accumulates, so issue order across warps is free
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    for (int c = 0; c < G.n_rows * kTile; c += 4) tmem_st4(tmem_base + lane_base + c, 0u, 0u, 0u, 0u);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // =================================================================== activation producers
-    const int tid = threadIdx.x;  // 0..127
-    int step = 0;
-    // conv: this thread's output position (row m0+tid) decomposed once
-    int64_t img_base = 0;
-    int ih0 = 0, iw0 = 0;
-    bool row_ok = (m0 + tid) < p.M;
+    const int half = warp >> 2;                 // owns stages with (step & 1) == half
+    const int tid = threadIdx.x & 127;          // activation row inside the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t xcol = tmem_base + lane_base + kAccCols + half * kXStageCols;
+    const int64_t m = m0 + tid;
+    const bool row_ok = m < p.M;
+    // conv: this thread's output position and the tile's first output row
+    int64_t R0 = 0;
+    int rl = 0, ow = 0, oh = 0;
+    int64_t img = 0;
     if (kConv) {
-      const int64_t m = m0 + tid;
       const int64_t P = static_cast<int64_t>(p.Ho) * p.Wo;
-      const int64_t n = row_ok ? m / P : 0;
-      const int pp = row_ok ? static_cast<int>(m - n * P) : 0;
-      const int oh = pp / p.Wo, ow = pp - oh * p.Wo;
-      ih0 = oh * p.stride - p.pad;
-      iw0 = ow * p.stride - p.pad;
-      img_base = n * static_cast<int64_t>(p.C) * p.H * p.W;
+      R0 = m0 / p.Wo;                                        // global output-row id (n*Ho + oh) of the tile start
+      const int64_t mm = row_ok ? m : m0;
+      const int64_t R = mm / p.Wo;
+      ow = static_cast<int>(mm - R * p.Wo);
+      rl = static_cast<int>(R - R0);
+      img = mm / P;
+      oh = static_cast<int>(R - img * p.Ho);
     }
+    uint8_t* halo = smem + kSmemHalo + half * p.halo_bytes;
+    int step = 0;
     for (int b = G.batch_begin; b < G.batch_end; ++b) {
       const BatchInfo bi = p.batches[b];
-      if (!(bi.flags & 1)) continue;  // one activation stage per K chunk
-      const int s = step % kXStages;
-      const uint32_t ph = (step / kXStages) & 1;
-      mbar_wait(&x_empty[s], ph ^ 1);
-      uint8_t* stage = smem + kSmemX + s * kXStageBytes;
+      if (!(bi.flags & 1)) continue;            // one activation stage per K chunk
+      const int my = (step & 1) == half;
+      const int use = step >> 1;
+      ++step;
+      if (!my) continue;
+      mbar_wait(&x_empty[half], (use & 1) ^ 1);
+      tc_fence_after();
       const int k_chunk0 = static_cast<int>(bi.chunk) * kChunkTiles * kBlock;
       if (!kConv) {
-        // 16 threads cover one row's 16 K tiles (224 contiguous bytes); 8 rows per pass
-        const int t = tid & 15;
-        const int k0 = k_chunk0 + t * kBlock;
-#pragma unroll 4
-        for (int it = 0; it < kTileM / 8; ++it) {
-          const int r = it * 8 + (tid >> 4);
-          const int64_t m = m0 + r;
-          uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-          if (m < p.M && k0 < p.K) {
-            const int8_t* src = p.x + m * p.lda + k0;
-            if (p.x_align2 && k0 + kBlock <= p.K) {
-              const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
-              const uint32_t h0 = s16[0], h1 = s16[1], h2 = s16[2], h3 = s16[3], h4 = s16[4], h5 = s16[5], h6 = s16[6];
-              w0 = h0 | (h1 << 16); w1 = h2 | (h3 << 16); w2 = h4 | (h5 << 16); w3 = h6;
-            } else {
-              uint32_t bytes[16];
+        // ---------------- GEMM rows: 9 tiles x 14 bytes, re-strided to 16.  Control flow is warp-uniform
+        // (tcgen05.st is .sync.aligned): rows past M load nothing but still store their zeros.
+        const int8_t* src = p.x + m * p.lda + k_chunk0;
+        if (p.x_align2 && k_chunk0 + kChunkTiles * kBlock <= p.K) {
+          const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                bytes[i] = (i < kBlock && k0 + i < p.K) ? static_cast<uint32_t>(static_cast<uint8_t>(src[i])) : 0u;
-              w0 = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
-              w1 = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
-              w2 = bytes[8] | (bytes[9] << 8) | (bytes[10] << 16) | (bytes[11] << 24);
-              w3 = bytes[12] | (bytes[13] << 8);
+          for (int t = 0; t < kChunkTiles; ++t) {
+            uint32_t h[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) h[j] = row_ok ? static_cast<uint32_t>(s16[t * 7 + j]) : 0u;
+            tmem_st4(xcol + t * 4, h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6]);
+          }
+        } else {
+#pragma unroll 1
+          for (int t = 0; t < kChunkTiles; ++t) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int i = 0; i < kBlock; ++i) {
+              const int k = k_chunk0 + t * kBlock + i;
+              const uint32_t v = (row_ok && k < p.K) ? static_cast<uint32_t>(static_cast<uint8_t>(src[t * kBlock + i])) : 0u;
+              w[i >> 2] |= v << ((i & 3) * 8);
+            }
+            tmem_st4(xcol + t * 4, w[0], w[1], w[2], w[3]);
+          }
+        }
+      } else if (p.halo_bytes > 0) {
+        // ---------------- 3x3 conv: stage the 14 channels' input rows, then the compile-time gather
+        const int c0 = static_cast<int>(bi.chunk) * 14;
+        const int per_ch = p.halo_rows * 3;
+        const int wpr = (p.W + 3) >> 2;                       // 4-byte words per input row
+        const bool vec = (p.W & 3) == 0;
+        for (int cl = 0; cl < 14; ++cl) {
+          const int c = c0 + cl;
+          for (int idx = tid >> 4; idx < per_ch; idx += 8) {  // 16 lanes per halo row, 8 rows per pass
+            const int rr = idx / 3, kh = idx - rr * 3;
+            const int n = tab_n[rr];
+            const int ih = tab_ih0[rr] + kh;
+            const bool ok = c < p.C && n >= 0 && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H);
+            const int8_t* g = p.x + ((static_cast<int64_t>(n) * p.C + c) * p.H + ih) * p.W;
+            uint8_t* d = halo + (cl * per_ch + idx) * p.halo_pitch + 4;
+            for (int wd = tid & 15; wd < wpr; wd += 16) {
+              uint32_t v = 0u;
+              if (ok) {
+                if (vec) v = *reinterpret_cast<const uint32_t*>(g + wd * 4);
+                else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (wd * 4 + j < p.W) v |= static_cast<uint32_t>(static_cast<uint8_t>(g[wd * 4 + j])) << (8 * j);
+                }
+              }
+              *reinterpret_cast<uint32_t*>(d + wd * 4) = v;
             }
           }
-          *reinterpret_cast<uint4*>(stage + t * kXTileStride + r * kTile) = make_uint4(w0, w1, w2, w3);
         }
+        named_bar_sync(1 + half, 128);
+        const int chan_stride = p.halo_rows * 3 * p.halo_pitch;
+        const uint8_t* rowp = halo + rl * 3 * p.halo_pitch + ow * p.stride + 4 - p.pad;
+        gather3x3_to_tmem(rowp, chan_stride, p.halo_pitch, xcol);
+        named_bar_sync(1 + half, 128);                        // halo is reused by this half's next stage
       } else {
-        // one thread = one output position; walk k = (c, kh, kw) incrementally over the chunk
+        // ---------------- general k x k (1x1 downsample, 7x7 stem): incremental (c, kh, kw) walk from global
         int k = k_chunk0;
         const int kk = p.ksz * p.ksz;
         int c = k / kk;
         int rem = k - c * kk;
         int kh = rem / p.ksz, kw = rem - kh * p.ksz;
-        const int8_t* img = p.x + img_base;
+        const int8_t* im = p.x + img * static_cast<int64_t>(p.C) * p.H * p.W;
+        const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
+#pragma unroll 1
         for (int t = 0; t < kChunkTiles; ++t) {
           uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -190,45 +292,38 @@ __global__ void __launch_bounds__(kThreads, 1) bsr_tc_kernel(const __grid_consta
             const int ih = ih0 + kh, iw = iw0 + kw;
             if (row_ok && k < p.K && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
                 static_cast<unsigned>(iw) < static_cast<unsigned>(p.W))
-              v = static_cast<uint8_t>(img[(static_cast<int64_t>(c) * p.H + ih) * p.W + iw]);
+              v = static_cast<uint8_t>(im[(static_cast<int64_t>(c) * p.H + ih) * p.W + iw]);
             w[i >> 2] |= v << ((i & 3) * 8);
             ++k;
             if (++kw == p.ksz) { kw = 0; if (++kh == p.ksz) { kh = 0; ++c; } }
           }
-          *reinterpret_cast<uint4*>(stage + t * kXTileStride + tid * kTile) = make_uint4(w[0], w[1], w[2], w[3]);
+          tmem_st4(xcol + t * 4, w[0], w[1], w[2], w[3]);
         }
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&x_full[s]);
-      ++step;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&x_full[half]);
     }
 
-    // =================================================================== epilogue (same 4 warps)
+    // =================================================================== epilogue (same 8 warps)
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int64_t m = m0 + tid;
-    const bool valid = m < p.M;
+    const bool valid = row_ok;
     const int flags = p.epi.flags;
     int64_t out_base = 0;
     if (valid) {
-      const int64_t img = m / p.lay.rows_per_image;
-      out_base = img * p.lay.image_stride + (m - img * p.lay.rows_per_image) * p.lay.row_stride;
+      const int64_t im = m / p.lay.rows_per_image;
+      out_base = im * p.lay.image_stride + (m - im * p.lay.rows_per_image) * p.lay.row_stride;
     }
     uint32_t sat = 0;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    for (int g = 0; g < G.n_rows; ++g) {
+    for (int g = half; g < G.n_rows; g += 2) {
       uint32_t v[16];
-      if ((G.nonempty >> g) & 1u) {
-        tmem_ld16(tmem_base + lane_base + g * kTile, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0u;
-      }
-      const int c0 = (G.br0 + g) * kBlock;
+      tmem_ld16(tmem_base + lane_base + g * kTile, v);
+      tmem_ld_wait();
+      const int cb = (G.br0 + g) * kBlock;
 #pragma unroll
       for (int h = 0; h < kBlock; ++h) {
-        const int c = c0 + h;
+        const int c = cb + h;
         const bool chan_ok = c < p.epi.n_channels;   // warp-uniform
         int acc = static_cast<int>(v[h]);
         if (chan_ok && p.epi.bias) acc += p.epi.bias[c];
@@ -265,46 +360,39 @@ __global__ void __launch_bounds__(kThreads, 1) bsr_tc_kernel(const __grid_consta
       if (lane == 0 && wsum) atomicAdd(p.epi.sat_count, static_cast<unsigned long long>(wsum));
     }
     tc_fence_before();
-  } else if (warp == 4) {
-    // =================================================================== MMA issuer
+  } else if (warp < kProducerWarps + kIssuers) {
+    // =================================================================== MMA issuers
+    const int me = warp - kProducerWarps;
     const uint32_t idesc = idesc_i8(kTileM, kTile);
-    uint32_t inited = 0;
-    int step = -1, wcount = 0;
-    int xs = 0;
+    int step = -1, wcount = 0, xs = 0;
     for (int b = G.batch_begin; b < G.batch_end; ++b) {
       const BatchInfo bi = p.batches[b];
       if (bi.flags & 1) {
         ++step;
-        xs = step % kXStages;
-        mbar_wait(&x_full[xs], (step / kXStages) & 1);
+        xs = step & 1;
+        mbar_wait(&x_full[xs], (step >> 1) & 1);
       }
       const int ws_i = wcount % kWStages;
       mbar_wait(&w_full[ws_i], (wcount / kWStages) & 1);
       tc_fence_after();
-      const uint8_t* wst = smem + kSmemW + ws_i * ((kWStageBytes + 127) / 128 * 128);
-      const uint32_t x_addr = smem_u32(smem + kSmemX + xs * kXStageBytes);
+      const uint8_t* wst = smem + kSmemW + ws_i * kWStageBytes;
       const uint32_t w_addr = smem_u32(wst);
-      // Lane-parallel decode: lane i owns op i of the batch.  Everything that depends on the op's
-      // metadata is computed once, in vector registers, for all ops at the same time; the issue loop
-      // below only broadcasts one packed word per op (shfl -> warp-uniform -> uniform registers).
+      // Lane-parallel decode: lane i owns op i of the batch; the issue loop only broadcasts one packed
+      // word per op (shfl -> warp-uniform -> uniform registers for the descriptors).
       const int n_ops = bi.n_ops;
       uint32_t mt = 0;
       if (lane < n_ops) mt = reinterpret_cast<const uint16_t*>(wst + n_ops * kBTileBytes)[lane];
-      const uint32_t g = mt & 31u, win = mt >> 5;
-      const uint32_t same = __match_any_sync(0xffffffffu, lane < n_ops ? g : 32u + lane);
-      const uint32_t acc = ((inited >> g) & 1u) | ((same & ((1u << lane) - 1u)) != 0u ? 1u : 0u);
-      // packed: bits 0..13 A start address >> 4, bits 14..22 D column, bit 23 accumulate
-      const uint32_t packed = (((x_addr + win * kXTileStride) >> 4) & 0x3FFFu) | ((g * kTile) << 14) | (acc << 23);
-      inited |= __reduce_or_sync(0xffffffffu, lane < n_ops ? (1u << g) : 0u);
-      const uint64_t adesc_hi = smem_desc_kmajor(0, kXTileStride, 128);
+      const uint32_t g = mt & 15u, win = mt >> 4;
+      // packed: bits 0..8 A column, bits 9..17 D column
+      const uint32_t packed = (kAccCols + xs * kXStageCols + win * 4) | ((g * kTile) << 9);
       const uint64_t bdesc0 = smem_desc_kmajor(w_addr, 256, 128);
 #pragma unroll
-      for (int i = 0; i < kOpsPerBatch; ++i) {
-        if (i < n_ops) {                                   // warp-uniform
-          const uint32_t pk = __shfl_sync(0xffffffffu, packed, i);
-          const uint64_t adesc = adesc_hi | static_cast<uint64_t>(pk & 0x3FFFu);
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((i * kBTileBytes) >> 4);
-          if (elect_one()) mma_i8_ss(tmem_base + ((pk >> 14) & 0x1FFu), adesc, bdesc, idesc, (pk >> 23) & 1u);
+      for (int i = 0; i < kOpsPerBatch / kIssuers; ++i) {
+        const int op = i * kIssuers + me;                  // ops are dealt round-robin to the issuing warps
+        if (op < n_ops) {                                  // warp-uniform
+          const uint32_t pk = __shfl_sync(0xffffffffu, packed, op);
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((op * kBTileBytes) >> 4);
+          if (elect_one()) mma_i8_ts(tmem_base + (pk >> 9), tmem_base + (pk & 0x1FFu), bdesc, idesc, 1u);
         }
       }
       if (elect_one()) {
@@ -330,8 +418,8 @@ __global__ void __launch_bounds__(kThreads, 1) bsr_tc_kernel(const __grid_consta
         mbar_wait(&w_empty[ws_i], ((wcount / kWStages) & 1) ^ 1);
         const uint32_t bytes = bi.n_ops * kBTileBytes + kBatchMetaBytes;
         mbar_arrive_expect_tx(&w_full[ws_i], bytes);
-        bulk_g2s(smem + kSmemW + ws_i * ((kWStageBytes + 127) / 128 * 128), p.ws + static_cast<size_t>(bi.blob_off16) * 16,
-                 bytes, &w_full[ws_i]);
+        bulk_g2s(smem + kSmemW + ws_i * kWStageBytes, p.ws + static_cast<size_t>(bi.blob_off16) * 16, bytes,
+                 &w_full[ws_i]);
         ++wcount;
       }
     }
@@ -339,9 +427,9 @@ __global__ void __launch_bounds__(kThreads, 1) bsr_tc_kernel(const __grid_consta
   }
 
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kProducerWarps) {
     tc_fence_after();
-    tmem_dealloc_dyn(tmem_base, static_cast<uint32_t>(G.tmem_cols));
+    tmem_dealloc_dyn(tmem_base, kTmemCols);
   }
 }
 

@@ -9,9 +9,8 @@ namespace accel {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int32_t tmem_cols_for(int32_t rows) {
-  int32_t need = rows * kTile, c = 32;
-  while (c < need) c <<= 1;
-  return c;
+  (void)rows;
+  return 256;  // accumulators + two activation stages (bsr_tc.cuh)
 }
 
 std::string build_plan(const int32_t* row_ptr, const int32_t* col_idx, int32_t nbr, int32_t nbc, Plan* p) {
@@ -116,7 +115,7 @@ std::string build_plan(const int32_t* row_ptr, const int32_t* col_idx, int32_t n
           const PendingOp& op = per_row[g][depth];
           const BatchInfo& b = p->batches.back();
           p->op_src.push_back(op.src);
-          p->op_meta.push_back(static_cast<uint16_t>((g & 31) | (op.win << 5)));
+          p->op_meta.push_back(static_cast<uint16_t>((g & 15) | (op.win << 4)));
           p->op_blob_off.push_back(static_cast<uint32_t>(static_cast<size_t>(b.blob_off16) * 16 +
                                                          static_cast<size_t>(ops_in_batch) * kBTileBytes));
           p->op_meta_off.push_back(0);

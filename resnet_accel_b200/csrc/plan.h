@@ -16,12 +16,12 @@ namespace accel {
 
 constexpr int kBlock = 14;           // reference block size (export_bsr_14x14.py:48)
 constexpr int kTile = 16;            // padded K slot / padded block-row height
-constexpr int kChunkTiles = 16;      // K tiles staged per activation stage
-constexpr int kMaxGroupRows = 32;    // block-rows per CTA (32 x 16 = 512 TMEM columns)
-constexpr int kDefaultGroupRows = 16;  // 256 TMEM columns: two CTAs can share an SM
-constexpr int kOpsPerBatch = 16;     // B tiles per weight stage
+constexpr int kChunkTiles = 9;       // K tiles per activation stage: 126 k = 14 channels x 9 taps of a 3x3 conv
+constexpr int kMaxGroupRows = 11;    // block-rows per CTA: 11 x 16 accumulator columns + 2 x 36 activation columns <= 256
+constexpr int kDefaultGroupRows = 11;
+constexpr int kOpsPerBatch = 32;     // B tiles per weight stage (one per lane of the decoding warp)
 constexpr int kBTileBytes = 512;     // 16 rows x 32 bytes
-constexpr int kBatchMetaBytes = 32;  // kOpsPerBatch x u16
+constexpr int kBatchMetaBytes = 64;  // kOpsPerBatch x u16
 constexpr int kBatchBytes = kOpsPerBatch * kBTileBytes + kBatchMetaBytes;
 
 struct BatchInfo {       // 8 bytes, read by the loader / issuer / producer warps
@@ -54,7 +54,7 @@ struct Plan {
   int32_t group_rows = 0;
   std::vector<GroupInfo> groups;
   std::vector<BatchInfo> batches;
-  std::vector<uint16_t> op_meta;   // per op: (g & 31) | (window_tile << 5)
+  std::vector<uint16_t> op_meta;   // per op: (g & 15) | (window_tile << 4)
   std::vector<OpSrc> op_src;       // per op
   std::vector<uint32_t> op_blob_off;  // byte offset of each op's B tile in the workspace
   std::vector<uint32_t> op_meta_off;  // byte offset of each op's u16 meta in the workspace

@@ -10,7 +10,7 @@ import pytest
 from oracle import bsr_oracle as O
 from resnet_accel_b200 import _lib
 
-CHUNK = 16
+CHUNK = 9
 
 
 def _export(rp, ci, nbr, nbc, group_rows=0):
