@@ -51,7 +51,7 @@ cudaError_t g_attr_err = cudaSuccess;
 constexpr int kMaxHaloBytes = 28 * 1024;   // per producer half; keeps two CTAs (2 x ~106 KB) on one SM
 void set_kernel_attrs() {
   g_attr_err = cudaFuncSetAttribute(accel::bsr_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    accel::kSmemHalo);
+                                    accel::kSmemHalo + 2 * accel::kGemmStageBytes);
   if (g_attr_err == cudaSuccess)
     g_attr_err = cudaFuncSetAttribute(accel::bsr_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       accel::kSmemHalo + 2 * kMaxHaloBytes);
@@ -87,7 +87,7 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, bool conv, cudaStream_
   if (conv)
     accel::bsr_tc_kernel<true><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemHalo + 2 * prm.halo_bytes, st>>>(prm);
   else
-    accel::bsr_tc_kernel<false><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemHalo, st>>>(prm);
+    accel::bsr_tc_kernel<false><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemHalo + 2 * accel::kGemmStageBytes, st>>>(prm);
   CU(cudaGetLastError());
   return ACCEL_OK;
 }
@@ -200,6 +200,7 @@ int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64_t M, int6
   std::memset(&prm, 0, sizeof(prm));
   prm.x = act; prm.M = M; prm.K = static_cast<int32_t>(K); prm.lda = lda;
   prm.x_align2 = ((reinterpret_cast<uintptr_t>(act) | static_cast<uintptr_t>(lda)) & 1) == 0;
+  prm.gemm_staged = ((reinterpret_cast<uintptr_t>(act) | static_cast<uintptr_t>(lda)) & 15) == 0;
   prm.epi = *epi; prm.out = out; prm.lay = *layout;
   return launch_tc(&plan->p, prm, false, static_cast<cudaStream_t>(stream));
 }
@@ -231,8 +232,16 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
     const int rows = (accel::kTileM - 1) / prm.Wo + 2;
     const int pitch = ((g->w + 3) / 4) * 4 + 8;             // 4 zero bytes left, >= 4 right (pad <= 3)
     const int bytes = ((14 * rows * 3 * pitch + 127) / 128) * 128;
-    if (rows <= accel::kMaxHaloRows && bytes <= kMaxHaloBytes) {   // else: the general gather path
+    const int wpr = (g->w + 3) / 4;
+    if (rows <= accel::kMaxHaloRows && bytes <= kMaxHaloBytes && wpr <= 32) {   // else: the general gather path
       prm.halo_rows = rows; prm.halo_pitch = pitch; prm.halo_bytes = bytes;
+      int lpr = 1;
+      while (lpr < wpr) lpr <<= 1;
+      prm.halo_lpr = lpr;
+      // 4-byte async copies need 4-byte aligned global rows: W % 4 == 0 and a 4-byte aligned tensor base
+      prm.halo_vec = (g->w % 4 == 0) && ((reinterpret_cast<uintptr_t>(input_nchw) & 3) == 0);
+      const unsigned per_ch = static_cast<unsigned>(rows * 3);
+      prm.halo_perch_magic = static_cast<uint32_t>(((1ull << 32) + per_ch - 1) / per_ch);
     }
   }
   return launch_tc(&plan->p, prm, true, static_cast<cudaStream_t>(stream));

@@ -49,6 +49,8 @@ constexpr int kSmemBar = kSmemW + kWStages * kWStageBytes;
 constexpr int kSmemTab = kSmemBar + 128;                        // per-halo-row (image, first input row) tables
 constexpr int kMaxHaloRows = 40;
 constexpr int kSmemHalo = kSmemBar + 128 + 2 * kMaxHaloRows * 4 + 64;   // two halo buffers follow (conv only)
+constexpr int kGemmStagePitch = 148;                            // 37 words: odd pitch -> conflict-free per-row reads
+constexpr int kGemmStageBytes = kTileM * kGemmStagePitch + 64;  // one staging buffer per producer half (GEMM only)
 
 struct TcParams {
   // activation source
@@ -57,9 +59,12 @@ struct TcParams {
   int32_t K;
   int64_t lda;
   int32_t x_align2;  // GEMM: base pointer and lda are even -> 16-bit loads
+  int32_t gemm_staged;  // GEMM: base pointer and lda are multiples of 16 -> coalesced 16-byte loads via shared memory
   // conv geometry (conv mode only)
   int32_t C, H, W, ksz, stride, pad, Ho, Wo;
   int32_t halo_pitch, halo_rows, halo_bytes;   // per producer half: [14 ch][halo_rows][ksz][halo_pitch]
+  int32_t halo_lpr, halo_vec;                  // lanes per halo row (pow2 >= words per row); rows are 4-byte copyable
+  uint32_t halo_perch_magic;                   // ceil(2^32 / (halo_rows*3)): row / per_ch by __umulhi
   // plan
   const uint8_t* ws;
   const BatchInfo* batches;
@@ -217,27 +222,73 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
       if (!kConv) {
         // ---------------- GEMM rows: 9 tiles x 14 bytes, re-strided to 16.  Control flow is warp-uniform
         // (tcgen05.st is .sync.aligned): rows past M load nothing but still store their zeros.
-        const int8_t* src = p.x + m * p.lda + k_chunk0;
-        if (p.x_align2 && k_chunk0 + kChunkTiles * kBlock <= p.K) {
-          const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
+        if (p.gemm_staged) {
+          // Coalesced path (16-byte aligned rows): the 128 x 144-byte window that covers this stage is pulled
+          // with 16-byte loads (9 consecutive lanes per row), parked in shared memory with an odd word pitch,
+          // then every thread re-strides its own row conflict-free.
+          uint8_t* stg = smem + kSmemHalo + half * kGemmStageBytes;
+          const int a0 = k_chunk0 & ~15;
+          const int shift = k_chunk0 - a0;                    // even, <= 14
+          uint4 v[kChunkTiles];
+#pragma unroll
+          for (int it = 0; it < kChunkTiles; ++it) {
+            const int item = it * 128 + tid;
+            const int row = item / kChunkTiles, ch = item - row * kChunkTiles;
+            const int64_t gm = m0 + row;
+            const int ka = a0 + ch * 16;
+            v[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (gm < p.M && ka < p.K) {
+              const int8_t* g = p.x + gm * p.lda + ka;
+              if (ka + 16 <= p.K) {
+                v[it] = *reinterpret_cast<const uint4*>(g);
+              } else {                                        // the one chunk per row that straddles K
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                for (int j = 0; j < 16; ++j)
+                  if (ka + j < p.K) w[j >> 2] |= static_cast<uint32_t>(static_cast<uint8_t>(g[j])) << ((j & 3) * 8);
+                v[it] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < kChunkTiles; ++it) {
+            const int item = it * 128 + tid;
+            const int row = item / kChunkTiles, ch = item - row * kChunkTiles;
+            uint32_t* d = reinterpret_cast<uint32_t*>(stg + row * kGemmStagePitch + ch * 16);
+            d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w;
+          }
+          named_bar_sync(1 + half, 128);
+          const uint16_t* s16 = reinterpret_cast<const uint16_t*>(stg + tid * kGemmStagePitch + shift);
 #pragma unroll
           for (int t = 0; t < kChunkTiles; ++t) {
             uint32_t h[7];
 #pragma unroll
-            for (int j = 0; j < 7; ++j) h[j] = row_ok ? static_cast<uint32_t>(s16[t * 7 + j]) : 0u;
+            for (int j = 0; j < 7; ++j) h[j] = s16[t * 7 + j];
             tmem_st4(xcol + t * 4, h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6]);
           }
+          named_bar_sync(1 + half, 128);
         } else {
-#pragma unroll 1
-          for (int t = 0; t < kChunkTiles; ++t) {
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
+          const int8_t* src = p.x + m * p.lda + k_chunk0;
+          if (p.x_align2 && k_chunk0 + kChunkTiles * kBlock <= p.K) {
+            const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
 #pragma unroll
-            for (int i = 0; i < kBlock; ++i) {
-              const int k = k_chunk0 + t * kBlock + i;
-              const uint32_t v = (row_ok && k < p.K) ? static_cast<uint32_t>(static_cast<uint8_t>(src[t * kBlock + i])) : 0u;
-              w[i >> 2] |= v << ((i & 3) * 8);
+            for (int t = 0; t < kChunkTiles; ++t) {
+              uint32_t h[7];
+#pragma unroll
+              for (int j = 0; j < 7; ++j) h[j] = row_ok ? static_cast<uint32_t>(s16[t * 7 + j]) : 0u;
+              tmem_st4(xcol + t * 4, h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6]);
             }
-            tmem_st4(xcol + t * 4, w[0], w[1], w[2], w[3]);
+          } else {
+#pragma unroll 1
+            for (int t = 0; t < kChunkTiles; ++t) {
+              uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+              for (int i = 0; i < kBlock; ++i) {
+                const int k = k_chunk0 + t * kBlock + i;
+                const uint32_t v = (row_ok && k < p.K) ? static_cast<uint32_t>(static_cast<uint8_t>(src[t * kBlock + i])) : 0u;
+                w[i >> 2] |= v << ((i & 3) * 8);
+              }
+              tmem_st4(xcol + t * 4, w[0], w[1], w[2], w[3]);
+            }
           }
         }
       } else if (p.halo_bytes > 0) {
@@ -245,30 +296,37 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
         const int c0 = static_cast<int>(bi.chunk) * 14;
         const int per_ch = p.halo_rows * 3;
         const int wpr = (p.W + 3) >> 2;                       // 4-byte words per input row
-        const bool vec = (p.W & 3) == 0;
-        for (int cl = 0; cl < 14; ++cl) {
-          const int c = c0 + cl;
-          for (int idx = tid >> 4; idx < per_ch; idx += 8) {  // 16 lanes per halo row, 8 rows per pass
+        const int total_rows = 14 * per_ch;
+        const int lpr = p.halo_lpr;                           // lanes per halo row (power of two >= wpr)
+        const int wl = tid & (lpr - 1);
+        const int rpp = 128 / lpr;                            // halo rows per pass
+        if (wl < wpr) {
+          for (int row = tid / lpr; row < total_rows; row += rpp) {
+            const int cl = __umulhi(static_cast<unsigned>(row), p.halo_perch_magic);   // row / per_ch
+            const int idx = row - cl * per_ch;
             const int rr = idx / 3, kh = idx - rr * 3;
             const int n = tab_n[rr];
             const int ih = tab_ih0[rr] + kh;
+            const int c = c0 + cl;
             const bool ok = c < p.C && n >= 0 && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H);
-            const int8_t* g = p.x + ((static_cast<int64_t>(n) * p.C + c) * p.H + ih) * p.W;
-            uint8_t* d = halo + (cl * per_ch + idx) * p.halo_pitch + 4;
-            for (int wd = tid & 15; wd < wpr; wd += 16) {
+            uint8_t* d = halo + row * p.halo_pitch + 4 + wl * 4;
+            if (p.halo_vec) {
+              // asynchronous 4-byte copies (LDGSTS), zero-filled for padding rows: nothing waits until the end
+              const int8_t* g = ok ? p.x + ((static_cast<int64_t>(n) * p.C + c) * p.H + ih) * p.W + wl * 4 : p.x;
+              cp_async4_zfill(d, g, ok);
+            } else {
               uint32_t v = 0u;
               if (ok) {
-                if (vec) v = *reinterpret_cast<const uint32_t*>(g + wd * 4);
-                else {
+                const int8_t* g = p.x + ((static_cast<int64_t>(n) * p.C + c) * p.H + ih) * p.W + wl * 4;
 #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (wd * 4 + j < p.W) v |= static_cast<uint32_t>(static_cast<uint8_t>(g[wd * 4 + j])) << (8 * j);
-                }
+                for (int j = 0; j < 4; ++j)
+                  if (wl * 4 + j < p.W) v |= static_cast<uint32_t>(static_cast<uint8_t>(g[j])) << (8 * j);
               }
-              *reinterpret_cast<uint32_t*>(d + wd * 4) = v;
+              *reinterpret_cast<uint32_t*>(d) = v;
             }
           }
         }
+        cp_async_wait_all();
         named_bar_sync(1 + half, 128);
         const int chan_stride = p.halo_rows * 3 * p.halo_pitch;
         const uint8_t* rowp = halo + rl * 3 * p.halo_pitch + ow * p.stride + 4 - p.pad;
