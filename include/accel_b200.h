@@ -101,10 +101,14 @@ ACCEL_API int accel_plan_upload(accel_plan* plan, const int8_t* blocks_dev, void
                       accel_stream_t stream);
 ACCEL_API void accel_plan_destroy(accel_plan* plan);
 ACCEL_API int64_t accel_plan_num_blocks(const accel_plan* plan);
-ACCEL_API int64_t accel_plan_num_mma(const accel_plan* plan); /* tcgen05.mma instructions per 128-row tile */
-/* Schedule read-out for tests / tooling: writes up to `cap` records of 8 int32
- * {group, first_block_row, local_row, k_chunk, window_tile, block_lo, block_hi, batch} and returns the op count. */
+ACCEL_API int64_t accel_plan_num_mma(const accel_plan* plan);   /* tcgen05.mma instructions per 128-row tile */
+ACCEL_API int64_t accel_plan_num_tiles(const accel_plan* plan); /* 16x32 weight tiles (512 B each) */
+/* Schedule read-out for tests / tooling.  export_ops: one record of 8 int32 per weight tile, in blob order,
+ * {group, first_block_row, local_row, k_chunk, window_tile, block_lo, block_hi, batch}; returns the tile count.
+ * export_mma: one record of 8 int32 per tcgen05.mma {group, batch, accumulator_column, N, activation_column,
+ * first_tile (blob order), k_chunk, first_block_row}; returns the MMA count. */
 ACCEL_API int64_t accel_plan_export_ops(const accel_plan* plan, int32_t* records, int64_t cap);
+ACCEL_API int64_t accel_plan_export_mma(const accel_plan* plan, int32_t* records, int64_t cap);
 
 /* --- K1+K3: block-sparse GEMM, tcgen05 kind::i8, fused epilogue.
  * Replaces gemm_bsr_int8_golden (sw/golden/golden_fc1_test.py:49-108), AccelDriver.run_inference

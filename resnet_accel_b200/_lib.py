@@ -54,7 +54,9 @@ SYMBOLS = {
     "accel_plan_destroy": (None, [_P]),
     "accel_plan_num_blocks": (_I64, [_P]),
     "accel_plan_num_mma": (_I64, [_P]),
+    "accel_plan_num_tiles": (_I64, [_P]),
     "accel_plan_export_ops": (_I64, [_P, _P, _I64]),
+    "accel_plan_export_mma": (_I64, [_P, _P, _I64]),
     "accel_bsr_gemm_i8": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(Epilogue), _P, C.POINTER(OutLayout), _P]),
     "accel_conv_bsr_i8": (C.c_int, [_P, _P, C.POINTER(ConvGeom), C.POINTER(Epilogue), _P, C.POINTER(OutLayout), _P]),
     "accel_bsr_gemm_generic": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _P, _I64, _P]),

@@ -2,8 +2,11 @@
 // parameter block, launch on the caller's stream.  No device allocation, no CPU arithmetic.
 #include <cuda_runtime.h>
 
+#include <array>
 #include <climits>
+#include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 
@@ -48,13 +51,17 @@ int grid_for(int64_t work_items, int threads, int per_sm = 8) {
 
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
-constexpr int kMaxHaloBytes = 28 * 1024;   // per producer half; keeps two CTAs (2 x ~106 KB) on one SM
+constexpr int kSmemTwoCtas = 113 * 1024;    // per CTA when two CTAs share an SM (227 KB usable, 1 KB reserved each)
+constexpr int kSmemOneCta = 200 * 1024;
 void set_kernel_attrs() {
-  g_attr_err = cudaFuncSetAttribute(accel::bsr_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    accel::kSmemHalo + 2 * accel::kGemmStageBytes);
-  if (g_attr_err == cudaSuccess)
-    g_attr_err = cudaFuncSetAttribute(accel::bsr_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      accel::kSmemHalo + 2 * kMaxHaloBytes);
+  const void* fns[] = {reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeGemm>),
+                       reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeConv3>),
+                       reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeConv7>),
+                       reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeDirect>)};
+  for (const void* f : fns) {
+    if (g_attr_err == cudaSuccess)
+      g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOneCta);
+  }
 }
 
 int check_epilogue(const accel_epilogue* epi, const accel_out_layout* lay, const void* out, int32_t max_channels) {
@@ -72,23 +79,95 @@ int check_epilogue(const accel_epilogue* epi, const accel_out_layout* lay, const
   return ACCEL_OK;
 }
 
-int launch_tc(const accel::Plan* P, accel::TcParams& prm, bool conv, cudaStream_t st) {
+// add_residual_int8 divides by s_out (golden_models.cpp:486).  The kernel may replace the IEEE divide by
+//   q0 = s * rcp;  e = fma(-q0, s_out, s);  q = fma(e, rcp, q0)      with rcp = RN(1 / s_out)
+// when that reproduces the reference's int8 result for EVERY (main, residual) int8 pair - decided here,
+// once per scale triple, by exhaustive comparison with the true quotient.
+bool residual_fast_divide_ok(float s_main, float s_res, float s_out) {
+  static std::mutex mu;
+  static std::map<std::array<uint32_t, 3>, bool> cache;
+  std::array<uint32_t, 3> key;
+  std::memcpy(&key[0], &s_main, 4); std::memcpy(&key[1], &s_res, 4); std::memcpy(&key[2], &s_out, 4);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  bool ok = std::isfinite(s_out) && s_out != 0.f;
+  const float rcp = 1.0f / s_out;
+  ok = ok && std::isfinite(rcp);
+  auto sat8 = [](float f) {
+    const float r = std::nearbyintf(f);
+    return r > 127.f ? 127 : (r < -128.f ? -128 : static_cast<int>(r));
+  };
+  for (int a = -128; ok && a < 128; ++a) {
+    volatile float am = static_cast<float>(a) * s_main;    // volatile: no contraction into an FMA
+    for (int r = -128; r < 128; ++r) {
+      volatile float rr = static_cast<float>(r) * s_res;
+      volatile float sum = am + rr;
+      const float s = sum;
+      const float truth = s / s_out;
+      const float q0 = s * rcp;
+      const float e = std::fmaf(-q0, s_out, s);
+      const float q = std::fmaf(e, rcp, q0);
+      if (!std::isfinite(truth) || !std::isfinite(q) || sat8(q) != sat8(truth)) { ok = false; break; }
+    }
+  }
+  cache[key] = ok;
+  return ok;
+}
+
+template <int MODE>
+cudaError_t launch_mode(const accel::TcLaunch& L, unsigned ctas, int smem, cudaStream_t st) {
+  accel::bsr_tc_kernel<MODE><<<ctas, accel::kThreads, smem, st>>>(L);
+  return cudaGetLastError();
+}
+
+// One or more launches: each carries the schedule tables of a range of block-row groups in its parameter block.
+int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cudaStream_t st) {
   std::call_once(g_attr_once, set_kernel_attrs);
   if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(smem)");
   const int n_groups = static_cast<int>(P->groups.size());
   const int64_t m_tiles = (prm.M + accel::kTileM - 1) / accel::kTileM;
   if (n_groups == 0 || m_tiles == 0) return ACCEL_OK;
-  const int64_t ctas = m_tiles * n_groups;
-  if (ctas > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "grid too large");
-  prm.ws = P->ws_dev + P->off_blob;
-  prm.batches = reinterpret_cast<const accel::BatchInfo*>(P->ws_dev + P->off_batches);
-  prm.groups = reinterpret_cast<const accel::GroupInfo*>(P->ws_dev + P->off_groups);
-  prm.n_groups = n_groups;
-  if (conv)
-    accel::bsr_tc_kernel<true><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemHalo + 2 * prm.halo_bytes, st>>>(prm);
-  else
-    accel::bsr_tc_kernel<false><<<static_cast<unsigned>(ctas), accel::kThreads, accel::kSmemHalo + 2 * accel::kGemmStageBytes, st>>>(prm);
-  CU(cudaGetLastError());
+  prm.blob = P->ws_dev + P->off_blob;
+  if (prm.epi.residual) {
+    prm.res_fast = residual_fast_divide_ok(prm.epi.res_scale_main, prm.epi.res_scale_res, prm.epi.res_scale_out) ? 1 : 0;
+    prm.res_rcp = 1.0f / prm.epi.res_scale_out;
+  }
+  static thread_local accel::TcLaunch L;    // 28 KB: keep it off the stack
+  int g0 = 0;
+  while (g0 < n_groups) {
+    int g1 = g0;
+    uint32_t nb = 0, no = 0;
+    while (g1 < n_groups && g1 - g0 < accel::kMaxGroupsL) {
+      const accel::GroupRec& G = P->groups[g1];
+      const uint32_t gb = G.batch_end - G.batch_begin;
+      const uint32_t go = (g1 + 1 < n_groups ? P->groups[g1 + 1].op_begin : static_cast<uint32_t>(P->ops.size())) - G.op_begin;
+      if (nb + gb > accel::kMaxBatchesL || no + go > accel::kMaxOpsL) break;
+      nb += gb; no += go; ++g1;
+    }
+    if (g1 == g0) return fail(ACCEL_INVALID_CONFIG, "block-row group exceeds the launch tables");
+    const uint32_t b0 = P->groups[g0].batch_begin, o0 = P->groups[g0].op_begin;
+    L.p = prm;
+    L.n_groups = static_cast<uint32_t>(g1 - g0);
+    for (int g = g0; g < g1; ++g) {
+      accel::GroupRec G = P->groups[g];
+      G.batch_begin -= b0; G.batch_end -= b0; G.op_begin -= o0;
+      L.groups[g - g0] = G;
+    }
+    if (nb) std::memcpy(L.batches, P->batches.data() + b0, nb * sizeof(uint32_t));
+    if (no) std::memcpy(L.ops, P->ops.data() + o0, no * sizeof(accel::OpRec));
+    const int64_t ctas = m_tiles * (g1 - g0);
+    if (ctas > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "grid too large");
+    cudaError_t e;
+    switch (mode) {
+      case accel::kModeGemm: e = launch_mode<accel::kModeGemm>(L, static_cast<unsigned>(ctas), smem, st); break;
+      case accel::kModeConv3: e = launch_mode<accel::kModeConv3>(L, static_cast<unsigned>(ctas), smem, st); break;
+      case accel::kModeConv7: e = launch_mode<accel::kModeConv7>(L, static_cast<unsigned>(ctas), smem, st); break;
+      default: e = launch_mode<accel::kModeDirect>(L, static_cast<unsigned>(ctas), smem, st); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "bsr_tc_kernel launch");
+    g0 = g1;
+  }
   return ACCEL_OK;
 }
 
@@ -140,23 +219,14 @@ int accel_plan_upload(accel_plan* plan, const int8_t* blocks_dev, void* workspac
   if (P.nnz > 0 && !blocks_dev) return fail(ACCEL_INVALID_CONFIG, "null blocks");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
-  auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
-    return bytes ? cudaMemcpyAsync(ws + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
-  };
-  CU(up(P.off_batches, P.batches.data(), P.batches.size() * sizeof(accel::BatchInfo)));
-  CU(up(P.off_groups, P.groups.data(), P.groups.size() * sizeof(accel::GroupInfo)));
-  CU(up(P.off_opsrc, P.op_src.data(), P.op_src.size() * sizeof(accel::OpSrc)));
-  CU(up(P.off_opoff, P.op_blob_off.data(), P.op_blob_off.size() * sizeof(uint32_t)));
-  CU(up(P.off_opmoff, P.op_meta_off.data(), P.op_meta_off.size() * sizeof(uint32_t)));
-  CU(up(P.off_opmeta, P.op_meta.data(), P.op_meta.size() * sizeof(uint16_t)));
-  if (P.n_ops > 0) {
-    accel::repack_blocks_kernel<<<static_cast<unsigned>(P.n_ops), 128, 0, st>>>(
-        blocks_dev, ws + P.off_blob, reinterpret_cast<const accel::OpSrc*>(ws + P.off_opsrc),
-        reinterpret_cast<const uint32_t*>(ws + P.off_opoff), reinterpret_cast<const uint32_t*>(ws + P.off_opmoff),
-        reinterpret_cast<const uint16_t*>(ws + P.off_opmeta), P.n_ops);
+  if (P.n_tiles > 0) {
+    CU(cudaMemcpyAsync(ws + P.off_tilesrc, P.tile_src.data(), P.tile_src.size() * sizeof(accel::TileSrc),
+                       cudaMemcpyHostToDevice, st));
+    accel::repack_blocks_kernel<<<static_cast<unsigned>(P.n_tiles), 128, 0, st>>>(
+        blocks_dev, ws + P.off_blob, reinterpret_cast<const accel::TileSrc*>(ws + P.off_tilesrc), P.n_tiles);
     CU(cudaGetLastError());
   }
-  // the host vectors are pageable: make sure the copies have consumed them before returning
+  // the host vector is pageable: make sure the copy has consumed it before returning
   CU(cudaStreamSynchronize(st));
   P.ws_dev = ws;
   P.uploaded = true;
@@ -165,24 +235,53 @@ int accel_plan_upload(accel_plan* plan, const int8_t* blocks_dev, void* workspac
 
 void accel_plan_destroy(accel_plan* plan) { delete plan; }
 int64_t accel_plan_num_blocks(const accel_plan* plan) { return plan ? plan->p.nnz : 0; }
-int64_t accel_plan_num_mma(const accel_plan* plan) { return plan ? plan->p.n_ops : 0; }
+int64_t accel_plan_num_mma(const accel_plan* plan) { return plan ? static_cast<int64_t>(plan->p.ops.size()) : 0; }
+int64_t accel_plan_num_tiles(const accel_plan* plan) { return plan ? plan->p.n_tiles : 0; }
 
 int64_t accel_plan_export_ops(const accel_plan* plan, int32_t* rec, int64_t cap) {
   if (!plan) return 0;
   const accel::Plan& P = plan->p;
-  int64_t op = 0;
+  int64_t t = 0;
   for (size_t gi = 0; gi < P.groups.size(); ++gi) {
-    const accel::GroupInfo& G = P.groups[gi];
-    for (int32_t b = G.batch_begin; b < G.batch_end; ++b)
-      for (int i = 0; i < P.batches[b].n_ops; ++i, ++op) {
-        if (rec && op < cap) {
-          int32_t* r = rec + op * 8;
-          r[0] = static_cast<int32_t>(gi); r[1] = G.br0; r[2] = P.op_meta[op] & 15; r[3] = P.batches[b].chunk;
-          r[4] = P.op_meta[op] >> 4; r[5] = P.op_src[op].blk_lo; r[6] = P.op_src[op].blk_hi; r[7] = b;
+    const accel::GroupRec& G = P.groups[gi];
+    for (uint32_t b = G.batch_begin; b < G.batch_end; ++b)
+      for (uint32_t i = 0; i < accel::batch_tiles(P.batches[b]); ++i, ++t) {
+        if (rec && t < cap) {
+          int32_t* r = rec + t * 8;
+          r[0] = static_cast<int32_t>(gi); r[1] = static_cast<int32_t>(G.br0_rows & 0xffffu); r[2] = P.tile_dbg[t * 4 + 1];
+          r[3] = P.tile_dbg[t * 4 + 2]; r[4] = P.tile_dbg[t * 4 + 3]; r[5] = P.tile_src[t].blk_lo;
+          r[6] = P.tile_src[t].blk_hi; r[7] = static_cast<int32_t>(b);
         }
       }
   }
-  return op;
+  return t;
+}
+
+int64_t accel_plan_export_mma(const accel_plan* plan, int32_t* rec, int64_t cap) {
+  if (!plan) return 0;
+  const accel::Plan& P = plan->p;
+  int64_t n = 0, tile0 = 0;
+  for (size_t gi = 0; gi < P.groups.size(); ++gi) {
+    const accel::GroupRec& G = P.groups[gi];
+    uint32_t op = G.op_begin;
+    for (uint32_t b = G.batch_begin; b < G.batch_end; ++b) {
+      for (uint32_t i = 0; i < accel::batch_runs(P.batches[b]); ++i, ++op, ++n) {
+        if (rec && n < cap) {
+          int32_t* r = rec + n * 8;
+          const accel::OpRec& o = P.ops[op];
+          r[0] = static_cast<int32_t>(gi); r[1] = static_cast<int32_t>(b);
+          r[2] = static_cast<int32_t>(o.d_n & 0x1ffu);                 // accumulator column
+          r[3] = static_cast<int32_t>(((o.d_n >> 17) & 0x3fu) * 8);    // N
+          r[4] = static_cast<int32_t>(o.a_b & 0x1ffu);                 // activation column inside the stage
+          r[5] = static_cast<int32_t>(tile0 + (o.a_b >> 16) / (accel::kBTileBytes / 16));   // first B tile (blob order)
+          r[6] = static_cast<int32_t>(accel::batch_chunk(P.batches[b]));
+          r[7] = static_cast<int32_t>(G.br0_rows & 0xffffu);
+        }
+      }
+      tile0 += accel::batch_tiles(P.batches[b]);
+    }
+  }
+  return n;
 }
 
 int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64_t M, int64_t K, int64_t lda,
@@ -200,9 +299,15 @@ int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64_t M, int6
   std::memset(&prm, 0, sizeof(prm));
   prm.x = act; prm.M = M; prm.K = static_cast<int32_t>(K); prm.lda = lda;
   prm.x_align2 = ((reinterpret_cast<uintptr_t>(act) | static_cast<uintptr_t>(lda)) & 1) == 0;
-  prm.gemm_staged = ((reinterpret_cast<uintptr_t>(act) | static_cast<uintptr_t>(lda)) & 15) == 0;
   prm.epi = *epi; prm.out = out; prm.lay = *layout;
-  return launch_tc(&plan->p, prm, false, static_cast<cudaStream_t>(stream));
+  const bool ring = ((reinterpret_cast<uintptr_t>(act) | static_cast<uintptr_t>(lda)) & 15) == 0;
+  if (ring) {   // 16-byte aligned rows: the loader warp streams them into the shared-memory ring
+    prm.ring_slots = accel::kMaxRingSlots;
+    prm.slot_bytes = accel::kGemmSlotBytes;
+    return launch_tc(&plan->p, prm, accel::kModeGemm, accel::kSmemRing + prm.ring_slots * prm.slot_bytes + accel::kRingSlack,
+                     static_cast<cudaStream_t>(stream));
+  }
+  return launch_tc(&plan->p, prm, accel::kModeDirect, accel::kSmemRing, static_cast<cudaStream_t>(stream));
 }
 
 int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const accel_conv_geom* g,
@@ -226,25 +331,41 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
   prm.Wo = (g->w + 2 * g->pad - g->ksize) / g->stride + 1;
   prm.x = input_nchw; prm.M = static_cast<int64_t>(g->batch) * prm.Ho * prm.Wo; prm.K = static_cast<int32_t>(K);
   prm.C = g->c_in; prm.H = g->h; prm.W = g->w; prm.ksz = g->ksize; prm.stride = g->stride; prm.pad = g->pad;
+  prm.conv = 1;
   prm.epi = *epi; prm.out = out; prm.lay = *layout;
-  if (g->ksize == 3 && g->pad <= 3) {
-    // shared-memory staging of the input rows one 14-channel stage needs: [14][halo_rows][3][pitch]
-    const int rows = (accel::kTileM - 1) / prm.Wo + 2;
-    const int pitch = ((g->w + 3) / 4) * 4 + 8;             // 4 zero bytes left, >= 4 right (pad <= 3)
-    const int bytes = ((14 * rows * 3 * pitch + 127) / 128) * 128;
-    const int wpr = (g->w + 3) / 4;
-    if (rows <= accel::kMaxHaloRows && bytes <= kMaxHaloBytes && wpr <= 32) {   // else: the general gather path
-      prm.halo_rows = rows; prm.halo_pitch = pitch; prm.halo_bytes = bytes;
-      int lpr = 1;
-      while (lpr < wpr) lpr <<= 1;
-      prm.halo_lpr = lpr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((g->ksize == 3 || g->ksize == 7) && g->pad <= 3) {
+    // Shared-memory ring of the input rows one stage needs: [channel plane][input row][pitch], each row once.
+    const int ks = g->ksize, gps = 126 / ks;
+    const int64_t out_rows_total = static_cast<int64_t>(g->batch) * prm.Ho;
+    int ro = (accel::kTileM - 1) / prm.Wo + 2;                       // output rows one 128-row tile can touch
+    if (ro > out_rows_total) ro = static_cast<int>(out_rows_total);
+    int ni = (ro - 1) / prm.Ho + 2;                                  // images it can touch
+    if (ni > ro) ni = ro;
+    const int extra = ks > g->stride ? ks - g->stride : 0;
+    const int hr = (ro - 1) * g->stride + (ni - 1) * extra + ks;      // input rows per channel plane (upper bound)
+    const int pitch = ((g->w + 3) / 4) * 4 + 8;                      // 4 zero bytes left, >= 4 right (pad <= 3)
+    const int nch = (gps % ks == 0) ? gps / ks : (gps + ks - 2) / ks + 1;
+    const int64_t slot = ((static_cast<int64_t>(nch) * hr * pitch + 15) / 16) * 16;
+    int slots = 0, budget = 0;
+    const int fixed = accel::kSmemRing + accel::kRingSlack;
+    if (fixed + 3 * slot <= kSmemTwoCtas) { slots = 3; budget = 2; }
+    else if (fixed + 2 * slot <= kSmemTwoCtas) { slots = 2; budget = 2; }
+    else if (fixed + 3 * slot <= kSmemOneCta) { slots = 3; budget = 1; }
+    else if (fixed + 2 * slot <= kSmemOneCta) { slots = 2; budget = 1; }
+    (void)budget;
+    if (slots && ro < accel::kMaxOutRows && hr <= accel::kMaxHaloRows) {
+      prm.ring_slots = slots; prm.slot_bytes = static_cast<int32_t>(slot);
+      prm.halo_rows = hr; prm.halo_pitch = pitch; prm.halo_nch = nch;
       // 4-byte async copies need 4-byte aligned global rows: W % 4 == 0 and a 4-byte aligned tensor base
       prm.halo_vec = (g->w % 4 == 0) && ((reinterpret_cast<uintptr_t>(input_nchw) & 3) == 0);
-      const unsigned per_ch = static_cast<unsigned>(rows * 3);
-      prm.halo_perch_magic = static_cast<uint32_t>(((1ull << 32) + per_ch - 1) / per_ch);
+      const unsigned wpr = static_cast<unsigned>((g->w + 3) / 4);
+      prm.wpr_magic = wpr > 1 ? static_cast<uint32_t>(((1ull << 32) + wpr - 1) / wpr) : 0u;
+      return launch_tc(&plan->p, prm, ks == 3 ? accel::kModeConv3 : accel::kModeConv7,
+                       fixed + slots * static_cast<int>(slot), st);
     }
   }
-  return launch_tc(&plan->p, prm, true, static_cast<cudaStream_t>(stream));
+  return launch_tc(&plan->p, prm, accel::kModeDirect, accel::kSmemRing, st);
 }
 
 int accel_bsr_gemm_generic(const int8_t* act, int64_t M, int64_t K, int64_t lda, const int32_t* row_ptr,

@@ -9,19 +9,24 @@
 //     columns [176, 248)      two activation stages of 9 K-tiles (16 bytes = 4 columns per tile, 14 data + 2 zero)
 // so two CTAs share an SM and overlap each other's prologue / epilogue.  Every stored block is a true
 // dense contraction, issued as (half of) one  tcgen05.mma.kind::i8  with A = activations FROM TMEM
-// (M=128), B = the block-row's 16x32 weight tile from shared memory (N=16, K=32 = two adjacent K tiles).
-// Measured on B200 (tools/probe): an SS-mode N=16 MMA is bound by the 4 KB shared-memory read of A
-// (~45 cycles); with A in TMEM and several issuing warps the same MMA sustains ~16 cycles.
+// (M=128), B = 16x32 weight tiles from shared memory (K=32 = two adjacent K tiles); block-rows that are
+// adjacent and use the same K window are issued together as one MMA with N = 16*len.
 //
-// Warp roles:
+// Warp roles (14 warps):
 //   warps 0-7   activation producers, thread = activation row (TMEM lane), two halves of 4 warps that own
-//               alternating stages.  GEMM: re-stride 14 -> 16 from the row-major activations.
-//               Conv: implicit im2col in the reference K order (c, kh, kw) - the input rows a stage needs
-//               are staged once in shared memory (coalesced, zero padded), then each thread walks its
-//               patch with a compile-time (3x3) or incremental (general) pattern and writes 16-byte
-//               tiles straight into TMEM with tcgen05.st.  Afterwards the same warps run the epilogue.
-//   warps 8..   MMA issuers (kIssuers warps, ops dealt round-robin) + TMEM allocation.
-//   last warp   weight loader: cp.async.bulk of pre-packed B-tile batches into a ring.
+//               alternating stages; they re-stride 14 -> 16 and write tiles into TMEM with tcgen05.st.
+//                 GEMM    rows come from a shared-memory ring filled by the activation loader (16-byte
+//                         cp.async), re-strided with compile-time byte permutes.
+//                 CONV<KS> implicit im2col in the reference K order (c, kh, kw): the input rows a stage needs
+//                         sit in a shared-memory ring (each input row once, zero padded); every (c, kh)
+//                         contributes KS contiguous bytes, merged with compile-time byte permutes.
+//                 DIRECT  any kernel size / unaligned tensors: per-element gather from global memory.
+//               Afterwards the same warps run the fused epilogue (per-channel constants cached in smem).
+//   warps 8-11  MMA issuers.  The whole issue loop runs on one elected thread in the uniform datapath:
+//               per MMA one 8-byte record from the kernel parameter bank, a handful of uniform ALU ops, UTCIMMA.
+//   warp 12     weight loader: cp.async.bulk of pre-packed B-tile batches into a 3-stage ring.
+//   warp 13     activation loader: cp.async (LDGSTS) of GEMM rows / conv input rows into the activation ring,
+//               running up to 3 stages ahead of the producers.
 #pragma once
 #include <climits>
 #include <cstdint>
@@ -36,21 +41,31 @@ namespace accel {
 constexpr int kTileM = 128;
 constexpr int kProducerWarps = 8;
 constexpr int kIssuers = 4;
-constexpr int kThreads = (kProducerWarps + kIssuers + 1) * 32;
-constexpr int kXStages = 2;
+constexpr int kWarpWLoad = kProducerWarps + kIssuers;
+constexpr int kWarpALoad = kWarpWLoad + 1;
+constexpr int kThreads = (kWarpALoad + 1) * 32;                 // 448
 constexpr int kWStages = 3;
+constexpr int kWStageBytes = kTilesPerBatch * kBTileBytes;      // 16 KB
 constexpr int kAccCols = kMaxGroupRows * kTile;                 // 176
 constexpr int kXStageCols = kChunkTiles * 4;                    // 36
 constexpr int kTmemCols = 256;
-static_assert(kAccCols + kXStages * kXStageCols <= kTmemCols, "TMEM budget");
-constexpr int kWStageBytes = (kBatchBytes + 127) / 128 * 128;
+static_assert(kAccCols + 2 * kXStageCols <= kTmemCols, "TMEM budget");
+constexpr int kMaxRingSlots = 3;
+constexpr int kMaxHaloRows = 48;                                // input rows held per channel plane
+constexpr int kMaxOutRows = 40;                                 // output rows touched by one 128-row tile
+constexpr int kGemmSlotBytes = kTileM * 144;                    // 128 rows x 9 x 16 B
+// shared-memory map
 constexpr int kSmemW = 0;
-constexpr int kSmemBar = kSmemW + kWStages * kWStageBytes;
-constexpr int kSmemTab = kSmemBar + 128;                        // per-halo-row (image, first input row) tables
-constexpr int kMaxHaloRows = 40;
-constexpr int kSmemHalo = kSmemBar + 128 + 2 * kMaxHaloRows * 4 + 64;   // two halo buffers follow (conv only)
-constexpr int kGemmStagePitch = 148;                            // 37 words: odd pitch -> conflict-free per-row reads
-constexpr int kGemmStageBytes = kTileM * kGemmStagePitch + 64;  // one staging buffer per producer half (GEMM only)
+constexpr int kSmemBar = kSmemW + kWStages * kWStageBytes;      // barriers (256 B)
+constexpr int kSmemScale = kSmemBar + 256;                      // float [176]
+constexpr int kSmemBias = kSmemScale + kAccCols * 4;            // int32 [176]
+constexpr int kSmemRowOff = kSmemBias + kAccCols * 4;           // int64 [kMaxHaloRows]
+constexpr int kSmemHBase = kSmemRowOff + kMaxHaloRows * 8;      // int32 [kMaxOutRows] halo row of out-row's first input row
+constexpr int kSmemOutRow = kSmemHBase + kMaxOutRows * 4;       // int32 [kMaxOutRows] image | flags
+constexpr int kSmemRing = (kSmemOutRow + kMaxOutRows * 4 + 127) / 128 * 128;
+constexpr int kRingSlack = 32;                                  // the gathers read whole words past a row's last byte
+
+enum TcMode { kModeGemm = 0, kModeConv3 = 1, kModeConv7 = 2, kModeDirect = 3 };
 
 struct TcParams {
   // activation source
@@ -58,132 +73,259 @@ struct TcParams {
   int64_t M;
   int32_t K;
   int64_t lda;
-  int32_t x_align2;  // GEMM: base pointer and lda are even -> 16-bit loads
-  int32_t gemm_staged;  // GEMM: base pointer and lda are multiples of 16 -> coalesced 16-byte loads via shared memory
-  // conv geometry (conv mode only)
+  int32_t x_align2;     // DIRECT GEMM: base pointer and lda are even -> 16-bit loads
+  int32_t conv;         // DIRECT: 0 = GEMM rows, 1 = convolution gather
+  // conv geometry
   int32_t C, H, W, ksz, stride, pad, Ho, Wo;
-  int32_t halo_pitch, halo_rows, halo_bytes;   // per producer half: [14 ch][halo_rows][ksz][halo_pitch]
-  int32_t halo_lpr, halo_vec;                  // lanes per halo row (pow2 >= words per row); rows are 4-byte copyable
-  uint32_t halo_perch_magic;                   // ceil(2^32 / (halo_rows*3)): row / per_ch by __umulhi
-  // plan
-  const uint8_t* ws;
-  const BatchInfo* batches;
-  const GroupInfo* groups;
-  int32_t n_groups;
+  // activation ring
+  int32_t ring_slots;   // 2 or 3
+  int32_t slot_bytes;   // bytes per ring slot (16-byte multiple)
+  int32_t halo_rows;    // allocated input rows per channel plane
+  int32_t halo_pitch;   // bytes per staged input row: 4 zero bytes, W data bytes, >= 4 zero bytes
+  int32_t halo_nch;     // channel planes per stage
+  int32_t halo_vec;     // rows are 4-byte copyable (W % 4 == 0, 4-byte aligned base)
+  uint32_t wpr_magic;   // ceil(2^32 / words_per_row)
+  // weights
+  const uint8_t* blob;
   // epilogue
   accel_epilogue epi;
+  int32_t res_fast;     // residual divide may use the 3-instruction exact sequence (checked on the host)
+  float res_rcp;        // RN(1 / res_scale_out)
   void* out;
   accel_out_layout lay;
 };
 
+struct TcLaunch {
+  TcParams p;
+  uint32_t n_groups;
+  uint32_t pad_;
+  GroupRec groups[kMaxGroupsL];
+  uint32_t batches[kMaxBatchesL];
+  OpRec ops[kMaxOpsL];
+};
+static_assert(sizeof(TcLaunch) <= 32764, "kernel parameter block too large");
+
 // ---------------------------------------------------------------------------------------------
-// Repack: 14x14 reference blocks -> 16x32 B tiles (canonical K-major core matrices) + op meta.
-// B tile bytes: [k_slot(2)][row(16)][16 B]; row n < 14 of slot s holds block row n (14 bytes).
-__global__ void repack_blocks_kernel(const int8_t* __restrict__ blocks, uint8_t* __restrict__ ws,
-                                     const OpSrc* __restrict__ op_src, const uint32_t* __restrict__ op_off,
-                                     const uint32_t* __restrict__ op_meta_off, const uint16_t* __restrict__ op_meta,
-                                     int64_t n_ops) {
-  const int64_t op = blockIdx.x;
-  if (op >= n_ops) return;
-  const OpSrc s = op_src[op];
-  uint8_t* dst = ws + op_off[op];
+// Repack: 14x14 reference blocks -> 16x32 B tiles.  B tile bytes: [row_group(2)][k_slot(2)][8 rows][16 B]
+// (K-major core matrices: LBO = 128 between the K halves, SBO = 256 between 8-row groups), so `len`
+// consecutive tiles form one N = 16*len operand.  Row n < 14 of slot s holds block row n (14 bytes).
+__global__ void repack_blocks_kernel(const int8_t* __restrict__ blocks, uint8_t* __restrict__ blob,
+                                     const TileSrc* __restrict__ src, int64_t n_tiles) {
+  const int64_t t = blockIdx.x;
+  if (t >= n_tiles) return;
+  const TileSrc s = src[t];
+  uint8_t* dst = blob + t * kBTileBytes;
   for (int i = threadIdx.x; i < kBTileBytes; i += blockDim.x) {
-    const int slot = i >> 8, row = (i >> 4) & 15, col = i & 15;
+    const int rg = i >> 8, slot = (i >> 7) & 1, r8 = (i >> 4) & 7, col = i & 15;
+    const int row = rg * 8 + r8;
     const int32_t blk = slot ? s.blk_hi : s.blk_lo;
     int8_t v = 0;
     if (blk >= 0 && row < kBlock && col < kBlock) v = blocks[static_cast<int64_t>(blk) * 196 + row * kBlock + col];
     dst[i] = static_cast<uint8_t>(v);
   }
-  if (threadIdx.x == 0) *reinterpret_cast<uint16_t*>(ws + op_meta_off[op]) = op_meta[op];
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int8_t sat8_count(int v, uint32_t& sat) {
-  if (v > 127) { ++sat; return 127; }
-  if (v < -128) { ++sat; return -128; }
-  return static_cast<int8_t>(v);
-}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ int8_t cvt_sat_s8(float f) {   // round-half-even + saturate in one instruction
+  int v;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(v) : "f"(f));
+  return static_cast<int8_t>(v);
+}
 
-// 3x3 fast path: one stage = 9 K tiles = 126 k = exactly 14 input channels x 9 taps, so the (channel, tap) ->
-// (tile, byte) map is a compile-time pattern.  `rowp` points at this thread's patch origin inside the halo.
-__device__ __forceinline__ void gather3x3_to_tmem(const uint8_t* rowp, int chan_stride, int pitch, uint32_t tcol) {
-  uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-  for (int c = 0; c < 14; ++c) {
-    const uint8_t* pc = rowp + c * chan_stride;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const uint8_t* pr = pc + kh * pitch;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int kl = c * 9 + kh * 3 + kw;        // compile-time
-        const int i = kl % 14;
-        const uint32_t b = pr[kw];
-        if ((i & 3) == 0) w[i >> 2] = b; else w[i >> 2] |= b << ((i & 3) * 8);
-        if (i == 13) {
-          tmem_st4(tcol + (kl / 14) * 4, w[0], w[1], w[2], w[3]);
-          w[3] = 0u;
-        }
-      }
-    }
+// ---- 14-in-16 tile stream: insert the `nb` bytes [src_byte, src_byte + nb) of `v` at stream byte `pos`.
+// Stream byte d lives in tile d / 14 at byte d % 14; a tile is 4 words, its bytes 14, 15 stay zero.
+template <int pos, int nb, int src_byte = 0>
+__device__ __forceinline__ void stream_insert(uint32_t (&w)[36], uint32_t v) {
+  if constexpr (nb > 0) {
+    constexpr int t = pos / 14, b = pos % 14;
+    constexpr int word = t * 4 + b / 4, byte = b % 4;
+    constexpr int room_w = 4 - byte, room_t = 14 - b;
+    constexpr int n = nb < room_w ? (nb < room_t ? nb : room_t) : (room_w < room_t ? room_w : room_t);
+    constexpr uint32_t sel = ((byte <= 0 && 0 < byte + n) ? (4u + src_byte + 0 - byte) : 0u) |
+                             (((byte <= 1 && 1 < byte + n) ? (4u + src_byte + 1 - byte) : 1u) << 4) |
+                             (((byte <= 2 && 2 < byte + n) ? (4u + src_byte + 2 - byte) : 2u) << 8) |
+                             (((byte <= 3 && 3 < byte + n) ? (4u + src_byte + 3 - byte) : 3u) << 12);
+    w[word] = __byte_perm(w[word], v, sel);
+    stream_insert<pos + n, nb - n, src_byte + n>(w, v);
+  }
+}
+template <int t0, int t1>
+__device__ __forceinline__ void stream_flush(const uint32_t (&w)[36], uint32_t xcol) {
+  if constexpr (t0 < t1) {
+    tmem_st4(xcol + t0 * 4, w[t0 * 4], w[t0 * 4 + 1], w[t0 * 4 + 2], w[t0 * 4 + 3]);
+    stream_flush<t0 + 1, t1>(w, xcol);
   }
 }
 
-template <bool kConv>
-__global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_constant__ TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
-  uint64_t* x_full = bars;                 // [2]  count 128 (one producer half)
-  uint64_t* x_empty = bars + 2;            // [2]  count kIssuers
-  uint64_t* w_full = bars + 4;             // [kWStages] count 1 (+tx bytes)
-  uint64_t* w_empty = w_full + kWStages;   // [kWStages] count kIssuers
-  uint64_t* acc_full = w_empty + kWStages; // [1]  count kIssuers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+// ---- CONV<KS>: one stage = 126 stream bytes = 126 / KS groups; group (c, kh) = KS contiguous bytes of one
+// staged input row.  `abase` = shared address of the aligned word that holds this thread's first tap of
+// (channel plane 0, this thread's first input row); `sh8` = 8 * (byte offset inside that word).
+template <int KS, int j, int e, int NG>
+__device__ __forceinline__ void conv_extract(uint32_t (&w)[36], const uint32_t (&g)[NG], uint32_t sh8) {
+  constexpr int NE = (KS + 3) / 4;          // extracted registers per group
+  if constexpr (e < NE) {
+    const uint32_t v = __funnelshift_r(g[e], g[e + 1], sh8);
+    stream_insert<j * KS + 4 * e, (KS - 4 * e) < 4 ? (KS - 4 * e) : 4>(w, v);
+    conv_extract<KS, j, e + 1, NG>(w, g, sh8);
+  }
+}
+template <int KS, int j>
+__device__ __forceinline__ void conv_group(uint32_t (&w)[36], uint32_t rp, uint32_t sh8, bool on) {
+  constexpr int NW = (KS + 3 + 3) / 4;      // words that can hold KS bytes at byte offset <= 3
+  uint32_t g[NW + 1];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) g[i] = on ? lds32(rp + 4 * i) : 0u;
+  g[NW] = 0u;
+  conv_extract<KS, j, 0, NW + 1>(w, g, sh8);
+}
 
-  const int warp = threadIdx.x >> 5;
+template <int KS, int j>
+__device__ __forceinline__ void conv_groups(uint32_t (&w)[36], uint32_t xcol, uint32_t& rp, uint32_t sh8, uint32_t pitch,
+                                            uint32_t cs, int& kh, int groups_left) {
+  constexpr int GPS = 126 / KS;
+  if constexpr (j < GPS) {
+    conv_group<KS, j>(w, rp, sh8, j < groups_left);
+    // next group: next input row of this channel, or first row of the next channel plane
+    if constexpr (GPS % KS == 0) {          // stage-aligned channels (3x3): compile-time pattern
+      rp += ((j % KS) == KS - 1) ? (cs - (KS - 1) * pitch) : pitch;
+    } else {
+      ++kh;
+      if (kh == KS) { kh = 0; rp += cs - (KS - 1) * pitch; } else { rp += pitch; }
+    }
+    stream_flush<(j * KS) / 14, ((j + 1) * KS) / 14>(w, xcol);
+    conv_groups<KS, j + 1>(w, xcol, rp, sh8, pitch, cs, kh, groups_left);
+  }
+}
+
+// ---- GEMM: this thread's 144-byte window (9 x 16 B, the row's K range rounded down to 16) -> 9 tiles.
+template <int SHIFT>
+__device__ __forceinline__ void gemm_restride(const uint32_t (&r)[37], uint32_t xcol) {
+#pragma unroll
+  for (int t = 0; t < kChunkTiles; ++t) {
+    uint32_t o[4];
+#pragma unroll
+    for (int jw = 0; jw < 4; ++jw) {
+      const int byte0 = SHIFT + 14 * t + 4 * jw;             // compile-time after unrolling
+      const int wi = byte0 >> 2, bs = byte0 & 3;
+      uint32_t v = bs == 0 ? r[wi] : __byte_perm(r[wi], r[wi + 1], 0x3210u + 0x1111u * bs);
+      if (jw == 3) v &= 0xffffu;                             // bytes 14, 15 of the tile are padding
+      o[jw] = v;
+    }
+    tmem_st4(xcol + t * 4, o[0], o[1], o[2], o[3]);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_constant__ TcLaunch L) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcParams& p = L.p;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+  uint64_t* x_full = bars;                      // [2]  count 4 (one elected lane per producer warp of the half)
+  uint64_t* x_empty = bars + 2;                 // [2]  count kIssuers
+  uint64_t* w_full = bars + 4;                  // [kWStages] count 1 (+tx bytes)
+  uint64_t* w_empty = w_full + kWStages;        // [kWStages] count kIssuers
+  uint64_t* acc_full = w_empty + kWStages;      // [1]  count kIssuers
+  uint64_t* h_full = acc_full + 1;              // [kMaxRingSlots] count 32 (loader lanes)
+  uint64_t* h_empty = h_full + kMaxRingSlots;   // [kMaxRingSlots] count 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + kMaxRingSlots);
+  float* s_scale = reinterpret_cast<float*>(smem + kSmemScale);
+  int32_t* s_bias = reinterpret_cast<int32_t*>(smem + kSmemBias);
+  int64_t* s_rowoff = reinterpret_cast<int64_t*>(smem + kSmemRowOff);
+  int32_t* s_hbase = reinterpret_cast<int32_t*>(smem + kSmemHBase);
+  int32_t* s_outrow = reinterpret_cast<int32_t*>(smem + kSmemOutRow);
+
+  constexpr bool kRing = (MODE != kModeDirect);
+  constexpr bool kHalo = (MODE == kModeConv3 || MODE == kModeConv7);
+  constexpr int KS = MODE == kModeConv7 ? 7 : 3;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int gi = blockIdx.x % p.n_groups;
-  const int64_t mtile = blockIdx.x / p.n_groups;
-  const GroupInfo G = p.groups[gi];
+  const uint32_t gi = blockIdx.x % L.n_groups;
+  const int64_t mtile = blockIdx.x / L.n_groups;
   const int64_t m0 = mtile * kTileM;
+  const uint32_t g_br0 = L.groups[gi].br0_rows & 0xffffu, g_rows = L.groups[gi].br0_rows >> 16;
+  const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 128); mbar_init(&x_empty[s], kIssuers); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 4); mbar_init(&x_empty[s], kIssuers); }
     for (int s = 0; s < kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kIssuers); }
     mbar_init(acc_full, kIssuers);
+    for (int s = 0; s < kMaxRingSlots; ++s) { mbar_init(&h_full[s], 32); mbar_init(&h_empty[s], 4); }
     fence_mbar_init();
   }
   if (warp == kProducerWarps) {
     tmem_alloc_dyn(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  int* tab_n = reinterpret_cast<int*>(smem + kSmemTab);        // image index of halo row rr (-1: past the batch)
-  int* tab_ih0 = tab_n + kMaxHaloRows;                          // first input row (oh*stride - pad) of halo row rr
-  if (kConv) {  // halo pads (left/right columns, rows never written) must read as zero
-    uint32_t* h = reinterpret_cast<uint32_t*>(smem + kSmemHalo);
-    for (int i = threadIdx.x; i < (2 * p.halo_bytes) / 4; i += kThreads) h[i] = 0u;
-    if (threadIdx.x < p.halo_rows) {
-      const int Rg = static_cast<int>(m0 / p.Wo) + threadIdx.x;
-      const int n = Rg / p.Ho;
-      tab_n[threadIdx.x] = (static_cast<int64_t>(n) * p.Ho * p.Wo < p.M) ? n : -1;
-      tab_ih0[threadIdx.x] = (Rg - n * p.Ho) * p.stride - p.pad;
+  // per-channel epilogue constants of this group
+  if (threadIdx.x < g_rows * kBlock) {
+    const int c = g_br0 * kBlock + threadIdx.x;
+    const bool ok = c < p.epi.n_channels;
+    s_scale[threadIdx.x] = (ok && p.epi.chan_scale) ? p.epi.chan_scale[c] : 0.f;
+    s_bias[threadIdx.x] = (ok && p.epi.bias) ? p.epi.bias[c] : 0;
+  }
+  int hr_used = 0;
+  if constexpr (kHalo) {
+    // ---- which input rows does this tile need?  Output rows R0.. (global row id n*Ho + oh); consecutive output
+    // rows of one image share input rows, so halo row ids advance by `stride`; a new image starts a fresh set.
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + kSmemRing);
+    const int ring_words = (p.ring_slots * p.slot_bytes + kRingSlack) >> 2;
+    for (int i = threadIdx.x; i < ring_words; i += kThreads) ring[i] = 0u;   // pads must read as zero
+    const int64_t R0 = m0 / p.Wo;
+    const int64_t m_last = (m0 + kTileM - 1 < p.M ? m0 + kTileM - 1 : p.M - 1);
+    const int n_out_rows = static_cast<int>(m_last / p.Wo - R0) + 1;
+    if (threadIdx.x == 0) {
+      int hb = 0;
+      int64_t prev_n = -1;
+      for (int rr = 0; rr < n_out_rows; ++rr) {
+        const int64_t Rg = R0 + rr;
+        const int64_t n = Rg / p.Ho;
+        if (rr > 0) hb += (n == prev_n) ? p.stride : max(p.ksz, p.stride);
+        s_hbase[rr] = hb;
+        s_outrow[rr] = static_cast<int32_t>(n);
+        prev_n = n;
+      }
+      s_hbase[kMaxOutRows - 1] = hb + p.ksz;   // rows in use
+    }
+    for (int i = threadIdx.x; i < kMaxHaloRows; i += kThreads) s_rowoff[i] = -1;
+    __syncthreads();
+    hr_used = s_hbase[kMaxOutRows - 1];
+    for (int i = threadIdx.x; i < n_out_rows * p.ksz; i += kThreads) {
+      const int rr = i / p.ksz, kh = i - rr * p.ksz;
+      const int64_t n = s_outrow[rr];
+      const int oh = static_cast<int>((R0 + rr) - n * p.Ho);
+      const int ih = oh * p.stride - p.pad + kh;
+      if (static_cast<unsigned>(ih) < static_cast<unsigned>(p.H))
+        s_rowoff[s_hbase[rr] + kh] = ((n * p.C) * p.H + ih) * static_cast<int64_t>(p.W);
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (warp < 4) {  // zero the accumulators: every MMA accumulates, so issue order across warps is free
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    for (int c = 0; c < G.n_rows * kTile; c += 4) tmem_st4(tmem_base + lane_base + c, 0u, 0u, 0u, 0u);
+    for (uint32_t c = 0; c < g_rows * kTile; c += 4) tmem_st4(tmem_base + lane_base + c, 0u, 0u, 0u, 0u);
     tmem_st_wait();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+
+  const uint32_t ring_addr = smem_u32(smem + kSmemRing);
 
   if (warp < kProducerWarps) {
     // =================================================================== activation producers
@@ -193,147 +335,99 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
     const uint32_t xcol = tmem_base + lane_base + kAccCols + half * kXStageCols;
     const int64_t m = m0 + tid;
     const bool row_ok = m < p.M;
-    // conv: this thread's output position and the tile's first output row
-    int64_t R0 = 0;
-    int rl = 0, ow = 0, oh = 0;
+    // conv: this thread's output position
+    int ow = 0, oh = 0;
     int64_t img = 0;
-    if (kConv) {
+    uint32_t thr_off = 0, sh8 = 0;
+    if (MODE != kModeGemm && (kHalo || p.conv)) {
       const int64_t P = static_cast<int64_t>(p.Ho) * p.Wo;
-      R0 = m0 / p.Wo;                                        // global output-row id (n*Ho + oh) of the tile start
       const int64_t mm = row_ok ? m : m0;
       const int64_t R = mm / p.Wo;
       ow = static_cast<int>(mm - R * p.Wo);
-      rl = static_cast<int>(R - R0);
       img = mm / P;
       oh = static_cast<int>(R - img * p.Ho);
+      if constexpr (kHalo) {
+        const int rr = static_cast<int>(R - m0 / p.Wo);
+        const uint32_t xb = static_cast<uint32_t>(ow * p.stride - p.pad + 4);
+        thr_off = static_cast<uint32_t>(s_hbase[rr]) * p.halo_pitch + (xb & ~3u);
+        sh8 = (xb & 3u) * 8u;
+      }
     }
-    uint8_t* halo = smem + kSmemHalo + half * p.halo_bytes;
-    int step = 0;
-    for (int b = G.batch_begin; b < G.batch_end; ++b) {
-      const BatchInfo bi = p.batches[b];
-      if (!(bi.flags & 1)) continue;            // one activation stage per K chunk
-      const int my = (step & 1) == half;
-      const int use = step >> 1;
+    uint32_t step = 0;
+    for (uint32_t b = g_bb; b < g_be; ++b) {
+      const uint32_t bw = L.batches[b];
+      if (!(bw & kBatchFirst)) continue;        // one activation stage per K chunk
+      const bool my = (step & 1u) == static_cast<uint32_t>(half);
+      const uint32_t use = step >> 1;
+      const uint32_t slot = step % static_cast<uint32_t>(kRing ? p.ring_slots : 1);
+      const uint32_t sphase = (step / static_cast<uint32_t>(kRing ? p.ring_slots : 1)) & 1u;
       ++step;
       if (!my) continue;
-      mbar_wait(&x_empty[half], (use & 1) ^ 1);
+      const int chunk = static_cast<int>(bw >> 16);
+      const int k_chunk0 = chunk * kChunkTiles * kBlock;
+      if constexpr (kRing) mbar_wait(&h_full[slot], sphase);
+      mbar_wait(&x_empty[half], (use & 1u) ^ 1u);
       tc_fence_after();
-      const int k_chunk0 = static_cast<int>(bi.chunk) * kChunkTiles * kBlock;
-      if (!kConv) {
-        // ---------------- GEMM rows: 9 tiles x 14 bytes, re-strided to 16.  Control flow is warp-uniform
-        // (tcgen05.st is .sync.aligned): rows past M load nothing but still store their zeros.
-        if (p.gemm_staged) {
-          // Coalesced path (16-byte aligned rows): the 128 x 144-byte window that covers this stage is pulled
-          // with 16-byte loads (9 consecutive lanes per row), parked in shared memory with an odd word pitch,
-          // then every thread re-strides its own row conflict-free.
-          uint8_t* stg = smem + kSmemHalo + half * kGemmStageBytes;
-          const int a0 = k_chunk0 & ~15;
-          const int shift = k_chunk0 - a0;                    // even, <= 14
-          uint4 v[kChunkTiles];
+      if constexpr (MODE == kModeGemm) {
+        // ---------------- GEMM rows from the ring: 9 x 16 B (pitch 144 B: conflict-free 16-byte reads)
+        const uint32_t src = ring_addr + slot * p.slot_bytes + tid * 144;
+        uint32_t r[37];
 #pragma unroll
-          for (int it = 0; it < kChunkTiles; ++it) {
-            const int item = it * 128 + tid;
-            const int row = item / kChunkTiles, ch = item - row * kChunkTiles;
-            const int64_t gm = m0 + row;
-            const int ka = a0 + ch * 16;
-            v[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (gm < p.M && ka < p.K) {
-              const int8_t* g = p.x + gm * p.lda + ka;
-              if (ka + 16 <= p.K) {
-                v[it] = *reinterpret_cast<const uint4*>(g);
-              } else {                                        // the one chunk per row that straddles K
-                uint32_t w[4] = {0u, 0u, 0u, 0u};
-                for (int j = 0; j < 16; ++j)
-                  if (ka + j < p.K) w[j >> 2] |= static_cast<uint32_t>(static_cast<uint8_t>(g[j])) << ((j & 3) * 8);
-                v[it] = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-            }
-          }
+        for (int i = 0; i < 9; ++i) {
+          const uint4 v = lds128(src + i * 16);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        r[36] = 0u;
+        switch (k_chunk0 & 15) {                 // 126 * chunk mod 16: even values only
+          case 0: gemm_restride<0>(r, xcol); break;
+          case 2: gemm_restride<2>(r, xcol); break;
+          case 4: gemm_restride<4>(r, xcol); break;
+          case 6: gemm_restride<6>(r, xcol); break;
+          case 8: gemm_restride<8>(r, xcol); break;
+          case 10: gemm_restride<10>(r, xcol); break;
+          case 12: gemm_restride<12>(r, xcol); break;
+          default: gemm_restride<14>(r, xcol); break;
+        }
+      } else if constexpr (kHalo) {
+        // ---------------- conv from the staged input rows
+        constexpr int GPS = 126 / KS;
+        const uint32_t cs = static_cast<uint32_t>(p.halo_rows) * p.halo_pitch;
+        const int g0 = chunk * GPS;                                   // first (c, kh) group of the stage
+        const int c_first = g0 / KS;
+        int kh = g0 - c_first * KS;
+        const int groups_left = p.C * KS - g0;                        // groups past the tensor contribute zeros
+        uint32_t rp = ring_addr + slot * p.slot_bytes + thr_off + kh * p.halo_pitch;
+        uint32_t w[36];
 #pragma unroll
-          for (int it = 0; it < kChunkTiles; ++it) {
-            const int item = it * 128 + tid;
-            const int row = item / kChunkTiles, ch = item - row * kChunkTiles;
-            uint32_t* d = reinterpret_cast<uint32_t*>(stg + row * kGemmStagePitch + ch * 16);
-            d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w;
-          }
-          named_bar_sync(1 + half, 128);
-          const uint16_t* s16 = reinterpret_cast<const uint16_t*>(stg + tid * kGemmStagePitch + shift);
+        for (int i = 0; i < 36; ++i) w[i] = 0u;
+        conv_groups<KS, 0>(w, xcol, rp, sh8, p.halo_pitch, cs, kh, groups_left);
+      } else if (!p.conv) {
+        // ---------------- DIRECT GEMM rows (unaligned base / leading dimension)
+        const int8_t* src = p.x + m * p.lda + k_chunk0;
+        if (p.x_align2 && k_chunk0 + kChunkTiles * kBlock <= p.K) {
+          const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
 #pragma unroll
           for (int t = 0; t < kChunkTiles; ++t) {
             uint32_t h[7];
 #pragma unroll
-            for (int j = 0; j < 7; ++j) h[j] = s16[t * 7 + j];
+            for (int j = 0; j < 7; ++j) h[j] = row_ok ? static_cast<uint32_t>(s16[t * 7 + j]) : 0u;
             tmem_st4(xcol + t * 4, h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6]);
           }
-          named_bar_sync(1 + half, 128);
         } else {
-          const int8_t* src = p.x + m * p.lda + k_chunk0;
-          if (p.x_align2 && k_chunk0 + kChunkTiles * kBlock <= p.K) {
-            const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
-#pragma unroll
-            for (int t = 0; t < kChunkTiles; ++t) {
-              uint32_t h[7];
-#pragma unroll
-              for (int j = 0; j < 7; ++j) h[j] = row_ok ? static_cast<uint32_t>(s16[t * 7 + j]) : 0u;
-              tmem_st4(xcol + t * 4, h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6]);
-            }
-          } else {
 #pragma unroll 1
-            for (int t = 0; t < kChunkTiles; ++t) {
-              uint32_t w[4] = {0u, 0u, 0u, 0u};
+          for (int t = 0; t < kChunkTiles; ++t) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-              for (int i = 0; i < kBlock; ++i) {
-                const int k = k_chunk0 + t * kBlock + i;
-                const uint32_t v = (row_ok && k < p.K) ? static_cast<uint32_t>(static_cast<uint8_t>(src[t * kBlock + i])) : 0u;
-                w[i >> 2] |= v << ((i & 3) * 8);
-              }
-              tmem_st4(xcol + t * 4, w[0], w[1], w[2], w[3]);
+            for (int i = 0; i < kBlock; ++i) {
+              const int k = k_chunk0 + t * kBlock + i;
+              const uint32_t v = (row_ok && k < p.K) ? static_cast<uint32_t>(static_cast<uint8_t>(src[t * kBlock + i])) : 0u;
+              w[i >> 2] |= v << ((i & 3) * 8);
             }
+            tmem_st4(xcol + t * 4, w[0], w[1], w[2], w[3]);
           }
         }
-      } else if (p.halo_bytes > 0) {
-        // ---------------- 3x3 conv: stage the 14 channels' input rows, then the compile-time gather
-        const int c0 = static_cast<int>(bi.chunk) * 14;
-        const int per_ch = p.halo_rows * 3;
-        const int wpr = (p.W + 3) >> 2;                       // 4-byte words per input row
-        const int total_rows = 14 * per_ch;
-        const int lpr = p.halo_lpr;                           // lanes per halo row (power of two >= wpr)
-        const int wl = tid & (lpr - 1);
-        const int rpp = 128 / lpr;                            // halo rows per pass
-        if (wl < wpr) {
-          for (int row = tid / lpr; row < total_rows; row += rpp) {
-            const int cl = __umulhi(static_cast<unsigned>(row), p.halo_perch_magic);   // row / per_ch
-            const int idx = row - cl * per_ch;
-            const int rr = idx / 3, kh = idx - rr * 3;
-            const int n = tab_n[rr];
-            const int ih = tab_ih0[rr] + kh;
-            const int c = c0 + cl;
-            const bool ok = c < p.C && n >= 0 && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H);
-            uint8_t* d = halo + row * p.halo_pitch + 4 + wl * 4;
-            if (p.halo_vec) {
-              // asynchronous 4-byte copies (LDGSTS), zero-filled for padding rows: nothing waits until the end
-              const int8_t* g = ok ? p.x + ((static_cast<int64_t>(n) * p.C + c) * p.H + ih) * p.W + wl * 4 : p.x;
-              cp_async4_zfill(d, g, ok);
-            } else {
-              uint32_t v = 0u;
-              if (ok) {
-                const int8_t* g = p.x + ((static_cast<int64_t>(n) * p.C + c) * p.H + ih) * p.W + wl * 4;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (wl * 4 + j < p.W) v |= static_cast<uint32_t>(static_cast<uint8_t>(g[j])) << (8 * j);
-              }
-              *reinterpret_cast<uint32_t*>(d) = v;
-            }
-          }
-        }
-        cp_async_wait_all();
-        named_bar_sync(1 + half, 128);
-        const int chan_stride = p.halo_rows * 3 * p.halo_pitch;
-        const uint8_t* rowp = halo + rl * 3 * p.halo_pitch + ow * p.stride + 4 - p.pad;
-        gather3x3_to_tmem(rowp, chan_stride, p.halo_pitch, xcol);
-        named_bar_sync(1 + half, 128);                        // halo is reused by this half's next stage
       } else {
-        // ---------------- general k x k (1x1 downsample, 7x7 stem): incremental (c, kh, kw) walk from global
+        // ---------------- DIRECT conv: any k x k, incremental (c, kh, kw) walk; a tile's 14 loads are independent
         int k = k_chunk0;
         const int kk = p.ksz * p.ksz;
         int c = k / kk;
@@ -343,73 +437,111 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
         const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
 #pragma unroll 1
         for (int t = 0; t < kChunkTiles; ++t) {
-          uint32_t w[4] = {0u, 0u, 0u, 0u};
+          uint32_t v[kBlock];
 #pragma unroll
           for (int i = 0; i < kBlock; ++i) {
-            uint32_t v = 0;
             const int ih = ih0 + kh, iw = iw0 + kw;
+            v[i] = 0u;
             if (row_ok && k < p.K && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
                 static_cast<unsigned>(iw) < static_cast<unsigned>(p.W))
-              v = static_cast<uint8_t>(im[(static_cast<int64_t>(c) * p.H + ih) * p.W + iw]);
-            w[i >> 2] |= v << ((i & 3) * 8);
+              v[i] = static_cast<uint8_t>(im[(static_cast<int64_t>(c) * p.H + ih) * p.W + iw]);
             ++k;
             if (++kw == p.ksz) { kw = 0; if (++kh == p.ksz) { kh = 0; ++c; } }
           }
+          uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int i = 0; i < kBlock; ++i) w[i >> 2] |= v[i] << ((i & 3) * 8);
           tmem_st4(xcol + t * 4, w[0], w[1], w[2], w[3]);
         }
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&x_full[half]);
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kRing) mbar_arrive(&h_empty[slot]);
+        mbar_arrive(&x_full[half]);
+      }
     }
 
     // =================================================================== epilogue (same 8 warps)
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const bool valid = row_ok;
     const int flags = p.epi.flags;
     int64_t out_base = 0;
-    if (valid) {
+    if (row_ok) {
       const int64_t im = m / p.lay.rows_per_image;
       out_base = im * p.lay.image_stride + (m - im * p.lay.rows_per_image) * p.lay.row_stride;
     }
+    const int8_t* __restrict__ resid = p.epi.residual;
     uint32_t sat = 0;
-    for (int g = half; g < G.n_rows; g += 2) {
+    for (uint32_t g = half; g < g_rows; g += 2) {
       uint32_t v[16];
       tmem_ld16(tmem_base + lane_base + g * kTile, v);
+      const int cb = (g_br0 + g) * kBlock;
+      const int n_ok = min(kBlock, p.epi.n_channels - cb);   // channels of this block-row that exist (warp-uniform)
+      const int64_t o0 = out_base + static_cast<int64_t>(cb) * p.lay.chan_stride;
+      int rv[kBlock];
+      if (resid && row_ok) {
+#pragma unroll
+        for (int h = 0; h < kBlock; ++h) rv[h] = h < n_ok ? static_cast<int>(resid[o0 + h * p.lay.chan_stride]) : 0;
+      }
       tmem_ld_wait();
-      const int cb = (G.br0 + g) * kBlock;
+      int acc[kBlock];
 #pragma unroll
       for (int h = 0; h < kBlock; ++h) {
-        const int c = cb + h;
-        const bool chan_ok = c < p.epi.n_channels;   // warp-uniform
-        int acc = static_cast<int>(v[h]);
-        if (chan_ok && p.epi.bias) acc += p.epi.bias[c];
-        if (flags & ACCEL_RELU) acc = max(acc, 0);
-        if (p.epi.chan_absmax && chan_ok) {
-          const int a = valid ? (acc < 0 ? (acc == INT_MIN ? INT_MAX : -acc) : acc) : 0;
+        acc[h] = static_cast<int>(v[h]) + s_bias[g * kBlock + h];
+        if (flags & ACCEL_RELU) acc[h] = max(acc[h], 0);
+      }
+      if (p.epi.chan_absmax) {
+#pragma unroll
+        for (int h = 0; h < kBlock; ++h) {
+          const int a = row_ok ? (acc[h] < 0 ? (acc[h] == INT_MIN ? INT_MAX : -acc[h]) : acc[h]) : 0;
           const int wmax = __reduce_max_sync(0xffffffffu, a);
-          if (lane == 0 && wmax > 0) atomicMax(p.epi.chan_absmax + c, wmax);
+          if (lane == 0 && wmax > 0 && h < n_ok) atomicMax(p.epi.chan_absmax + cb + h, wmax);
         }
-        if (!valid || !chan_ok) continue;
-        const int64_t o = out_base + static_cast<int64_t>(c) * p.lay.chan_stride;
-        if (flags & ACCEL_OUT_I32) {
-          reinterpret_cast<int32_t*>(p.out)[o] = acc;
-        } else if (flags & ACCEL_OUT_F32) {
-          reinterpret_cast<float*>(p.out)[o] = __fmul_rn(__int2float_rn(acc), p.epi.chan_scale[c]);
-        } else {
+      }
+      if (!row_ok) continue;
+      if (flags & ACCEL_OUT_I32) {
+        int32_t* o = reinterpret_cast<int32_t*>(p.out) + o0;
+#pragma unroll
+        for (int h = 0; h < kBlock; ++h)
+          if (h < n_ok) o[h * p.lay.chan_stride] = acc[h];
+      } else if (flags & ACCEL_OUT_F32) {
+        float* o = reinterpret_cast<float*>(p.out) + o0;
+#pragma unroll
+        for (int h = 0; h < kBlock; ++h)
+          if (h < n_ok) o[h * p.lay.chan_stride] = __fmul_rn(__int2float_rn(acc[h]), s_scale[g * kBlock + h]);
+      } else {
+        int8_t* o = reinterpret_cast<int8_t*>(p.out) + o0;
+#pragma unroll
+        for (int h = 0; h < kBlock; ++h) {
           // golden_models.cpp:378-411, per channel: one float32 multiply, round-half-even, saturate
-          const int q = __float2int_rn(__fmul_rn(__int2float_rn(acc), p.epi.chan_scale[c]));
-          int8_t q8 = sat8_count(q, sat);
-          if (p.epi.residual) {
-            // golden_models.cpp:465-490: (main*s_main + res*s_res) / s_out, float32, no FMA
-            const float a = __fmul_rn(__int2float_rn(q8), p.epi.res_scale_main);
-            const float r = __fmul_rn(__int2float_rn(p.epi.residual[o]), p.epi.res_scale_res);
-            const int z = __float2int_rn(__fdiv_rn(__fadd_rn(a, r), p.epi.res_scale_out));
-            q8 = static_cast<int8_t>(min(127, max(-128, z)));
+          const float f = __fmul_rn(__int2float_rn(acc[h]), s_scale[g * kBlock + h]);
+          int q;
+          if (p.epi.sat_count) {
+            const int qi = __float2int_rn(f);
+            q = min(127, max(-128, qi));
+            sat += (qi != q && h < n_ok) ? 1u : 0u;
+          } else {
+            q = cvt_sat_s8(f);
           }
-          if ((flags & ACCEL_RELU_OUT) && q8 < 0) q8 = 0;   // relu_int8, golden_models.cpp:278-283
-          reinterpret_cast<int8_t*>(p.out)[o] = q8;
+          if (resid) {
+            // golden_models.cpp:465-490: (main*s_main + res*s_res) / s_out, float32, no FMA in the sum
+            const float a = __fmul_rn(__int2float_rn(q), p.epi.res_scale_main);
+            const float r = __fmul_rn(__int2float_rn(rv[h]), p.epi.res_scale_res);
+            const float s = __fadd_rn(a, r);
+            float d;
+            if (p.res_fast) {   // correctly rounded quotient for every (int8, int8) pair: verified on the host
+              const float q0 = __fmul_rn(s, p.res_rcp);
+              const float e = __fmaf_rn(-q0, p.epi.res_scale_out, s);
+              d = __fmaf_rn(e, p.res_rcp, q0);
+            } else {
+              d = __fdiv_rn(s, p.epi.res_scale_out);
+            }
+            q = cvt_sat_s8(d);
+          }
+          if (flags & ACCEL_RELU_OUT) q = max(q, 0);          // relu_int8, golden_models.cpp:278-283
+          if (h < n_ok) o[h * p.lay.chan_stride] = static_cast<int8_t>(q);
         }
       }
     }
@@ -418,70 +550,147 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
       if (lane == 0 && wsum) atomicAdd(p.epi.sat_count, static_cast<unsigned long long>(wsum));
     }
     tc_fence_before();
-  } else if (warp < kProducerWarps + kIssuers) {
-    // =================================================================== MMA issuers
-    const int me = warp - kProducerWarps;
-    const uint32_t idesc = idesc_i8(kTileM, kTile);
-    int step = -1, wcount = 0, xs = 0;
-    for (int b = G.batch_begin; b < G.batch_end; ++b) {
-      const BatchInfo bi = p.batches[b];
-      if (bi.flags & 1) {
-        ++step;
-        xs = step & 1;
-        mbar_wait(&x_full[xs], (step >> 1) & 1);
-      }
-      const int ws_i = wcount % kWStages;
-      mbar_wait(&w_full[ws_i], (wcount / kWStages) & 1);
-      tc_fence_after();
-      const uint8_t* wst = smem + kSmemW + ws_i * kWStageBytes;
-      const uint32_t w_addr = smem_u32(wst);
-      // Lane-parallel decode: lane i owns op i of the batch; the issue loop only broadcasts one packed
-      // word per op (shfl -> warp-uniform -> uniform registers for the descriptors).
-      const int n_ops = bi.n_ops;
-      uint32_t mt = 0;
-      if (lane < n_ops) mt = reinterpret_cast<const uint16_t*>(wst + n_ops * kBTileBytes)[lane];
-      const uint32_t g = mt & 15u, win = mt >> 4;
-      // packed: bits 0..8 A column, bits 9..17 D column
-      const uint32_t packed = (kAccCols + xs * kXStageCols + win * 4) | ((g * kTile) << 9);
-      const uint64_t bdesc0 = smem_desc_kmajor(w_addr, 256, 128);
-#pragma unroll
-      for (int i = 0; i < kOpsPerBatch / kIssuers; ++i) {
-        const int op = i * kIssuers + me;                  // ops are dealt round-robin to the issuing warps
-        if (op < n_ops) {                                  // warp-uniform
-          const uint32_t pk = __shfl_sync(0xffffffffu, packed, op);
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((op * kBTileBytes) >> 4);
-          if (elect_one()) mma_i8_ts(tmem_base + (pk >> 9), tmem_base + (pk & 0x1FFu), bdesc, idesc, 1u);
+  } else if (warp < kWarpWLoad) {
+    // =================================================================== MMA issuers (uniform datapath)
+    const uint32_t me = static_cast<uint32_t>(warp - kProducerWarps);
+    if (elect_one()) {
+      const uint32_t idesc0 = idesc_i8(kTileM, 0);
+      const uint32_t w_addr = smem_u32(smem + kSmemW);
+      const uint64_t bdesc0 = smem_desc_kmajor(0, 128, 256);
+      const uint32_t bdesc_hi = static_cast<uint32_t>(bdesc0 >> 32);
+      const uint32_t bdesc_lo0 = static_cast<uint32_t>(bdesc0);
+      uint32_t step = 0, wcount = 0, xs = 0;
+      uint32_t opb = L.groups[gi].op_begin;
+      for (uint32_t b = g_bb; b < g_be; ++b) {
+        const uint32_t bw = L.batches[b];
+        if (bw & kBatchFirst) {
+          xs = step & 1u;
+          mbar_wait(&x_full[xs], (step >> 1) & 1u);
+          ++step;
         }
-      }
-      if (elect_one()) {
+        const uint32_t ws_i = wcount % kWStages;
+        mbar_wait(&w_full[ws_i], (wcount / kWStages) & 1u);
+        tc_fence_after();
+        const uint32_t n_runs = bw & 0xffu;
+        const uint32_t xa = tmem_base + kAccCols + xs * kXStageCols;
+        const uint32_t blo = bdesc_lo0 | (((w_addr + ws_i * kWStageBytes) >> 4) & 0x3FFFu);
+        for (uint32_t i = me; i < n_runs; i += kIssuers) {
+          const OpRec o = L.ops[opb + i];
+          const uint32_t d = tmem_base + (o.d_n & 0x1ffu);
+          const uint32_t idesc = idesc0 | (o.d_n & 0x7E0000u);
+          const uint32_t a = xa + (o.a_b & 0x1ffu);
+          const uint64_t bdesc = (static_cast<uint64_t>(bdesc_hi) << 32) | (blo + (o.a_b >> 16));
+          mma_i8_ts(d, a, bdesc, idesc, 1u);
+        }
+        opb += n_runs;
         mma_commit(&w_empty[ws_i]);
-        if (bi.flags & 2) mma_commit(&x_empty[xs]);
-        if (b == G.batch_end - 1) mma_commit(acc_full);
+        if (bw & kBatchLast) mma_commit(&x_empty[xs]);
+        if (b == g_be - 1) mma_commit(acc_full);
+        ++wcount;
       }
-      __syncwarp();
-      ++wcount;
+      if (g_bb == g_be) mbar_arrive(acc_full);  // nothing stored in this group: outputs are bias only
     }
-    if (G.batch_begin == G.batch_end) {
-      if (lane == 0) mbar_arrive(acc_full);  // nothing stored in this group: outputs are bias only
-      __syncwarp();
-    }
+    __syncwarp();
     tc_fence_before();
-  } else {
+  } else if (warp == kWarpWLoad) {
     // =================================================================== weight loader
     if (lane == 0) {
-      int wcount = 0;
-      for (int b = G.batch_begin; b < G.batch_end; ++b) {
-        const BatchInfo bi = p.batches[b];
-        const int ws_i = wcount % kWStages;
-        mbar_wait(&w_empty[ws_i], ((wcount / kWStages) & 1) ^ 1);
-        const uint32_t bytes = bi.n_ops * kBTileBytes + kBatchMetaBytes;
+      uint32_t wcount = 0;
+      const uint8_t* src = p.blob + static_cast<size_t>(L.groups[gi].blob_off16) * 16;
+      for (uint32_t b = g_bb; b < g_be; ++b) {
+        const uint32_t bw = L.batches[b];
+        const uint32_t ws_i = wcount % kWStages;
+        mbar_wait(&w_empty[ws_i], ((wcount / kWStages) & 1u) ^ 1u);
+        const uint32_t bytes = (((bw >> 8) & 0x3fu) + 1u) * kBTileBytes;
         mbar_arrive_expect_tx(&w_full[ws_i], bytes);
-        bulk_g2s(smem + kSmemW + ws_i * kWStageBytes, p.ws + static_cast<size_t>(bi.blob_off16) * 16, bytes,
-                 &w_full[ws_i]);
+        bulk_g2s(smem + kSmemW + ws_i * kWStageBytes, src, bytes, &w_full[ws_i]);
+        src += bytes;
         ++wcount;
       }
     }
     __syncwarp();
+  } else if (kRing) {
+    // =================================================================== activation loader
+    uint32_t step = 0;
+    for (uint32_t b = g_bb; b < g_be; ++b) {
+      const uint32_t bw = L.batches[b];
+      if (!(bw & kBatchFirst)) continue;
+      const uint32_t slot = step % static_cast<uint32_t>(p.ring_slots);
+      const uint32_t sphase = (step / static_cast<uint32_t>(p.ring_slots)) & 1u;
+      ++step;
+      mbar_wait(&h_empty[slot], sphase ^ 1u);
+      const int chunk = static_cast<int>(bw >> 16);
+      uint8_t* dst_slot = smem + kSmemRing + slot * p.slot_bytes;
+      if constexpr (MODE == kModeGemm) {
+        const int a0 = (chunk * kChunkTiles * kBlock) & ~15;
+#pragma unroll 4
+        for (int it = 0; it < 36; ++it) {
+          const int item = it * 32 + lane;
+          const int row = item / 9, ch = item - row * 9;
+          const int64_t gm = m0 + row;
+          const int ka = a0 + ch * 16;
+          int nbytes = p.K - ka;
+          nbytes = nbytes > 16 ? 16 : (nbytes < 0 ? 0 : nbytes);
+          if (gm >= p.M) nbytes = 0;
+          const int8_t* g = nbytes ? p.x + gm * p.lda + ka : p.x;
+          cp_async16_zfill(dst_slot + row * 144 + ch * 16, g, nbytes);
+        }
+        cp_async_mbar_arrive(&h_full[slot]);
+      } else {
+        constexpr int GPS = 126 / KS;
+        const int g0 = chunk * GPS;
+        const int c_first = g0 / KS;
+        const int wpr = (p.W + 3) >> 2;
+        const int items = hr_used * wpr;
+        const uint32_t cs = static_cast<uint32_t>(p.halo_rows) * p.halo_pitch;
+        const int64_t HW = static_cast<int64_t>(p.H) * p.W;
+        const int nch = min(p.halo_nch, p.C - c_first);
+        for (int idx = lane; idx < items; idx += 32) {
+          const int h = wpr > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), p.wpr_magic)) : idx;
+          const int wd = idx - h * wpr;
+          const int64_t off = s_rowoff[h];
+          uint8_t* d = dst_slot + h * p.halo_pitch + 4 + wd * 4;
+          if (p.halo_vec) {
+            const int8_t* g = off >= 0 ? p.x + off + c_first * HW + wd * 4 : p.x;
+            for (int c = 0; c < p.halo_nch; ++c) {
+              cp_async4_zfill(d, (off >= 0 && c < nch) ? g : p.x, off >= 0 && c < nch);
+              g += HW;
+              d += cs;
+            }
+          } else {
+            // rows at any byte alignment: aligned 32-bit loads, funnel shift, mask the row tail.  Channel planes
+            // are handled in batches so that the independent loads of a batch are all in flight together.
+            const int nb = min(4, p.W - wd * 4);
+            const uint32_t mask = nb >= 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
+            constexpr int kB = 7;
+            for (int c0 = 0; c0 < p.halo_nch; c0 += kB) {
+              uint32_t lo[kB], hi[kB], sh[kB];
+#pragma unroll
+              for (int i = 0; i < kB; ++i) {
+                const int c = c0 + i;
+                lo[i] = 0u; hi[i] = 0u; sh[i] = 0u;
+                if (off >= 0 && c < nch) {
+                  const uintptr_t a = reinterpret_cast<uintptr_t>(p.x + off + (c_first + c) * HW + wd * 4);
+                  const uint32_t* a4 = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+                  const uint32_t s = static_cast<uint32_t>(a & 3);
+                  sh[i] = s * 8;
+                  lo[i] = __ldg(a4);
+                  if (s + nb > 4) hi[i] = __ldg(a4 + 1);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < kB; ++i) {
+                if (c0 + i < p.halo_nch)
+                  *reinterpret_cast<uint32_t*>(d + (c0 + i) * cs) = __funnelshift_r(lo[i], hi[i], sh[i]) & mask;
+              }
+            }
+          }
+        }
+        if (p.halo_vec) cp_async_mbar_arrive(&h_full[slot]);
+        else mbar_arrive(&h_full[slot]);
+      }
+    }
+    cp_async_wait_all();
   }
 
   __syncthreads();

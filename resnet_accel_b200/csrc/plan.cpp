@@ -8,10 +8,88 @@ namespace accel {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int32_t tmem_cols_for(int32_t rows) {
-  (void)rows;
-  return 256;  // accumulators + two activation stages (bsr_tc.cuh)
+namespace {
+struct PendingTile {
+  int32_t g, win;
+  TileSrc src;
+};
+
+// One attempt with a fixed number of block-rows per group.  Returns false when a single group does not fit
+// the per-launch parameter tables (the caller retries with fewer rows per group).
+bool schedule(const int32_t* row_ptr, const int32_t* col_idx, int32_t nbr, int32_t nbc, int32_t rows_per, Plan* p) {
+  p->groups.clear(); p->batches.clear(); p->ops.clear(); p->tile_src.clear(); p->tile_dbg.clear();
+  const int32_t n_groups = nbr > 0 ? (nbr + rows_per - 1) / rows_per : 0;
+  std::vector<int32_t> cursor(kMaxGroupRows);
+  std::vector<PendingTile> tiles;
+  for (int32_t gi = 0; gi < n_groups; ++gi) {
+    GroupRec G{};
+    const int32_t br0 = gi * rows_per;
+    const int32_t n_rows = std::min(rows_per, nbr - br0);
+    G.br0_rows = static_cast<uint32_t>(br0) | (static_cast<uint32_t>(n_rows) << 16);
+    G.batch_begin = static_cast<uint32_t>(p->batches.size());
+    G.op_begin = static_cast<uint32_t>(p->ops.size());
+    G.blob_off16 = static_cast<uint32_t>(p->tile_src.size() * (kBTileBytes / 16));
+    for (int g = 0; g < n_rows; ++g) cursor[g] = row_ptr[br0 + g];
+    for (int32_t kc = 0; kc < p->n_chunks; ++kc) {
+      const int32_t t_lo = kc * kChunkTiles, t_hi = std::min(nbc, t_lo + kChunkTiles);
+      tiles.clear();
+      for (int g = 0; g < n_rows; ++g) {
+        const int32_t end = row_ptr[br0 + g + 1];
+        int32_t j = cursor[g];
+        while (j < end && col_idx[j] < t_hi) {
+          const int32_t t = col_idx[j] - t_lo;  // tile inside the chunk
+          PendingTile pt{g, 0, {-1, -1}};
+          if (j + 1 < end && col_idx[j + 1] == col_idx[j] + 1 && col_idx[j + 1] < t_hi) {
+            pt.src.blk_lo = j; pt.src.blk_hi = j + 1; pt.win = t; j += 2;   // adjacent pair: one K=32 slice
+          } else if (t + 1 < kChunkTiles) {
+            pt.src.blk_lo = j; pt.win = t; j += 1;                          // lone block in K slot 0
+          } else {
+            pt.src.blk_hi = j; pt.win = t - 1; j += 1;                      // last tile of the chunk: K slot 1
+          }
+          tiles.push_back(pt);
+        }
+        cursor[g] = j;
+      }
+      if (tiles.empty()) continue;
+      // (window, block-row) order: adjacent block-rows that share a window become one wide MMA
+      std::stable_sort(tiles.begin(), tiles.end(), [](const PendingTile& a, const PendingTile& b) {
+        return a.win != b.win ? a.win < b.win : a.g < b.g;
+      });
+      const size_t first_batch = p->batches.size();
+      for (size_t i0 = 0; i0 < tiles.size(); i0 += kTilesPerBatch) {
+        const size_t n = std::min<size_t>(kTilesPerBatch, tiles.size() - i0);
+        uint32_t runs = 0;
+        for (size_t i = 0; i < n;) {
+          size_t len = 1;
+          while (i + len < n && tiles[i0 + i + len].win == tiles[i0 + i].win &&
+                 tiles[i0 + i + len].g == tiles[i0 + i].g + static_cast<int32_t>(len))
+            ++len;
+          OpRec op;
+          op.d_n = static_cast<uint32_t>(tiles[i0 + i].g * kTile) | (static_cast<uint32_t>(2 * len) << 17);
+          op.a_b = static_cast<uint32_t>(tiles[i0 + i].win * 4) | (static_cast<uint32_t>(i * (kBTileBytes / 16)) << 16);
+          p->ops.push_back(op);
+          ++runs;
+          i += len;
+        }
+        for (size_t i = 0; i < n; ++i) {
+          p->tile_src.push_back(tiles[i0 + i].src);
+          p->tile_dbg.push_back(gi); p->tile_dbg.push_back(tiles[i0 + i].g); p->tile_dbg.push_back(kc);
+          p->tile_dbg.push_back(tiles[i0 + i].win);
+        }
+        p->batches.push_back(runs | (static_cast<uint32_t>(n - 1) << 8) | (static_cast<uint32_t>(kc) << 16));
+      }
+      p->batches[first_batch] |= kBatchFirst;
+      p->batches.back() |= kBatchLast;
+    }
+    G.batch_end = static_cast<uint32_t>(p->batches.size());
+    if (G.batch_end - G.batch_begin > static_cast<uint32_t>(kMaxBatchesL) ||
+        p->ops.size() - G.op_begin > static_cast<size_t>(kMaxOpsL))
+      return false;
+    p->groups.push_back(G);
+  }
+  return true;
 }
+}  // namespace
 
 std::string build_plan(const int32_t* row_ptr, const int32_t* col_idx, int32_t nbr, int32_t nbc, Plan* p) {
   // ---- structure validation: the rules of validate_bsr (hw/sim/cpp/include/bsr_packer.hpp:364-436)
@@ -31,119 +109,26 @@ std::string build_plan(const int32_t* row_ptr, const int32_t* col_idx, int32_t n
       prev = c;
     }
   }
+  if (nbc > 65535 * kChunkTiles) return "too many K tiles for the tensor-core schedule";
 
   p->nbr = nbr;
   p->nbc = nbc;
   p->nnz = nnz;
   p->n_chunks = (nbc + kChunkTiles - 1) / kChunkTiles;
-  int32_t want = p->group_rows > 0 ? std::min(p->group_rows, kMaxGroupRows) : kDefaultGroupRows;
-  const int32_t n_groups = nbr > 0 ? (nbr + want - 1) / want : 0;
-  const int32_t rows_per = n_groups ? (nbr + n_groups - 1) / n_groups : 0;  // balanced split
-  p->group_rows = rows_per;
-
-  p->groups.clear(); p->batches.clear(); p->op_meta.clear(); p->op_src.clear();
-  p->op_blob_off.clear(); p->op_meta_off.clear();
-
-  size_t blob_bytes = 0;
-  std::vector<int32_t> cursor(kMaxGroupRows);
-  for (int32_t gi = 0; gi < n_groups; ++gi) {
-    GroupInfo G{};
-    G.br0 = gi * rows_per;
-    G.n_rows = std::min(rows_per, nbr - G.br0);
-    G.tmem_cols = tmem_cols_for(G.n_rows);
-    G.batch_begin = static_cast<int32_t>(p->batches.size());
-    for (int g = 0; g < G.n_rows; ++g) {
-      cursor[g] = row_ptr[G.br0 + g];
-      if (row_ptr[G.br0 + g + 1] > row_ptr[G.br0 + g]) G.nonempty |= (1u << g);
-    }
-    for (int32_t kc = 0; kc < p->n_chunks; ++kc) {
-      const int32_t t_lo = kc * kChunkTiles, t_hi = std::min(nbc, t_lo + kChunkTiles);
-      const size_t first_batch_of_chunk = p->batches.size();
-      int ops_in_batch = 0;
-      auto open_batch = [&]() {
-        BatchInfo b{};
-        b.blob_off16 = static_cast<uint32_t>(blob_bytes / 16);
-        b.chunk = static_cast<uint16_t>(kc);
-        b.n_ops = 0;
-        b.flags = 0;
-        p->batches.push_back(b);
-        ops_in_batch = 0;
-      };
-      auto close_batch = [&]() {
-        BatchInfo& b = p->batches.back();
-        b.n_ops = static_cast<uint8_t>(ops_in_batch);
-        // meta u16s sit right behind the tiles of the batch
-        const size_t tiles = static_cast<size_t>(ops_in_batch) * kBTileBytes;
-        const size_t base = static_cast<size_t>(b.blob_off16) * 16;
-        for (int i = 0; i < ops_in_batch; ++i)
-          p->op_meta_off[p->op_meta_off.size() - ops_in_batch + i] = static_cast<uint32_t>(base + tiles + 2 * i);
-        blob_bytes = base + tiles + kBatchMetaBytes;
-      };
-      // Per block-row op lists of this chunk, then emitted round-robin across block-rows: consecutive
-      // tcgen05.mma instructions then target different TMEM accumulators, so the small N=16 MMAs do not
-      // serialise on the accumulate dependency of a single block-row.
-      struct PendingOp { OpSrc src; int32_t win; };
-      std::vector<std::vector<PendingOp>> per_row(G.n_rows);
-      for (int g = 0; g < G.n_rows; ++g) {
-        const int32_t end = row_ptr[G.br0 + g + 1];
-        int32_t j = cursor[g];
-        while (j < end && col_idx[j] < t_hi) {
-          const int32_t t = col_idx[j] - t_lo;  // tile inside the chunk
-          PendingOp op{{-1, -1}, 0};
-          if (j + 1 < end && col_idx[j + 1] == col_idx[j] + 1 && col_idx[j + 1] < t_hi) {
-            op.src.blk_lo = j; op.src.blk_hi = j + 1; op.win = t; j += 2;   // adjacent pair: one MMA
-          } else if (t + 1 < kChunkTiles) {
-            op.src.blk_lo = j; op.win = t; j += 1;                          // lone block in K slot 0
-          } else {
-            op.src.blk_hi = j; op.win = t - 1; j += 1;                      // last tile of the chunk: K slot 1
-          }
-          per_row[g].push_back(op);
-        }
-        cursor[g] = j;
-      }
-      bool any = false;
-      for (size_t depth = 0;; ++depth) {
-        bool found = false;
-        for (int g = 0; g < G.n_rows; ++g) {
-          if (depth >= per_row[g].size()) continue;
-          found = true;
-          if (!any || ops_in_batch == kOpsPerBatch) {
-            if (any) close_batch();
-            open_batch();
-            any = true;
-          }
-          const PendingOp& op = per_row[g][depth];
-          const BatchInfo& b = p->batches.back();
-          p->op_src.push_back(op.src);
-          p->op_meta.push_back(static_cast<uint16_t>((g & 15) | (op.win << 4)));
-          p->op_blob_off.push_back(static_cast<uint32_t>(static_cast<size_t>(b.blob_off16) * 16 +
-                                                         static_cast<size_t>(ops_in_batch) * kBTileBytes));
-          p->op_meta_off.push_back(0);
-          ++ops_in_batch;
-        }
-        if (!found) break;
-      }
-      if (any) {
-        close_batch();
-        p->batches[first_batch_of_chunk].flags |= 1;
-        p->batches.back().flags |= 2;
-        ++G.n_steps;
-      }
-    }
-    G.batch_end = static_cast<int32_t>(p->batches.size());
-    p->groups.push_back(G);
+  int32_t want = p->group_rows > 0 ? std::min(p->group_rows, kMaxGroupRows) : kMaxGroupRows;
+  for (;; --want) {
+    if (want < 1) return "matrix too large for the tensor-core schedule (one block-row exceeds the launch tables)";
+    const int32_t n_groups = nbr > 0 ? (nbr + want - 1) / want : 0;
+    const int32_t rows_per = n_groups ? (nbr + n_groups - 1) / n_groups : 0;  // balanced split
+    p->group_rows = rows_per;
+    if (n_groups == 0 || schedule(row_ptr, col_idx, nbr, nbc, rows_per, p)) break;
   }
-  p->n_ops = static_cast<int64_t>(p->op_src.size());
+  p->n_tiles = static_cast<int64_t>(p->tile_src.size());
 
-  // ---- device workspace layout
+  // ---- device workspace layout: the B-tile blob and the repack source list
   size_t off = 0;
-  p->off_blob = off;     off = align_up(off + std::max<size_t>(blob_bytes, 16), 256);
-  p->off_batches = off;  off = align_up(off + std::max<size_t>(p->batches.size(), 1) * sizeof(BatchInfo), 256);
-  p->off_groups = off;   off = align_up(off + std::max<size_t>(p->groups.size(), 1) * sizeof(GroupInfo), 256);
-  p->off_opsrc = off;    off = align_up(off + std::max<size_t>(p->op_src.size(), 1) * sizeof(OpSrc), 256);
-  p->off_opoff = off;    off = align_up(off + std::max<size_t>(p->op_blob_off.size(), 1) * sizeof(uint32_t), 256);
-  p->off_opmoff = off;   off = align_up(off + std::max<size_t>(p->op_meta_off.size(), 1) * sizeof(uint32_t), 256);
-  p->off_opmeta = off;   off = align_up(off + std::max<size_t>(p->op_meta.size(), 1) * sizeof(uint16_t), 256);
+  p->off_blob = off;     off = align_up(off + std::max<size_t>(p->tile_src.size() * kBTileBytes, 16), 256);
+  p->off_tilesrc = off;  off = align_up(off + std::max<size_t>(p->tile_src.size(), 1) * sizeof(TileSrc), 256);
   p->ws_bytes = off;
   return std::string();
 }

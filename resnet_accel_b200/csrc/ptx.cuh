@@ -68,6 +68,15 @@ __device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gmem
                : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// 16-byte copy of which the first `src_bytes` (0..16) come from global memory, the rest is zero-filled
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+// the mbarrier receives one arrival (of its expected count) once all earlier cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // ----------------------------------------------------------------------------- bulk async copy (global -> smem)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

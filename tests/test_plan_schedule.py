@@ -25,8 +25,28 @@ def _export(rp, ci, nbr, nbc, group_rows=0):
     rec = np.zeros((max(n, 1), 8), np.int32)
     L.accel_plan_export_ops(h, rec.ctypes.data, n)
     nblk = L.accel_plan_num_blocks(h)
+    nm = L.accel_plan_export_mma(h, None, 0)
+    mma = np.zeros((max(nm, 1), 8), np.int32)
+    L.accel_plan_export_mma(h, mma.ctypes.data, nm)
+    assert nm == L.accel_plan_num_mma(h) and n == L.accel_plan_num_tiles(h)
     L.accel_plan_destroy(h)
+    _check_mma_cover(rec[:n], mma[:nm])
     return rec[:n], nblk, ws.value
+
+
+def _check_mma_cover(rec, mma):
+    """Every weight tile is covered by exactly one tcgen05.mma record, and a wide MMA (N = 16*len) only merges
+    tiles of adjacent block-rows that share group, batch, K chunk and window."""
+    covered = np.zeros(len(rec), np.int32)
+    for grp, batch, dcol, N, acol, tile0, chunk, br0 in mma:
+        assert N % 16 == 0 and 16 <= N <= 176 and dcol % 16 == 0 and dcol + N <= 176
+        assert acol % 4 == 0 and 0 <= acol // 4 <= CHUNK - 2
+        for i in range(N // 16):
+            t = rec[tile0 + i]
+            assert (t[0], t[1], t[2], t[3], t[4], t[7]) == (grp, br0, dcol // 16 + i, chunk, acol // 4, batch)
+            covered[tile0 + i] += 1
+    assert np.all(covered == 1)
+    assert len(mma) <= len(rec)
 
 
 def _replay(A, rec, blocks, nbr, nbc):
