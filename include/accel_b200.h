@@ -48,15 +48,21 @@ enum {
   ACCEL_RELU_OUT = 1 << 4   /* relu_int8 on the final int8 value (after the residual add, golden_models.cpp:278) */
 };
 
-/* Where activation row m, output channel c lands:
- *   out[(m / rows_per_image) * image_stride + c * chan_stride + (m % rows_per_image) * row_stride]
+/* Where activation row m, output channel c lands (pix = m % rows_per_image):
+ *   row_len == 0:  out[(m / rows_per_image) * image_stride + c * chan_stride + pix * row_stride]
+ *   row_len  > 0:  out[(m / rows_per_image) * image_stride + c * chan_stride
+ *                      + (pix / row_len) * row_pitch + (pix % row_len) * row_stride]
  * Row-major [M, ld]:  rows_per_image = M, image_stride = 0, chan_stride = 1, row_stride = ld.
- * NCHW conv output:   rows_per_image = Ho*Wo, image_stride = Cout*Ho*Wo, chan_stride = Ho*Wo, row_stride = 1. */
+ * NCHW conv output:   rows_per_image = Ho*Wo, image_stride = Cout*Ho*Wo, chan_stride = Ho*Wo, row_stride = 1.
+ * NCHW with padded rows (pitch Wp >= Wo, e.g. a multiple of 16 so that the next layer can stream rows with
+ * 16-byte copies): row_len = Wo, row_pitch = Wp, chan_stride = Ho*Wp, image_stride = Cout*Ho*Wp. */
 typedef struct accel_out_layout {
   int64_t rows_per_image;
   int64_t image_stride;
   int64_t chan_stride;
   int64_t row_stride;
+  int64_t row_len;
+  int64_t row_pitch;
 } accel_out_layout;
 
 typedef struct accel_epilogue {
@@ -77,6 +83,7 @@ typedef struct accel_epilogue {
 typedef struct accel_conv_geom {
   int32_t batch, c_in, h, w;
   int32_t ksize, stride, pad;
+  int32_t in_row_pitch; /* bytes between input rows (>= w); 0 = w.  Planes / images are dense in that pitch. */
 } accel_conv_geom;
 
 typedef struct accel_plan accel_plan; /* opaque: host-side schedule of one BSR weight matrix */
@@ -86,6 +93,10 @@ ACCEL_API const char* accel_last_error_string(void);
 ACCEL_API const char* accel_version(void);
 /* 0 if a sm_100 device is current and the tcgen05 path can run, else ACCEL_INIT_FAILED. */
 ACCEL_API int accel_device_check(void);
+/* Developer aid: while non-NULL, every tensor-core launch writes 8 clock64 stamps per CTA into `dev_buffer`
+ * (kernel entry, prologue done, first activation stage acquired / published, main loop done by the producers,
+ * accumulators complete, epilogue done, CTA exit).  The buffer must hold 8 int64 per CTA of the largest launch. */
+ACCEL_API void accel_debug_set_timeline(long long* dev_buffer);
 
 /* --- weight plan: replaces AccelDriver.load_sparse_weights (sw/host/accel.py:177-236) and
  *     AcceleratorDriver::set_layer_weights / load_weights_bsr (accelerator_driver.cpp:643-760).
@@ -160,9 +171,11 @@ ACCEL_API int accel_requant_i32_i8(const int32_t* acc, int8_t* out, int64_t n_ou
                          accel_stream_t stream);
 ACCEL_API int accel_add_residual_i8(const int8_t* main_, const int8_t* res, int8_t* out, int64_t n, float s_main, float s_res,
                           float s_out, accel_stream_t stream);
+/* in_pitch / out_pitch: bytes between rows of the input / output planes (0 = dense) */
 ACCEL_API int accel_maxpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, int32_t pool,
-                     int32_t stride, int32_t pad, accel_stream_t stream);
-ACCEL_API int accel_avgpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, accel_stream_t stream);
+                     int32_t stride, int32_t pad, int32_t in_pitch, int32_t out_pitch, accel_stream_t stream);
+ACCEL_API int accel_avgpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, int32_t in_pitch,
+                     accel_stream_t stream);
 
 #ifdef __cplusplus
 }

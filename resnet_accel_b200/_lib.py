@@ -29,7 +29,7 @@ class AcceleratorError(RuntimeError):
 
 class OutLayout(C.Structure):
     _fields_ = [("rows_per_image", C.c_int64), ("image_stride", C.c_int64), ("chan_stride", C.c_int64),
-                ("row_stride", C.c_int64)]
+                ("row_stride", C.c_int64), ("row_len", C.c_int64), ("row_pitch", C.c_int64)]
 
 
 class Epilogue(C.Structure):
@@ -40,7 +40,7 @@ class Epilogue(C.Structure):
 
 class ConvGeom(C.Structure):
     _fields_ = [("batch", C.c_int32), ("c_in", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
-                ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32)]
+                ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("in_row_pitch", C.c_int32)]
 
 
 # every symbol include/accel_b200.h declares: name -> (restype, argtypes)
@@ -49,6 +49,7 @@ SYMBOLS = {
     "accel_last_error_string": (C.c_char_p, []),
     "accel_version": (C.c_char_p, []),
     "accel_device_check": (C.c_int, []),
+    "accel_debug_set_timeline": (None, [_P]),
     "accel_plan_create": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, C.POINTER(_P), C.POINTER(_SZ)]),
     "accel_plan_upload": (C.c_int, [_P, _P, _P, _SZ, _P]),
     "accel_plan_destroy": (None, [_P]),
@@ -70,8 +71,8 @@ SYMBOLS = {
     "accel_row_absmax_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
     "accel_requant_i32_i8": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I32, _P, _P]),
     "accel_add_residual_i8": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, _P]),
-    "accel_maxpool_i8": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
-    "accel_avgpool_i8": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
+    "accel_maxpool_i8": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "accel_avgpool_i8": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
 }
 
 _lib = None

@@ -5,6 +5,7 @@
 #include <array>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -49,6 +50,8 @@ int grid_for(int64_t work_items, int threads, int per_sm = 8) {
   return static_cast<int>(g < 1 ? 1 : g);
 }
 
+long long* g_timeline = nullptr;   // accel_debug_set_timeline
+int g_dbg_flags = 0;
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
 constexpr int kSmemTwoCtas = 113 * 1024;    // per CTA when two CTAs share an SM (227 KB usable, 1 KB reserved each)
@@ -129,6 +132,8 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cu
   const int64_t m_tiles = (prm.M + accel::kTileM - 1) / accel::kTileM;
   if (n_groups == 0 || m_tiles == 0) return ACCEL_OK;
   prm.blob = P->ws_dev + P->off_blob;
+  prm.timeline = g_timeline;
+  prm.dbg_flags = g_dbg_flags;
   if (prm.epi.residual) {
     prm.res_fast = residual_fast_divide_ok(prm.epi.res_scale_main, prm.epi.res_scale_res, prm.epi.res_scale_out) ? 1 : 0;
     prm.res_rcp = 1.0f / prm.epi.res_scale_out;
@@ -181,6 +186,12 @@ extern "C" {
 
 const char* accel_last_error_string(void) { return g_err.c_str(); }
 const char* accel_version(void) { return "accel_b200 0.1 (sm_100a, tcgen05 kind::i8)"; }
+
+void accel_debug_set_timeline(long long* dev_buffer) {
+  g_timeline = dev_buffer;
+  const char* f = std::getenv("ACCEL_DBG_FLAGS");
+  g_dbg_flags = f ? std::atoi(f) : 0;
+}
 
 int accel_device_check(void) {
   int dev = 0;
@@ -289,6 +300,7 @@ int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64_t M, int6
   if (!plan) return fail(ACCEL_INVALID_CONFIG, "null plan");
   if (!plan->p.uploaded) return fail(ACCEL_NOT_READY, "Weights not loaded");  // accel.py:296
   if (M < 0 || K < 0 || lda < K) return fail(ACCEL_INVALID_CONFIG, "bad activation shape");
+  if (M > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "more than 2^31 activation rows");
   if (M > 0 && !act) return fail(ACCEL_INVALID_CONFIG, "Activations not loaded");  // accel.py:297
   if (K > INT_MAX / 2) return fail(ACCEL_INVALID_CONFIG, "K too large");
   // accumulator overflow guard (SURVEY.md hard part 7): |acc| <= K*128*128 must stay below 2^31
@@ -331,6 +343,9 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
   prm.Wo = (g->w + 2 * g->pad - g->ksize) / g->stride + 1;
   prm.x = input_nchw; prm.M = static_cast<int64_t>(g->batch) * prm.Ho * prm.Wo; prm.K = static_cast<int32_t>(K);
   prm.C = g->c_in; prm.H = g->h; prm.W = g->w; prm.ksz = g->ksize; prm.stride = g->stride; prm.pad = g->pad;
+  prm.Wp = g->in_row_pitch > 0 ? g->in_row_pitch : g->w;
+  if (prm.Wp < g->w) return fail(ACCEL_INVALID_CONFIG, "in_row_pitch smaller than the row");
+  if (prm.M > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "more than 2^31 output positions");
   prm.conv = 1;
   prm.epi = *epi; prm.out = out; prm.lay = *layout;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -344,23 +359,33 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
     if (ni > ro) ni = ro;
     const int extra = ks > g->stride ? ks - g->stride : 0;
     const int hr = (ro - 1) * g->stride + (ni - 1) * extra + ks;      // input rows per channel plane (upper bound)
-    const int pitch = ((g->w + 3) / 4) * 4 + 8;                      // 4 zero bytes left, >= 4 right (pad <= 3)
+    // copy granularity: 16-byte cp.async when every input row starts 16-byte aligned, 4-byte cp.async when rows
+    // are 4-byte aligned, else 32-bit loads through registers
+    const uintptr_t xa = reinterpret_cast<uintptr_t>(input_nchw);
+    const int vec = ((xa | static_cast<uintptr_t>(prm.Wp)) & 15) == 0 ? 16
+                    : (((xa | static_cast<uintptr_t>(prm.Wp)) & 3) == 0 && g->w % 4 == 0) ? 4 : 0;
+    int pitch, lpad, ipr;
+    if (vec == 16) {
+      const int w16 = ((g->w + 15) / 16) * 16;
+      lpad = 16; ipr = w16 / 16;
+      pitch = 16 + w16 + ((w16 - g->w >= g->pad) ? 0 : 16);
+    } else {
+      lpad = 4; ipr = (g->w + 3) / 4;
+      pitch = ((g->w + 3) / 4) * 4 + 8;                              // 4 zero bytes left, >= 4 right (pad <= 3)
+    }
     const int nch = (gps % ks == 0) ? gps / ks : (gps + ks - 2) / ks + 1;
     const int64_t slot = ((static_cast<int64_t>(nch) * hr * pitch + 15) / 16) * 16;
-    int slots = 0, budget = 0;
+    int slots = 0;
     const int fixed = accel::kSmemRing + accel::kRingSlack;
-    if (fixed + 3 * slot <= kSmemTwoCtas) { slots = 3; budget = 2; }
-    else if (fixed + 2 * slot <= kSmemTwoCtas) { slots = 2; budget = 2; }
-    else if (fixed + 3 * slot <= kSmemOneCta) { slots = 3; budget = 1; }
-    else if (fixed + 2 * slot <= kSmemOneCta) { slots = 2; budget = 1; }
-    (void)budget;
+    if (fixed + 3 * slot <= kSmemTwoCtas) slots = 3;
+    else if (fixed + 2 * slot <= kSmemTwoCtas) slots = 2;
+    else if (fixed + 3 * slot <= kSmemOneCta) slots = 3;
+    else if (fixed + 2 * slot <= kSmemOneCta) slots = 2;
     if (slots && ro < accel::kMaxOutRows && hr <= accel::kMaxHaloRows) {
       prm.ring_slots = slots; prm.slot_bytes = static_cast<int32_t>(slot);
-      prm.halo_rows = hr; prm.halo_pitch = pitch; prm.halo_nch = nch;
-      // 4-byte async copies need 4-byte aligned global rows: W % 4 == 0 and a 4-byte aligned tensor base
-      prm.halo_vec = (g->w % 4 == 0) && ((reinterpret_cast<uintptr_t>(input_nchw) & 3) == 0);
-      const unsigned wpr = static_cast<unsigned>((g->w + 3) / 4);
-      prm.wpr_magic = wpr > 1 ? static_cast<uint32_t>(((1ull << 32) + wpr - 1) / wpr) : 0u;
+      prm.halo_rows = hr; prm.halo_pitch = pitch; prm.halo_lpad = lpad; prm.halo_nch = nch;
+      prm.halo_vec = vec; prm.halo_ipr = ipr;
+      prm.ipr_magic = ipr > 1 ? static_cast<uint32_t>(((1ull << 32) + ipr - 1) / ipr) : 0u;
       return launch_tc(&plan->p, prm, ks == 3 ? accel::kModeConv3 : accel::kModeConv7,
                        fixed + slots * static_cast<int>(slot), st);
     }
@@ -508,22 +533,28 @@ int accel_add_residual_i8(const int8_t* main_, const int8_t* res, int8_t* out, i
 }
 
 int accel_maxpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, int32_t pool,
-                     int32_t stride, int32_t pad, accel_stream_t stream) {
+                     int32_t stride, int32_t pad, int32_t in_pitch, int32_t out_pitch, accel_stream_t stream) {
   if (pool <= 0 || stride <= 0 || pad < 0 || h + 2 * pad < pool || w + 2 * pad < pool)
     return fail(ACCEL_INVALID_CONFIG, "bad pooling geometry");
   const int32_t Ho = (h + 2 * pad - pool) / stride + 1, Wo = (w + 2 * pad - pool) / stride + 1;
-  const int64_t total = n_planes * Ho * Wo;
+  if (in_pitch == 0) in_pitch = w;
+  if (out_pitch == 0) out_pitch = Wo;
+  if (in_pitch < w || out_pitch < Wo) return fail(ACCEL_INVALID_CONFIG, "row pitch smaller than the row");
+  const int64_t total = n_planes * Ho * ((Wo + 3) / 4);
   if (total <= 0) return ACCEL_OK;
-  accel::maxpool_i8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, out, n_planes, h, w, pool, stride, pad, Ho, Wo);
+  accel::maxpool_i8_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, out, n_planes, h, w, pool, stride, pad, Ho, Wo, in_pitch, out_pitch);
   CU(cudaGetLastError());
   return ACCEL_OK;
 }
 
-int accel_avgpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, accel_stream_t stream) {
+int accel_avgpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, int32_t in_pitch,
+                     accel_stream_t stream) {
   if (n_planes <= 0) return ACCEL_OK;
-  accel::avgpool_i8_kernel<<<grid_for(n_planes * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out,
-                                                                                                        n_planes, h * w);
+  if (in_pitch == 0) in_pitch = w;
+  if (in_pitch < w) return fail(ACCEL_INVALID_CONFIG, "row pitch smaller than the row");
+  accel::avgpool_i8_kernel<<<grid_for(n_planes * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, n_planes,
+                                                                                                        h, w, in_pitch);
   CU(cudaGetLastError());
   return ACCEL_OK;
 }

@@ -77,14 +77,17 @@ struct TcParams {
   int32_t conv;         // DIRECT: 0 = GEMM rows, 1 = convolution gather
   // conv geometry
   int32_t C, H, W, ksz, stride, pad, Ho, Wo;
+  int32_t Wp;           // bytes between input rows (>= W); planes and images are dense in that pitch
   // activation ring
   int32_t ring_slots;   // 2 or 3
   int32_t slot_bytes;   // bytes per ring slot (16-byte multiple)
   int32_t halo_rows;    // allocated input rows per channel plane
-  int32_t halo_pitch;   // bytes per staged input row: 4 zero bytes, W data bytes, >= 4 zero bytes
+  int32_t halo_pitch;   // bytes per staged input row: halo_lpad zero bytes, W data bytes, >= pad zero bytes
+  int32_t halo_lpad;    // 4 or 16
   int32_t halo_nch;     // channel planes per stage
-  int32_t halo_vec;     // rows are 4-byte copyable (W % 4 == 0, 4-byte aligned base)
-  uint32_t wpr_magic;   // ceil(2^32 / words_per_row)
+  int32_t halo_vec;     // copy granularity: 16 / 4 (cp.async of aligned rows) or 0 (any alignment, through registers)
+  int32_t halo_ipr;     // copy items per input row
+  uint32_t ipr_magic;   // ceil(2^32 / halo_ipr)
   // weights
   const uint8_t* blob;
   // epilogue
@@ -93,6 +96,8 @@ struct TcParams {
   float res_rcp;        // RN(1 / res_scale_out)
   void* out;
   accel_out_layout lay;
+  long long* timeline;  // developer aid: per-CTA clock64 stamps (32 per CTA) when non-null
+  int32_t dbg_flags;    // developer aid: bit 0 = skip the epilogue's global stores
 };
 
 struct TcLaunch {
@@ -228,6 +233,23 @@ __device__ __forceinline__ void gemm_restride(const uint32_t (&r)[37], uint32_t 
   }
 }
 
+// ---- fused epilogue of one block-row (14 channels) for this thread's activation row.
+enum EpiKind { kEpiI8 = 0, kEpiI8ResFast = 1, kEpiI8Res = 2, kEpiI32 = 3, kEpiGeneric = 4 };
+struct EpiCtx {
+  int flags;
+  bool row_ok;
+  int64_t out_base;     // element offset of (this row, channel 0)
+  int64_t cs;           // channel stride in elements
+  int relu_lo;          // 0 when ReLU acts on the accumulator, else INT_MIN
+  int out_lo;           // 0 when ReLU acts on the int8 result, else -128
+  uint32_t sat;
+  int lane;
+};
+
+template <int KIND>
+__device__ __forceinline__ void epilogue_row(const TcParams& p, EpiCtx& ec, uint32_t (&v)[16], int cb, int n_ok,
+                                             const float* sc, const int32_t* bi);
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_constant__ TcLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -258,13 +280,35 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
   const int64_t m0 = mtile * kTileM;
   const uint32_t g_br0 = L.groups[gi].br0_rows & 0xffffu, g_rows = L.groups[gi].br0_rows >> 16;
   const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
+  long long* tl = p.timeline ? p.timeline + static_cast<size_t>(blockIdx.x) * 32 : nullptr;
+  if (tl && threadIdx.x == 0) tl[0] = clock64();
 
+  // ---- prologue, two block-wide barriers: (A) barriers / TMEM allocation / tables, (B) accumulators zeroed
+  int n_out_rows = 0;
+  uint32_t R0 = 0;
+  if constexpr (kHalo) {
+    // which input rows does this tile need?  Output rows R0.. (global row id n*Ho + oh); consecutive output rows
+    // of one image share input rows, so halo row ids advance by `stride`; a new image starts a fresh set.
+    R0 = static_cast<uint32_t>(m0) / static_cast<uint32_t>(p.Wo);
+    const uint32_t m_last = static_cast<uint32_t>(m0 + kTileM - 1 < p.M ? m0 + kTileM - 1 : p.M - 1);
+    n_out_rows = static_cast<int>(m_last / static_cast<uint32_t>(p.Wo) - R0) + 1;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 4); mbar_init(&x_empty[s], kIssuers); }
     for (int s = 0; s < kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kIssuers); }
     mbar_init(acc_full, kIssuers);
     for (int s = 0; s < kMaxRingSlots; ++s) { mbar_init(&h_full[s], 32); mbar_init(&h_empty[s], 4); }
     fence_mbar_init();
+  } else if (kHalo && threadIdx.x == 32) {
+    int hb = 0;
+    uint32_t n = R0 / static_cast<uint32_t>(p.Ho);
+    uint32_t oh = R0 - n * p.Ho;
+    for (int rr = 0; rr < n_out_rows; ++rr) {
+      s_hbase[rr] = hb;
+      s_outrow[rr] = static_cast<int32_t>(n);
+      if (++oh == static_cast<uint32_t>(p.Ho)) { oh = 0; ++n; hb += max(p.ksz, p.stride); } else { hb += p.stride; }
+    }
+    s_hbase[kMaxOutRows - 1] = s_hbase[n_out_rows - 1] + p.ksz;   // rows in use
   }
   if (warp == kProducerWarps) {
     tmem_alloc_dyn(tmem_slot, kTmemCols);
@@ -277,55 +321,39 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
     s_scale[threadIdx.x] = (ok && p.epi.chan_scale) ? p.epi.chan_scale[c] : 0.f;
     s_bias[threadIdx.x] = (ok && p.epi.bias) ? p.epi.bias[c] : 0;
   }
-  int hr_used = 0;
   if constexpr (kHalo) {
-    // ---- which input rows does this tile need?  Output rows R0.. (global row id n*Ho + oh); consecutive output
-    // rows of one image share input rows, so halo row ids advance by `stride`; a new image starts a fresh set.
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + kSmemRing);
     const int ring_words = (p.ring_slots * p.slot_bytes + kRingSlack) >> 2;
     for (int i = threadIdx.x; i < ring_words; i += kThreads) ring[i] = 0u;   // pads must read as zero
-    const int64_t R0 = m0 / p.Wo;
-    const int64_t m_last = (m0 + kTileM - 1 < p.M ? m0 + kTileM - 1 : p.M - 1);
-    const int n_out_rows = static_cast<int>(m_last / p.Wo - R0) + 1;
-    if (threadIdx.x == 0) {
-      int hb = 0;
-      int64_t prev_n = -1;
-      for (int rr = 0; rr < n_out_rows; ++rr) {
-        const int64_t Rg = R0 + rr;
-        const int64_t n = Rg / p.Ho;
-        if (rr > 0) hb += (n == prev_n) ? p.stride : max(p.ksz, p.stride);
-        s_hbase[rr] = hb;
-        s_outrow[rr] = static_cast<int32_t>(n);
-        prev_n = n;
-      }
-      s_hbase[kMaxOutRows - 1] = hb + p.ksz;   // rows in use
-    }
     for (int i = threadIdx.x; i < kMaxHaloRows; i += kThreads) s_rowoff[i] = -1;
-    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();                                                             // (A)
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  int hr_used = 0;
+  if constexpr (kHalo) {
     hr_used = s_hbase[kMaxOutRows - 1];
     for (int i = threadIdx.x; i < n_out_rows * p.ksz; i += kThreads) {
       const int rr = i / p.ksz, kh = i - rr * p.ksz;
       const int64_t n = s_outrow[rr];
-      const int oh = static_cast<int>((R0 + rr) - n * p.Ho);
+      const int oh = static_cast<int>(static_cast<int64_t>(R0 + rr) - n * p.Ho);
       const int ih = oh * p.stride - p.pad + kh;
       if (static_cast<unsigned>(ih) < static_cast<unsigned>(p.H))
-        s_rowoff[s_hbase[rr] + kh] = ((n * p.C) * p.H + ih) * static_cast<int64_t>(p.W);
+        s_rowoff[s_hbase[rr] + kh] = ((n * p.C) * p.H + ih) * static_cast<int64_t>(p.Wp);
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (warp < 4) {  // zero the accumulators: every MMA accumulates, so issue order across warps is free
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     for (uint32_t c = 0; c < g_rows * kTile; c += 4) tmem_st4(tmem_base + lane_base + c, 0u, 0u, 0u, 0u);
     tmem_st_wait();
   }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                                                             // (B)
   tc_fence_after();
 
   const uint32_t ring_addr = smem_u32(smem + kSmemRing);
+  if (tl && threadIdx.x == 0) tl[1] = clock64();
 
   if (warp < kProducerWarps) {
     // =================================================================== activation producers
@@ -337,18 +365,17 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
     const bool row_ok = m < p.M;
     // conv: this thread's output position
     int ow = 0, oh = 0;
-    int64_t img = 0;
+    uint32_t img = 0;
     uint32_t thr_off = 0, sh8 = 0;
     if (MODE != kModeGemm && (kHalo || p.conv)) {
-      const int64_t P = static_cast<int64_t>(p.Ho) * p.Wo;
-      const int64_t mm = row_ok ? m : m0;
-      const int64_t R = mm / p.Wo;
+      const uint32_t mm = static_cast<uint32_t>(row_ok ? m : m0);
+      const uint32_t R = mm / static_cast<uint32_t>(p.Wo);
       ow = static_cast<int>(mm - R * p.Wo);
-      img = mm / P;
+      img = R / static_cast<uint32_t>(p.Ho);
       oh = static_cast<int>(R - img * p.Ho);
       if constexpr (kHalo) {
-        const int rr = static_cast<int>(R - m0 / p.Wo);
-        const uint32_t xb = static_cast<uint32_t>(ow * p.stride - p.pad + 4);
+        const int rr = static_cast<int>(R - R0);
+        const uint32_t xb = static_cast<uint32_t>(ow * p.stride - p.pad + p.halo_lpad);
         thr_off = static_cast<uint32_t>(s_hbase[rr]) * p.halo_pitch + (xb & ~3u);
         sh8 = (xb & 3u) * 8u;
       }
@@ -365,9 +392,13 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
       if (!my) continue;
       const int chunk = static_cast<int>(bw >> 16);
       const int k_chunk0 = chunk * kChunkTiles * kBlock;
+      if (tl && threadIdx.x == 0 && step == 3) tl[8] = clock64();
       if constexpr (kRing) mbar_wait(&h_full[slot], sphase);
+      if (tl && threadIdx.x == 0 && step == 3) tl[9] = clock64();
       mbar_wait(&x_empty[half], (use & 1u) ^ 1u);
       tc_fence_after();
+      if (tl && threadIdx.x == 0 && step == 1) tl[2] = clock64();
+      if (tl && threadIdx.x == 0 && step == 3) tl[10] = clock64();
       if constexpr (MODE == kModeGemm) {
         // ---------------- GEMM rows from the ring: 9 x 16 B (pitch 144 B: conflict-free 16-byte reads)
         const uint32_t src = ring_addr + slot * p.slot_bytes + tid * 144;
@@ -433,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
         int c = k / kk;
         int rem = k - c * kk;
         int kh = rem / p.ksz, kw = rem - kh * p.ksz;
-        const int8_t* im = p.x + img * static_cast<int64_t>(p.C) * p.H * p.W;
+        const int8_t* im = p.x + static_cast<int64_t>(img) * p.C * p.H * p.Wp;
         const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
 #pragma unroll 1
         for (int t = 0; t < kChunkTiles; ++t) {
@@ -444,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
             v[i] = 0u;
             if (row_ok && k < p.K && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
                 static_cast<unsigned>(iw) < static_cast<unsigned>(p.W))
-              v[i] = static_cast<uint8_t>(im[(static_cast<int64_t>(c) * p.H + ih) * p.W + iw]);
+              v[i] = static_cast<uint8_t>(im[(static_cast<int64_t>(c) * p.H + ih) * p.Wp + iw]);
             ++k;
             if (++kw == p.ksz) { kw = 0; if (++kh == p.ksz) { kh = 0; ++c; } }
           }
@@ -454,102 +485,72 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
           tmem_st4(xcol + t * 4, w[0], w[1], w[2], w[3]);
         }
       }
+      if (tl && threadIdx.x == 0 && step == 3) tl[11] = clock64();
       tmem_st_wait();
+      if (tl && threadIdx.x == 0 && step == 3) tl[12] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (kRing) mbar_arrive(&h_empty[slot]);
         mbar_arrive(&x_full[half]);
       }
+      if (tl && threadIdx.x == 0 && step == 1) tl[3] = clock64();
+      if (tl && threadIdx.x == 0 && step == 3) tl[13] = clock64();
     }
 
     // =================================================================== epilogue (same 8 warps)
+    if (tl && threadIdx.x == 0) tl[4] = clock64();
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int flags = p.epi.flags;
-    int64_t out_base = 0;
+    if (tl && threadIdx.x == 0) tl[5] = clock64();
+    EpiCtx ec;
+    ec.flags = p.epi.flags;
+    ec.row_ok = row_ok;
+    ec.out_base = 0;
     if (row_ok) {
       const int64_t im = m / p.lay.rows_per_image;
-      out_base = im * p.lay.image_stride + (m - im * p.lay.rows_per_image) * p.lay.row_stride;
+      const int64_t pix = m - im * p.lay.rows_per_image;
+      if (p.lay.row_len > 0) {
+        const int64_t r = pix / p.lay.row_len;
+        ec.out_base = im * p.lay.image_stride + r * p.lay.row_pitch + (pix - r * p.lay.row_len) * p.lay.row_stride;
+      } else {
+        ec.out_base = im * p.lay.image_stride + pix * p.lay.row_stride;
+      }
     }
-    const int8_t* __restrict__ resid = p.epi.residual;
-    uint32_t sat = 0;
+    ec.cs = p.lay.chan_stride;
+    ec.relu_lo = (ec.flags & ACCEL_RELU) ? 0 : INT_MIN;
+    ec.out_lo = (ec.flags & ACCEL_RELU_OUT) ? 0 : -128;
+    ec.sat = 0;
+    ec.lane = lane;
+    // one uniform decision per CTA: which specialised path handles every block-row of this tile
+    const bool plain = !p.epi.sat_count && !p.epi.chan_absmax;
+    int kind = kEpiGeneric;
+    if (plain && (ec.flags & ACCEL_OUT_I8)) kind = !p.epi.residual ? kEpiI8 : (p.res_fast ? kEpiI8ResFast : kEpiI8Res);
+    else if (plain && (ec.flags & ACCEL_OUT_I32)) kind = kEpiI32;
     for (uint32_t g = half; g < g_rows; g += 2) {
       uint32_t v[16];
+      if (tl && threadIdx.x == 0 && g < 6) tl[14 + 3 * (g >> 1)] = clock64();
       tmem_ld16(tmem_base + lane_base + g * kTile, v);
       const int cb = (g_br0 + g) * kBlock;
       const int n_ok = min(kBlock, p.epi.n_channels - cb);   // channels of this block-row that exist (warp-uniform)
-      const int64_t o0 = out_base + static_cast<int64_t>(cb) * p.lay.chan_stride;
-      int rv[kBlock];
-      if (resid && row_ok) {
-#pragma unroll
-        for (int h = 0; h < kBlock; ++h) rv[h] = h < n_ok ? static_cast<int>(resid[o0 + h * p.lay.chan_stride]) : 0;
+      const float* sc = s_scale + g * kBlock;
+      const int32_t* bi = s_bias + g * kBlock;
+      switch (kind) {
+        case kEpiI8: epilogue_row<kEpiI8>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI8ResFast: epilogue_row<kEpiI8ResFast>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI8Res: epilogue_row<kEpiI8Res>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI32: epilogue_row<kEpiI32>(p, ec, v, cb, n_ok, sc, bi); break;
+        default: epilogue_row<kEpiGeneric>(p, ec, v, cb, n_ok, sc, bi); break;
       }
-      tmem_ld_wait();
-      int acc[kBlock];
-#pragma unroll
-      for (int h = 0; h < kBlock; ++h) {
-        acc[h] = static_cast<int>(v[h]) + s_bias[g * kBlock + h];
-        if (flags & ACCEL_RELU) acc[h] = max(acc[h], 0);
-      }
-      if (p.epi.chan_absmax) {
-#pragma unroll
-        for (int h = 0; h < kBlock; ++h) {
-          const int a = row_ok ? (acc[h] < 0 ? (acc[h] == INT_MIN ? INT_MAX : -acc[h]) : acc[h]) : 0;
-          const int wmax = __reduce_max_sync(0xffffffffu, a);
-          if (lane == 0 && wmax > 0 && h < n_ok) atomicMax(p.epi.chan_absmax + cb + h, wmax);
-        }
-      }
-      if (!row_ok) continue;
-      if (flags & ACCEL_OUT_I32) {
-        int32_t* o = reinterpret_cast<int32_t*>(p.out) + o0;
-#pragma unroll
-        for (int h = 0; h < kBlock; ++h)
-          if (h < n_ok) o[h * p.lay.chan_stride] = acc[h];
-      } else if (flags & ACCEL_OUT_F32) {
-        float* o = reinterpret_cast<float*>(p.out) + o0;
-#pragma unroll
-        for (int h = 0; h < kBlock; ++h)
-          if (h < n_ok) o[h * p.lay.chan_stride] = __fmul_rn(__int2float_rn(acc[h]), s_scale[g * kBlock + h]);
-      } else {
-        int8_t* o = reinterpret_cast<int8_t*>(p.out) + o0;
-#pragma unroll
-        for (int h = 0; h < kBlock; ++h) {
-          // golden_models.cpp:378-411, per channel: one float32 multiply, round-half-even, saturate
-          const float f = __fmul_rn(__int2float_rn(acc[h]), s_scale[g * kBlock + h]);
-          int q;
-          if (p.epi.sat_count) {
-            const int qi = __float2int_rn(f);
-            q = min(127, max(-128, qi));
-            sat += (qi != q && h < n_ok) ? 1u : 0u;
-          } else {
-            q = cvt_sat_s8(f);
-          }
-          if (resid) {
-            // golden_models.cpp:465-490: (main*s_main + res*s_res) / s_out, float32, no FMA in the sum
-            const float a = __fmul_rn(__int2float_rn(q), p.epi.res_scale_main);
-            const float r = __fmul_rn(__int2float_rn(rv[h]), p.epi.res_scale_res);
-            const float s = __fadd_rn(a, r);
-            float d;
-            if (p.res_fast) {   // correctly rounded quotient for every (int8, int8) pair: verified on the host
-              const float q0 = __fmul_rn(s, p.res_rcp);
-              const float e = __fmaf_rn(-q0, p.epi.res_scale_out, s);
-              d = __fmaf_rn(e, p.res_rcp, q0);
-            } else {
-              d = __fdiv_rn(s, p.epi.res_scale_out);
-            }
-            q = cvt_sat_s8(d);
-          }
-          if (flags & ACCEL_RELU_OUT) q = max(q, 0);          // relu_int8, golden_models.cpp:278-283
-          if (h < n_ok) o[h * p.lay.chan_stride] = static_cast<int8_t>(q);
-        }
-      }
+      if (tl && threadIdx.x == 0 && g < 6) tl[15 + 3 * (g >> 1)] = clock64();
     }
+    if (tl && threadIdx.x == 0) tl[23] = clock64();
     if (p.epi.sat_count) {
-      const uint32_t wsum = __reduce_add_sync(0xffffffffu, sat);
+      const uint32_t wsum = __reduce_add_sync(0xffffffffu, ec.sat);
       if (lane == 0 && wsum) atomicAdd(p.epi.sat_count, static_cast<unsigned long long>(wsum));
     }
     tc_fence_before();
+    if (tl && threadIdx.x == 0) tl[6] = clock64();
   } else if (warp < kWarpWLoad) {
     // =================================================================== MMA issuers (uniform datapath)
     const uint32_t me = static_cast<uint32_t>(warp - kProducerWarps);
@@ -640,17 +641,27 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
         constexpr int GPS = 126 / KS;
         const int g0 = chunk * GPS;
         const int c_first = g0 / KS;
-        const int wpr = (p.W + 3) >> 2;
-        const int items = hr_used * wpr;
+        const int ipr = p.halo_ipr;                                   // copy items per input row
+        const int items = hr_used * ipr;
         const uint32_t cs = static_cast<uint32_t>(p.halo_rows) * p.halo_pitch;
-        const int64_t HW = static_cast<int64_t>(p.H) * p.W;
+        const int64_t HW = static_cast<int64_t>(p.H) * p.Wp;
         const int nch = min(p.halo_nch, p.C - c_first);
         for (int idx = lane; idx < items; idx += 32) {
-          const int h = wpr > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), p.wpr_magic)) : idx;
-          const int wd = idx - h * wpr;
+          const int h = ipr > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), p.ipr_magic)) : idx;
+          const int wd = idx - h * ipr;
           const int64_t off = s_rowoff[h];
-          uint8_t* d = dst_slot + h * p.halo_pitch + 4 + wd * 4;
-          if (p.halo_vec) {
+          if (p.halo_vec == 16) {
+            // 16-byte aligned rows: 16-byte copies, the row tail is zero-filled by the copy itself
+            uint8_t* d = dst_slot + h * p.halo_pitch + 16 + wd * 16;
+            const int nbytes = off >= 0 ? min(16, p.W - wd * 16) : 0;
+            const int8_t* g = off >= 0 ? p.x + off + c_first * HW + wd * 16 : p.x;
+            for (int c = 0; c < p.halo_nch; ++c) {
+              cp_async16_zfill(d, (nbytes && c < nch) ? g : p.x, c < nch ? nbytes : 0);
+              g += HW;
+              d += cs;
+            }
+          } else if (p.halo_vec == 4) {
+            uint8_t* d = dst_slot + h * p.halo_pitch + 4 + wd * 4;
             const int8_t* g = off >= 0 ? p.x + off + c_first * HW + wd * 4 : p.x;
             for (int c = 0; c < p.halo_nch; ++c) {
               cp_async4_zfill(d, (off >= 0 && c < nch) ? g : p.x, off >= 0 && c < nch);
@@ -660,6 +671,7 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
           } else {
             // rows at any byte alignment: aligned 32-bit loads, funnel shift, mask the row tail.  Channel planes
             // are handled in batches so that the independent loads of a batch are all in flight together.
+            uint8_t* d = dst_slot + h * p.halo_pitch + 4 + wd * 4;
             const int nb = min(4, p.W - wd * 4);
             const uint32_t mask = nb >= 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
             constexpr int kB = 7;
@@ -694,9 +706,130 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
   }
 
   __syncthreads();
+  if (tl && threadIdx.x == 0) tl[7] = clock64();
   if (warp == kProducerWarps) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, kTmemCols);
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void epilogue_row(const TcParams& p, EpiCtx& ec, uint32_t (&v)[16], int cb, int n_ok,
+                                             const float* sc, const int32_t* bi) {
+  const int64_t o0 = ec.out_base + static_cast<int64_t>(cb) * ec.cs;
+  if constexpr (KIND == kEpiI8 || KIND == kEpiI8ResFast || KIND == kEpiI8Res) {
+    // golden_models.cpp:378-411 per channel: one float32 multiply, round-half-even, saturate;
+    // then (residual variants) add_residual_int8, golden_models.cpp:465-490: (main*s_main + res*s_res) / s_out
+    constexpr bool kRes = KIND != kEpiI8;
+    int8_t* o = reinterpret_cast<int8_t*>(p.out) + o0;
+    int rv[kBlock];
+    if constexpr (kRes) {
+      const int8_t* __restrict__ r = p.epi.residual + o0;
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h) rv[h] = (ec.row_ok && h < n_ok) ? static_cast<int>(r[h * ec.cs]) : 0;
+    }
+    float scl[kBlock];
+    int bia[kBlock];
+#pragma unroll
+    for (int h = 0; h < kBlock; ++h) { scl[h] = sc[h]; bia[h] = bi[h]; }
+    tmem_ld_wait();
+    int q[kBlock];
+#pragma unroll
+    for (int h = 0; h < kBlock; ++h) {
+      const int acc = max(static_cast<int>(v[h]) + bia[h], ec.relu_lo);
+      int r8 = cvt_sat_s8(__fmul_rn(__int2float_rn(acc), scl[h]));
+      if constexpr (kRes) {
+        const float a = __fmul_rn(__int2float_rn(r8), p.epi.res_scale_main);
+        const float r = __fmul_rn(__int2float_rn(rv[h]), p.epi.res_scale_res);
+        const float s = __fadd_rn(a, r);
+        float d;
+        if constexpr (KIND == kEpiI8ResFast) {   // correctly rounded for every (int8, int8) pair: verified on the host
+          const float q0 = __fmul_rn(s, p.res_rcp);
+          const float e = __fmaf_rn(-q0, p.epi.res_scale_out, s);
+          d = __fmaf_rn(e, p.res_rcp, q0);
+        } else {
+          d = __fdiv_rn(s, p.epi.res_scale_out);
+        }
+        r8 = cvt_sat_s8(d);
+      }
+      q[h] = max(r8, ec.out_lo);                 // relu_int8 (golden_models.cpp:278-283) when requested
+    }
+    if (!ec.row_ok || (p.dbg_flags & 1)) return;
+    if (n_ok == kBlock) {
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h) o[h * ec.cs] = static_cast<int8_t>(q[h]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h)
+        if (h < n_ok) o[h * ec.cs] = static_cast<int8_t>(q[h]);
+    }
+  } else if constexpr (KIND == kEpiI32) {
+    int bia[kBlock];
+#pragma unroll
+    for (int h = 0; h < kBlock; ++h) bia[h] = bi[h];
+    tmem_ld_wait();
+    int acc[kBlock];
+#pragma unroll
+    for (int h = 0; h < kBlock; ++h) acc[h] = max(static_cast<int>(v[h]) + bia[h], ec.relu_lo);
+    if (!ec.row_ok) return;
+    int32_t* o = reinterpret_cast<int32_t*>(p.out) + o0;
+    if (n_ok == kBlock && ec.cs == 1 && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+#pragma unroll
+      for (int h = 0; h < kBlock; h += 2) *reinterpret_cast<int2*>(o + h) = make_int2(acc[h], acc[h + 1]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h)
+        if (h < n_ok) o[h * ec.cs] = acc[h];
+    }
+  } else {
+    // every option: saturation counter, per-channel |acc| maximum, float32 output
+    const int flags = ec.flags;
+    const int8_t* __restrict__ resid = p.epi.residual;
+    int rv[kBlock];
+    if (resid && ec.row_ok) {
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h) rv[h] = h < n_ok ? static_cast<int>(resid[o0 + h * ec.cs]) : 0;
+    }
+    tmem_ld_wait();
+    int acc[kBlock];
+#pragma unroll
+    for (int h = 0; h < kBlock; ++h) acc[h] = max(static_cast<int>(v[h]) + bi[h], ec.relu_lo);
+    if (p.epi.chan_absmax) {
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h) {
+        const int a = ec.row_ok ? (acc[h] < 0 ? (acc[h] == INT_MIN ? INT_MAX : -acc[h]) : acc[h]) : 0;
+        const int wmax = __reduce_max_sync(0xffffffffu, a);
+        if (ec.lane == 0 && wmax > 0 && h < n_ok) atomicMax(p.epi.chan_absmax + cb + h, wmax);
+      }
+    }
+    if (!ec.row_ok) return;
+    if (flags & ACCEL_OUT_I32) {
+      int32_t* o = reinterpret_cast<int32_t*>(p.out) + o0;
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h)
+        if (h < n_ok) o[h * ec.cs] = acc[h];
+    } else if (flags & ACCEL_OUT_F32) {
+      float* o = reinterpret_cast<float*>(p.out) + o0;
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h)
+        if (h < n_ok) o[h * ec.cs] = __fmul_rn(__int2float_rn(acc[h]), sc[h]);
+    } else {
+      int8_t* o = reinterpret_cast<int8_t*>(p.out) + o0;
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h) {
+        const float f = __fmul_rn(__int2float_rn(acc[h]), sc[h]);
+        const int qi = __float2int_rn(f);
+        int q = min(127, max(-128, qi));
+        ec.sat += (qi != q && h < n_ok) ? 1u : 0u;
+        if (resid) {
+          const float a = __fmul_rn(__int2float_rn(q), p.epi.res_scale_main);
+          const float r = __fmul_rn(__int2float_rn(rv[h]), p.epi.res_scale_res);
+          q = cvt_sat_s8(__fdiv_rn(__fadd_rn(a, r), p.epi.res_scale_out));
+        }
+        q = max(q, ec.out_lo);
+        if (h < n_ok) o[h * ec.cs] = static_cast<int8_t>(q);
+      }
+    }
   }
 }
 

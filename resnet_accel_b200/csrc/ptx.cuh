@@ -34,26 +34,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  const uint32_t addr = smem_u32(bar);
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.  try_wait carries a
+// suspend-time hint, so a waiting warp sleeps in hardware instead of burning issue slots its neighbours need.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity), "r"(100000u)
+      : "memory");
+  return ok;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
   const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) break;
+  while (!mbar_try_wait(addr, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       printf("accel_b200: mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
              blockIdx.y, threadIdx.x, addr, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  if (!mbar_try_wait(addr, parity)) mbar_wait_slow(addr, parity);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)

@@ -255,31 +255,61 @@ __global__ void add_residual_i8_kernel(const int8_t* __restrict__ a, const int8_
     out[i] = static_cast<int8_t>(min(127, max(-128, q)));
   }
 }
+// One thread per 4 adjacent outputs of a row: HBM-bound byte work, 4-byte stores, rows of the window re-used
+// from registers.  Padding reads as -128 (maxpool2d_int8 initialises its maximum to -128, golden_models.cpp:549).
 __global__ void maxpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out, int64_t n_planes, int32_t H,
-                                  int32_t W, int32_t pool, int32_t stride, int32_t pad, int32_t Ho, int32_t Wo) {
-  const int64_t total = n_planes * Ho * Wo;
+                                  int32_t W, int32_t pool, int32_t stride, int32_t pad, int32_t Ho, int32_t Wo,
+                                  int32_t in_pitch, int32_t out_pitch) {
+  const int wq = (Wo + 3) >> 2;
+  const int64_t total = n_planes * Ho * wq;
+  const bool vec_out = (out_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ow = static_cast<int>(idx % Wo), oh = static_cast<int>((idx / Wo) % Ho);
-    const int64_t pl = idx / (static_cast<int64_t>(Wo) * Ho);
-    int best = -128;
-    for (int ph = 0; ph < pool; ++ph)
-      for (int pw = 0; pw < pool; ++pw) {
-        const int ih = oh * stride + ph - pad, iw = ow * stride + pw - pad;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) best = max(best, static_cast<int>(x[(pl * H + ih) * W + iw]));
+    const int q = static_cast<int>(idx % wq), oh = static_cast<int>((idx / wq) % Ho);
+    const int64_t pl = idx / (static_cast<int64_t>(wq) * Ho);
+    const int ow0 = q * 4;
+    int best[4] = {-128, -128, -128, -128};
+    const int8_t* xp = x + pl * H * in_pitch;
+    for (int ph = 0; ph < pool; ++ph) {
+      const int ih = oh * stride + ph - pad;
+      if (ih < 0 || ih >= H) continue;
+      const int8_t* row = xp + static_cast<int64_t>(ih) * in_pitch;
+      const int iw0 = ow0 * stride - pad;
+      const int span = 3 * stride + pool;                 // input columns feeding the 4 outputs
+      for (int j = 0; j < span; ++j) {
+        const int iw = iw0 + j;
+        if (iw < 0 || iw >= W) continue;
+        const int v = row[iw];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int rel = j - o * stride;
+          if (rel >= 0 && rel < pool) best[o] = max(best[o], v);
+        }
       }
-    out[idx] = static_cast<int8_t>(best);
+    }
+    int8_t* orow = out + (pl * Ho + oh) * out_pitch + ow0;
+    if (vec_out && ow0 + 3 < Wo) {
+      const uint32_t pk = (static_cast<uint32_t>(best[0]) & 0xffu) | ((static_cast<uint32_t>(best[1]) & 0xffu) << 8) |
+                          ((static_cast<uint32_t>(best[2]) & 0xffu) << 16) | ((static_cast<uint32_t>(best[3]) & 0xffu) << 24);
+      *reinterpret_cast<uint32_t*>(orow) = pk;
+    } else {
+      for (int o = 0; o < 4 && ow0 + o < Wo; ++o) orow[o] = static_cast<int8_t>(best[o]);
+    }
   }
 }
 // one warp per plane: (sum + HW/2) / HW with C truncating division (golden_models.cpp:619)
 __global__ void avgpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out, int64_t n_planes,
-                                  int32_t hw) {
+                                  int32_t H, int32_t W, int32_t in_pitch) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int hw = H * W;
   for (int64_t pl = warp0; pl < n_planes; pl += nwarps) {
     int s = 0;
-    for (int i = lane; i < hw; i += 32) s += x[pl * hw + i];
+    for (int i = lane; i < hw; i += 32) {
+      const int r = i / W;
+      s += x[(pl * H + r) * in_pitch + (i - r * W)];
+    }
     s = __reduce_add_sync(0xffffffffu, s);
     if (lane == 0) out[pl] = static_cast<int8_t>(min(127, max(-128, (s + hw / 2) / hw)));
   }

@@ -177,8 +177,8 @@ class BsrNetwork:
                 self.buffers[sp.name] = torch.empty((batch, sp.c_out), dtype=torch.int32, device="cuda")
             elif sp.kind == "avgpool":
                 self.buffers[sp.name] = torch.empty((batch, sp.c_out), dtype=torch.int8, device="cuda")
-            else:
-                self.buffers[sp.name] = torch.empty((batch, sp.c_out, sp.h_out, sp.w_out), dtype=torch.int8, device="cuda")
+            else:   # rows padded to 16 bytes: the next layer streams them with 16-byte cp.async
+                self.buffers[sp.name] = ops.alloc_padded((batch, sp.c_out, sp.h_out, sp.w_out))
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_in: Optional[torch.Tensor] = None
         self.n_launches = sum(1 for _ in specs)
@@ -211,7 +211,8 @@ class BsrNetwork:
         return self.buffers[self.specs[-1].name]
 
     def capture(self, x: torch.Tensor) -> None:
-        self.static_in = x.clone()
+        self.static_in = ops.alloc_padded(tuple(x.shape))
+        self.static_in.copy_(x)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

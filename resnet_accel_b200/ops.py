@@ -45,6 +45,28 @@ def to_device(a, dtype: torch.dtype, device=None) -> torch.Tensor:
     return t.to(device, non_blocking=False).contiguous()
 
 
+def alloc_padded(shape, device=None, align: int = 16) -> torch.Tensor:
+    """int8 NCHW activation tensor whose rows start ``align``-byte aligned: a ``[..., :W]`` view of a zeroed
+    ``[B, C, H, Wp]`` buffer (Wp = W rounded up).  The conv loader streams such rows with 16-byte cp.async."""
+    device = device or _require_cuda()
+    *lead, W = shape
+    Wp = -(-W // align) * align
+    return torch.zeros((*lead, Wp), dtype=torch.int8, device=device)[..., :W]
+
+
+def _row_pitch(t: torch.Tensor) -> Optional[int]:
+    """Row pitch (elements) of an NCHW tensor that is dense except for padded rows, else None."""
+    B, Cn, H, W = t.shape
+    if t.stride(3) != 1 and W > 1:
+        return None
+    Wp = t.stride(2) if H > 1 else (t.stride(1) // max(H, 1) if Cn > 1 else W)
+    if Wp < W:
+        return None
+    if (Cn > 1 and t.stride(1) != H * Wp) or (B > 1 and t.stride(0) != Cn * H * Wp):
+        return None
+    return int(Wp)
+
+
 class BsrPlan:
     """A BSR weight matrix (Convention B, 14x14) resident on the GPU in MMA-tile form.
 
@@ -107,7 +129,10 @@ class BsrPlan:
         for name, val, dt in (("chan_scale", chan_scale, torch.float32), ("bias", bias, torch.int32),
                               ("residual", residual, torch.int8)):
             if val is not None:
-                t = val if _is_cuda(val) and val.dtype == dt and val.is_contiguous() else to_device(val, dt, self.device)
+                if name == "residual" and _is_cuda(val) and val.dtype == dt:
+                    t = val                                  # may have padded rows: same strides as the output
+                else:
+                    t = val if _is_cuda(val) and val.dtype == dt and val.is_contiguous() else to_device(val, dt, self.device)
                 if name != "residual" and t.numel() < n_channels:
                     raise AcceleratorError(_lib.INVALID_CONFIG, f"{name} has {t.numel()} entries, need {n_channels}")
                 keep.append(t)
@@ -134,9 +159,13 @@ class BsrPlan:
         dt = {"i8": torch.int8, "i32": torch.int32, "f32": torch.float32}[out_kind]
         if out is None:
             out = torch.empty((M, n_channels), dtype=dt, device=x.device)
+        if residual is not None and _is_cuda(residual):
+            residual = residual.contiguous()
+            if residual.shape != out.shape or residual.stride(0) != out.stride(0):
+                raise AcceleratorError(_lib.INVALID_CONFIG, "residual must have the output's shape and row stride")
         e, keep = self._epilogue(out_kind, n_channels, chan_scale, bias, relu, residual, res_scales, sat_count,
                                  chan_absmax, relu_out)
-        lay = OutLayout(max(M, 1), 0, 1, out.stride(0) if M else n_channels)
+        lay = OutLayout(max(M, 1), 0, 1, out.stride(0) if M else n_channels, 0, 0)
         check(_lib.lib().accel_bsr_gemm_i8(self._h, _ptr(x), M, K, x.stride(0) if M else K, C.byref(e), _ptr(out),
                                            C.byref(lay), _stream()))
         return out
@@ -145,22 +174,37 @@ class BsrPlan:
              chan_scale=None, bias=None, relu: bool = False, residual=None, res_scales=None,
              out: Optional[torch.Tensor] = None, sat_count: Optional[torch.Tensor] = None,
              chan_absmax: Optional[torch.Tensor] = None, relu_out: bool = False) -> torch.Tensor:
-        """Implicit-im2col BSR convolution.  x int8 NCHW (CUDA) -> [B, c_out, Ho, Wo]."""
+        """Implicit-im2col BSR convolution.  x int8 NCHW (CUDA) -> [B, c_out, Ho, Wo].  Input and output may have
+        padded rows (``alloc_padded``); the residual must share the output's strides."""
         if x.dtype != torch.int8 or x.dim() != 4 or not x.is_cuda:
             raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 4-D INT8 CUDA tensor (NCHW)")
-        x = x.contiguous()
+        in_pitch = _row_pitch(x)
+        if in_pitch is None:
+            x = x.contiguous()
+            in_pitch = x.shape[3]
         B, Cin, H, W = x.shape
         Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
         dt = {"i8": torch.int8, "i32": torch.int32, "f32": torch.float32}[out_kind]
         if out is None:
             out = torch.empty((B, c_out, Ho, Wo), dtype=dt, device=x.device)
-        if residual is not None and tuple(residual.shape) != tuple(out.shape):
-            raise AcceleratorError(_lib.INVALID_CONFIG, "residual shape must equal the output shape")
+        out_pitch = _row_pitch(out)
+        if out_pitch is None:
+            raise AcceleratorError(_lib.INVALID_CONFIG, "output must be NCHW, dense or with padded rows")
+        if residual is not None:
+            if tuple(residual.shape) != tuple(out.shape):
+                raise AcceleratorError(_lib.INVALID_CONFIG, "residual shape must equal the output shape")
+            if _is_cuda(residual) and _row_pitch(residual) != out_pitch:
+                residual = residual.contiguous() if out_pitch == Wo else None
+                if residual is None:
+                    raise AcceleratorError(_lib.INVALID_CONFIG, "residual strides must equal the output strides")
         e, keep = self._epilogue(out_kind, c_out, chan_scale, bias, relu, residual, res_scales, sat_count, chan_absmax,
                                  relu_out)
-        g = ConvGeom(B, Cin, H, W, ksize, stride, pad)
+        g = ConvGeom(B, Cin, H, W, ksize, stride, pad, in_pitch)
         P = max(Ho * Wo, 1)
-        lay = OutLayout(P, c_out * Ho * Wo, Ho * Wo, 1)
+        if out_pitch == Wo:
+            lay = OutLayout(P, c_out * Ho * Wo, Ho * Wo, 1, 0, 0)
+        else:
+            lay = OutLayout(P, c_out * Ho * out_pitch, Ho * out_pitch, 1, Wo, out_pitch)
         check(_lib.lib().accel_conv_bsr_i8(self._h, _ptr(x), C.byref(g), C.byref(e), _ptr(out), C.byref(lay), _stream()))
         return out
 
@@ -282,19 +326,29 @@ def add_residual_i8(a: torch.Tensor, b: torch.Tensor, s_main: float, s_res: floa
 
 
 def maxpool_i8(x: torch.Tensor, pool: int, stride: int, pad: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    x = x.contiguous()
+    in_pitch = _row_pitch(x) if x.dim() == 4 else None
+    if in_pitch is None:
+        x = x.contiguous()
+        in_pitch = x.shape[-1]
     H, W = x.shape[-2:]
     Ho, Wo = (H + 2 * pad - pool) // stride + 1, (W + 2 * pad - pool) // stride + 1
     if out is None:
         out = torch.empty(x.shape[:-2] + (Ho, Wo), dtype=torch.int8, device=x.device)
-    check(_lib.lib().accel_maxpool_i8(_ptr(x), _ptr(out), x.numel() // (H * W), H, W, pool, stride, pad, _stream()))
+    out_pitch = _row_pitch(out) if out.dim() == 4 else Wo
+    if out_pitch is None:
+        raise AcceleratorError(_lib.INVALID_CONFIG, "output must be dense or have padded rows")
+    n_planes = int(np.prod(x.shape[:-2]))
+    check(_lib.lib().accel_maxpool_i8(_ptr(x), _ptr(out), n_planes, H, W, pool, stride, pad, in_pitch, out_pitch, _stream()))
     return out
 
 
 def avgpool_i8(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    x = x.contiguous()
+    in_pitch = _row_pitch(x) if x.dim() == 4 else None
+    if in_pitch is None:
+        x = x.contiguous()
+        in_pitch = x.shape[-1]
     H, W = x.shape[-2:]
     if out is None:
         out = torch.empty(x.shape[:-2], dtype=torch.int8, device=x.device)
-    check(_lib.lib().accel_avgpool_i8(_ptr(x), _ptr(out), x.numel() // (H * W), H, W, _stream()))
+    check(_lib.lib().accel_avgpool_i8(_ptr(x), _ptr(out), int(np.prod(x.shape[:-2])), H, W, in_pitch, _stream()))
     return out
