@@ -1,5 +1,6 @@
 // C ABI of libaccel_b200.so (declared in include/accel_b200.h).  Thin: validate, fill the kernel
 // parameter block, launch on the caller's stream.  No device allocation, no CPU arithmetic.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <array>
@@ -118,6 +119,35 @@ bool residual_fast_divide_ok(float s_main, float s_res, float s_out) {
   return ok;
 }
 
+// ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda needed)
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// int8 tensor, dims / box innermost first, strides in bytes for dims 1..rank-1 (multiples of 16)
+bool encode_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                 const uint32_t* box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs, bx, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int MODE>
 cudaError_t launch_mode(const accel::TcLaunch& L, unsigned ctas, int smem, cudaStream_t st) {
   accel::bsr_tc_kernel<MODE><<<ctas, accel::kThreads, smem, st>>>(L);
@@ -125,7 +155,8 @@ cudaError_t launch_mode(const accel::TcLaunch& L, unsigned ctas, int smem, cudaS
 }
 
 // One or more launches: each carries the schedule tables of a range of block-row groups in its parameter block.
-int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cudaStream_t st) {
+int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cudaStream_t st,
+              const CUtensorMap* tmap = nullptr) {
   std::call_once(g_attr_once, set_kernel_attrs);
   if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(smem)");
   const int n_groups = static_cast<int>(P->groups.size());
@@ -153,6 +184,7 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cu
     if (g1 == g0) return fail(ACCEL_INVALID_CONFIG, "block-row group exceeds the launch tables");
     const uint32_t b0 = P->groups[g0].batch_begin, o0 = P->groups[g0].op_begin;
     L.p = prm;
+    if (tmap) L.tmap = *tmap;
     L.n_groups = static_cast<uint32_t>(g1 - g0);
     for (int g = g0; g < g1; ++g) {
       accel::GroupRec G = P->groups[g];
@@ -313,11 +345,16 @@ int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64_t M, int6
   prm.x_align2 = ((reinterpret_cast<uintptr_t>(act) | static_cast<uintptr_t>(lda)) & 1) == 0;
   prm.epi = *epi; prm.out = out; prm.lay = *layout;
   const bool ring = ((reinterpret_cast<uintptr_t>(act) | static_cast<uintptr_t>(lda)) & 15) == 0;
-  if (ring) {   // 16-byte aligned rows: the loader warp streams them into the shared-memory ring
+  if (ring) {   // 16-byte aligned rows: streamed into the shared-memory ring, by TMA when a descriptor can be made
     prm.ring_slots = accel::kMaxRingSlots;
     prm.slot_bytes = accel::kGemmSlotBytes;
+    CUtensorMap tm;
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(lda)};
+    const uint32_t box[2] = {144, accel::kTileM};
+    prm.use_tma = (M > 0 && K > 0 && encode_tmap(&tm, act, 2, dims, strides, box)) ? 1 : 0;
     return launch_tc(&plan->p, prm, accel::kModeGemm, accel::kSmemRing + prm.ring_slots * prm.slot_bytes + accel::kRingSlack,
-                     static_cast<cudaStream_t>(stream));
+                     static_cast<cudaStream_t>(stream), prm.use_tma ? &tm : nullptr);
   }
   return launch_tc(&plan->p, prm, accel::kModeDirect, accel::kSmemRing, static_cast<cudaStream_t>(stream));
 }
@@ -347,6 +384,7 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
   if (prm.Wp < g->w) return fail(ACCEL_INVALID_CONFIG, "in_row_pitch smaller than the row");
   if (prm.M > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "more than 2^31 output positions");
   prm.conv = 1;
+  prm.x_small = static_cast<int64_t>(g->batch) * g->c_in * g->h * prm.Wp < (1ll << 32);
   prm.epi = *epi; prm.out = out; prm.lay = *layout;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((g->ksize == 3 || g->ksize == 7) && g->pad <= 3) {
@@ -374,13 +412,37 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
       pitch = ((g->w + 3) / 4) * 4 + 8;                              // 4 zero bytes left, >= 4 right (pad <= 3)
     }
     const int nch = (gps % ks == 0) ? gps / ks : (gps + ks - 2) / ks + 1;
-    const int64_t slot = ((static_cast<int64_t>(nch) * hr * pitch + 15) / 16) * 16;
-    int slots = 0;
     const int fixed = accel::kSmemRing + accel::kRingSlack;
-    if (fixed + 3 * slot <= kSmemTwoCtas) slots = 3;
-    else if (fixed + 2 * slot <= kSmemTwoCtas) slots = 2;
-    else if (fixed + 3 * slot <= kSmemOneCta) slots = 3;
-    else if (fixed + 2 * slot <= kSmemOneCta) slots = 2;
+    auto pick_slots = [&](int64_t slot_bytes) {
+      if (fixed + 3 * slot_bytes <= kSmemTwoCtas) return 3;
+      if (fixed + 2 * slot_bytes <= kSmemTwoCtas) return 2;
+      if (fixed + 3 * slot_bytes <= kSmemOneCta) return 3;
+      if (fixed + 2 * slot_bytes <= kSmemOneCta) return 2;
+      return 0;
+    };
+    if (vec == 16 && g->batch > 0) {
+      // TMA: one [nch][rows][pitch] box per image the tile touches; everything outside the tensor reads as zero
+      const int ro_seg = ro < prm.Ho ? ro : prm.Ho;
+      const int rows = (ro_seg - 1) * g->stride + ks;
+      const int64_t seg = ((static_cast<int64_t>(nch) * rows * pitch + 127) / 128) * 128;
+      const int slots_t = pick_slots(ni * seg);
+      CUtensorMap tm;
+      const uint64_t Wp = static_cast<uint64_t>(prm.Wp);
+      const uint64_t dims[4] = {static_cast<uint64_t>(g->w), static_cast<uint64_t>(g->h), static_cast<uint64_t>(g->c_in),
+                                static_cast<uint64_t>(g->batch)};
+      const uint64_t strides[3] = {Wp, Wp * g->h, Wp * g->h * g->c_in};
+      const uint32_t box[4] = {static_cast<uint32_t>(pitch), static_cast<uint32_t>(rows), static_cast<uint32_t>(nch), 1u};
+      if (slots_t && pitch <= 256 && rows <= 256 && encode_tmap(&tm, input_nchw, 4, dims, strides, box)) {
+        prm.use_tma = 1;
+        prm.ring_slots = slots_t; prm.slot_bytes = static_cast<int32_t>(ni * seg); prm.seg_bytes = static_cast<int32_t>(seg);
+        prm.box_bytes = nch * rows * pitch;
+        prm.halo_rows = rows; prm.halo_pitch = pitch; prm.halo_lpad = lpad; prm.halo_nch = nch; prm.halo_vec = 16;
+        return launch_tc(&plan->p, prm, ks == 3 ? accel::kModeConv3 : accel::kModeConv7,
+                         fixed + slots_t * static_cast<int>(ni * seg), st, &tm);
+      }
+    }
+    const int64_t slot = ((static_cast<int64_t>(nch) * hr * pitch + 15) / 16) * 16;
+    const int slots = pick_slots(slot);
     if (slots && ro < accel::kMaxOutRows && hr <= accel::kMaxHaloRows) {
       prm.ring_slots = slots; prm.slot_bytes = static_cast<int32_t>(slot);
       prm.halo_rows = hr; prm.halo_pitch = pitch; prm.halo_lpad = lpad; prm.halo_nch = nch;

@@ -28,6 +28,8 @@
 //   warp 13     activation loader: cp.async (LDGSTS) of GEMM rows / conv input rows into the activation ring,
 //               running up to 3 stages ahead of the producers.
 #pragma once
+#include <cuda.h>
+
 #include <climits>
 #include <cstdint>
 #include <cstdio>
@@ -74,6 +76,7 @@ struct TcParams {
   int32_t K;
   int64_t lda;
   int32_t x_align2;     // DIRECT GEMM: base pointer and lda are even -> 16-bit loads
+  int32_t x_small;      // the activation tensor spans < 4 GiB: 32-bit byte offsets
   int32_t conv;         // DIRECT: 0 = GEMM rows, 1 = convolution gather
   // conv geometry
   int32_t C, H, W, ksz, stride, pad, Ho, Wo;
@@ -88,6 +91,10 @@ struct TcParams {
   int32_t halo_vec;     // copy granularity: 16 / 4 (cp.async of aligned rows) or 0 (any alignment, through registers)
   int32_t halo_ipr;     // copy items per input row
   uint32_t ipr_magic;   // ceil(2^32 / halo_ipr)
+  int32_t use_tma;      // activations arrive by TMA tensor tiles (16-byte aligned rows): GEMM 144 B x 128 rows per stage,
+                        // conv one [planes][halo_rows][halo_pitch] box per image the tile touches (out-of-bounds = 0)
+  int32_t seg_bytes;    // conv + TMA: bytes reserved for one image segment inside a ring slot (128-byte multiple)
+  int32_t box_bytes;    // conv + TMA: bytes one tensor tile delivers (planes x rows x pitch)
   // weights
   const uint8_t* blob;
   // epilogue
@@ -101,6 +108,7 @@ struct TcParams {
 };
 
 struct TcLaunch {
+  alignas(64) CUtensorMap tmap;   // activation tensor (use_tma)
   TcParams p;
   uint32_t n_groups;
   uint32_t pad_;
@@ -297,9 +305,10 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
     for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 4); mbar_init(&x_empty[s], kIssuers); }
     for (int s = 0; s < kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kIssuers); }
     mbar_init(acc_full, kIssuers);
-    for (int s = 0; s < kMaxRingSlots; ++s) { mbar_init(&h_full[s], 32); mbar_init(&h_empty[s], 4); }
+    // h_full: 32 loader lanes arrive (cp.async / register path), or one arrival + transaction bytes (TMA)
+    for (int s = 0; s < kMaxRingSlots; ++s) { mbar_init(&h_full[s], p.use_tma ? 1 : 32); mbar_init(&h_empty[s], 4); }
     fence_mbar_init();
-  } else if (kHalo && threadIdx.x == 32) {
+  } else if (kHalo && !p.use_tma && threadIdx.x == 32) {
     int hb = 0;
     uint32_t n = R0 / static_cast<uint32_t>(p.Ho);
     uint32_t oh = R0 - n * p.Ho;
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
     s_scale[threadIdx.x] = (ok && p.epi.chan_scale) ? p.epi.chan_scale[c] : 0.f;
     s_bias[threadIdx.x] = (ok && p.epi.bias) ? p.epi.bias[c] : 0;
   }
-  if constexpr (kHalo) {
+  if (kHalo && !p.use_tma) {
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + kSmemRing);
     const int ring_words = (p.ring_slots * p.slot_bytes + kRingSlack) >> 2;
     for (int i = threadIdx.x; i < ring_words; i += kThreads) ring[i] = 0u;   // pads must read as zero
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   int hr_used = 0;
-  if constexpr (kHalo) {
+  if (kHalo && !p.use_tma) {
     hr_used = s_hbase[kMaxOutRows - 1];
     for (int i = threadIdx.x; i < n_out_rows * p.ksz; i += kThreads) {
       const int rr = i / p.ksz, kh = i - rr * p.ksz;
@@ -374,9 +383,17 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
       img = R / static_cast<uint32_t>(p.Ho);
       oh = static_cast<int>(R - img * p.Ho);
       if constexpr (kHalo) {
-        const int rr = static_cast<int>(R - R0);
         const uint32_t xb = static_cast<uint32_t>(ow * p.stride - p.pad + p.halo_lpad);
-        thr_off = static_cast<uint32_t>(s_hbase[rr]) * p.halo_pitch + (xb & ~3u);
+        if (p.use_tma) {
+          // one box per image: rows start at the first input row of the image's first output row in this tile
+          const uint32_t img0 = R0 / static_cast<uint32_t>(p.Ho);
+          const uint32_t seg = img - img0;
+          const int ohf = seg == 0 ? static_cast<int>(R0 - img0 * p.Ho) : 0;
+          thr_off = seg * static_cast<uint32_t>(p.seg_bytes) + static_cast<uint32_t>((oh - ohf) * p.stride) * p.halo_pitch + (xb & ~3u);
+        } else {
+          const int rr = static_cast<int>(R - R0);
+          thr_off = static_cast<uint32_t>(s_hbase[rr]) * p.halo_pitch + (xb & ~3u);
+        }
         sh8 = (xb & 3u) * 8u;
       }
     }
@@ -612,6 +629,82 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
     __syncwarp();
   } else if (kRing) {
     // =================================================================== activation loader
+    if (p.use_tma) {
+      // One elected thread, one TMA tensor tile per stage (GEMM) or per image the tile touches (conv); rows,
+      // columns, channels and images outside the tensor arrive as zeros - that is the convolution's padding.
+      if (elect_one()) {
+        uint32_t n_seg = 1, img0 = 0;
+        int ih_first = 0;
+        if constexpr (kHalo) {
+          img0 = R0 / static_cast<uint32_t>(p.Ho);
+          const uint32_t m_last = static_cast<uint32_t>(m0 + kTileM - 1 < p.M ? m0 + kTileM - 1 : p.M - 1);
+          n_seg = m_last / static_cast<uint32_t>(p.Ho * p.Wo) - img0 + 1;
+          ih_first = static_cast<int>(R0 - img0 * p.Ho) * p.stride - p.pad;
+        }
+        const uint32_t box_bytes = kHalo ? static_cast<uint32_t>(p.box_bytes) : static_cast<uint32_t>(kGemmSlotBytes);
+        uint32_t step = 0;
+        for (uint32_t b = g_bb; b < g_be; ++b) {
+          const uint32_t bw = L.batches[b];
+          if (!(bw & kBatchFirst)) continue;
+          const uint32_t slot = step % static_cast<uint32_t>(p.ring_slots);
+          const uint32_t sphase = (step / static_cast<uint32_t>(p.ring_slots)) & 1u;
+          ++step;
+          mbar_wait(&h_empty[slot], sphase ^ 1u);
+          const int chunk = static_cast<int>(bw >> 16);
+          const uint32_t dst = ring_addr + slot * p.slot_bytes;
+          mbar_arrive_expect_tx(&h_full[slot], n_seg * box_bytes);
+          if constexpr (MODE == kModeGemm) {
+            tma_load_2d(dst, &L.tmap, (chunk * kChunkTiles * kBlock) & ~15, static_cast<int>(m0), &h_full[slot]);
+          } else {
+            const int c_first = (chunk * (126 / KS)) / KS;
+            for (uint32_t sg = 0; sg < n_seg; ++sg)
+              tma_load_4d(dst + sg * p.seg_bytes, &L.tmap, -p.halo_lpad, sg == 0 ? ih_first : -p.pad, c_first,
+                          static_cast<int>(img0 + sg), &h_full[slot]);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+    // A single warp issues ~1 dependent instruction per 5 cycles, so everything that does not change from stage
+    // to stage is computed once per tile and kept in registers: a copy then costs an add, a compare and the LDGSTS.
+    constexpr int kLd = kHalo ? 8 : 9;
+    uint32_t l_src[kLd];      // conv: byte offset of the piece inside channel plane 0 of the stage; GEMM: low word of the row offset
+    uint32_t l_meta[kLd];     // conv: smem offset / 4 | bytes << 16, 0xffffffff = nothing to copy
+    [[maybe_unused]] uint32_t l_src_hi[kHalo ? 1 : 9];
+    bool l_fast = false;
+    if constexpr (kHalo) {
+      // a lane owns up to 8 (input row, 16- or 4-byte piece) pairs and copies them for every channel plane
+      const int items = hr_used * p.halo_ipr;
+      const int piece = p.halo_vec == 16 ? 16 : 4;
+      l_fast = p.halo_vec != 0 && items <= 32 * kLd && p.x_small;
+#pragma unroll
+      for (int i = 0; i < kLd; ++i) {
+        const int idx = lane + 32 * i;
+        l_src[i] = 0; l_meta[i] = 0xffffffffu;
+        if (l_fast && idx < items) {
+          const int h = p.halo_ipr > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), p.ipr_magic)) : idx;
+          const int wd = idx - h * p.halo_ipr;
+          const int64_t off = s_rowoff[h];
+          if (off >= 0) {      // rows outside the image are never written: the ring was zeroed in the prologue
+            const int nb = min(piece, p.W - wd * piece);
+            const uint32_t d = static_cast<uint32_t>(h * p.halo_pitch + p.halo_lpad + wd * piece);
+            l_src[i] = static_cast<uint32_t>(off + wd * piece);
+            l_meta[i] = (d >> 2) | (static_cast<uint32_t>(nb) << 16);
+          }
+        }
+      }
+    } else {
+      // GEMM: item = it * 32 + lane covers (row = item / 9, 16-byte piece = item % 9); items 288 apart are 32 rows apart
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int item = i * 32 + lane;
+        const int row = item / 9, ch = item - row * 9;
+        const int64_t o = (m0 + row) * p.lda + ch * 16;
+        l_src[i] = static_cast<uint32_t>(o);
+        l_src_hi[i] = static_cast<uint32_t>(o >> 32);
+        l_meta[i] = static_cast<uint32_t>(row * 144 + ch * 16) | (static_cast<uint32_t>(row) << 16);
+      }
+    }
     uint32_t step = 0;
     for (uint32_t b = g_bb; b < g_be; ++b) {
       const uint32_t bw = L.batches[b];
@@ -619,22 +712,36 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
       const uint32_t slot = step % static_cast<uint32_t>(p.ring_slots);
       const uint32_t sphase = (step / static_cast<uint32_t>(p.ring_slots)) & 1u;
       ++step;
+      if (tl && lane == 0 && step <= 2) tl[24 + 2 * (step - 1)] = clock64();
       mbar_wait(&h_empty[slot], sphase ^ 1u);
       const int chunk = static_cast<int>(bw >> 16);
       uint8_t* dst_slot = smem + kSmemRing + slot * p.slot_bytes;
       if constexpr (MODE == kModeGemm) {
         const int a0 = (chunk * kChunkTiles * kBlock) & ~15;
-#pragma unroll 4
-        for (int it = 0; it < 36; ++it) {
-          const int item = it * 32 + lane;
-          const int row = item / 9, ch = item - row * 9;
-          const int64_t gm = m0 + row;
-          const int ka = a0 + ch * 16;
-          int nbytes = p.K - ka;
-          nbytes = nbytes > 16 ? 16 : (nbytes < 0 ? 0 : nbytes);
-          if (gm >= p.M) nbytes = 0;
-          const int8_t* g = nbytes ? p.x + gm * p.lda + ka : p.x;
-          cp_async16_zfill(dst_slot + row * 144 + ch * 16, g, nbytes);
+        const uint32_t slot_addr = ring_addr + slot * p.slot_bytes;
+        const int64_t row32 = 32 * p.lda;
+        if (a0 + 144 <= p.K && m0 + kTileM <= p.M) {          // interior: no clamping
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const int8_t* g = p.x + ((static_cast<int64_t>(l_src_hi[i]) << 32) | l_src[i]) + a0;
+            const uint32_t d = slot_addr + (l_meta[i] & 0xffffu);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) cp_async16_zfill_s(d + r * (32 * 144), g + r * row32, 16);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const int ch16 = static_cast<int>((l_meta[i] & 0xffffu) % 144u);
+            int nbytes = p.K - (a0 + ch16);
+            nbytes = nbytes > 16 ? 16 : (nbytes < 0 ? 0 : nbytes);
+            const int8_t* g = p.x + ((static_cast<int64_t>(l_src_hi[i]) << 32) | l_src[i]) + a0;
+            const uint32_t d = slot_addr + (l_meta[i] & 0xffffu);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const bool ok = m0 + static_cast<int64_t>(l_meta[i] >> 16) + 32 * r < p.M && nbytes > 0;
+              cp_async16_zfill_s(d + r * (32 * 144), ok ? g + r * row32 : p.x, ok ? nbytes : 0);
+            }
+          }
         }
         cp_async_mbar_arrive(&h_full[slot]);
       } else {
@@ -646,6 +753,26 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
         const uint32_t cs = static_cast<uint32_t>(p.halo_rows) * p.halo_pitch;
         const int64_t HW = static_cast<int64_t>(p.H) * p.Wp;
         const int nch = min(p.halo_nch, p.C - c_first);
+        if (l_fast) {
+          const int8_t* base = p.x + c_first * HW;
+          const uint32_t slot_addr = ring_addr + slot * p.slot_bytes;
+#pragma unroll
+          for (int i = 0; i < kLd; ++i) {
+            if (l_meta[i] == 0xffffffffu) continue;
+            const int8_t* g = base + l_src[i];
+            const uint32_t d = slot_addr + ((l_meta[i] & 0xffffu) << 2);
+            const int nb = static_cast<int>(l_meta[i] >> 16);
+            if (p.halo_vec == 16) {
+#pragma unroll
+              for (int c = 0; c < 14; ++c)
+                if (c < nch) cp_async16_zfill_s(d + c * cs, g + c * HW, nb);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 14; ++c)
+                if (c < nch) cp_async4_zfill_s(d + c * cs, g + c * HW, 4);
+            }
+          }
+        } else
         for (int idx = lane; idx < items; idx += 32) {
           const int h = ipr > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), p.ipr_magic)) : idx;
           const int wd = idx - h * ipr;
@@ -698,11 +825,14 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
             }
           }
         }
+        if (tl && lane == 0 && step <= 2) tl[28 + (step - 1)] = clock64();
         if (p.halo_vec) cp_async_mbar_arrive(&h_full[slot]);
         else mbar_arrive(&h_full[slot]);
+        if (tl && lane == 0 && step <= 2) tl[25 + 2 * (step - 1)] = clock64();
       }
     }
     cp_async_wait_all();
+    }
   }
 
   __syncthreads();

@@ -79,6 +79,13 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
                : "memory");
 }
+// same, destination given as a shared-space address
+__device__ __forceinline__ void cp_async16_zfill_s(uint32_t smem_dst, const void* gmem_src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill_s(uint32_t smem_dst, const void* gmem_src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
 // the mbarrier receives one arrival (of its expected count) once all earlier cp.async of this thread have landed
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -90,6 +97,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                    smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// ----------------------------------------------------------------------------- TMA tensor tiles (global -> smem)
+// Coordinates are element indices, innermost dimension first; they may lie outside the tensor (zero fill).
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
 }
 
 // ----------------------------------------------------------------------------- tcgen05: TMEM allocation

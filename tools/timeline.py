@@ -33,7 +33,8 @@ for name in os.environ.get("LAYER", "layer1.0.conv1,layer3.1.conv1").split(","):
     d = t - t[:, :1]
     names = ["entry", "prologue", "stage0 acquired", "stage0 published", "producers done", "acc complete", "epilogue done", "exit",
              "st2: start", "st2: h_full", "st2: x_empty", "st2: gathered", "st2: st_wait", "st2: published",
-             "epi0: top", "epi0: loaded", "-", "epi1: top", "epi1: loaded", "-", "epi2: top", "epi2: loaded", "-", "epi: loop end"]
+             "epi0: top", "epi0: loaded", "-", "epi1: top", "epi1: loaded", "-", "epi2: top", "epi2: loaded", "-", "epi: loop end",
+             "ld0: start", "ld0: issued", "ld1: start", "ld1: issued", "ld2: start", "ld2: issued", "ld3: start", "ld3: issued"]
     print(f"{name}: {len(t)} CTAs; median cycles since CTA entry (p10 / p50 / p90):")
     for i, n in enumerate(names):
         if n == "-":
