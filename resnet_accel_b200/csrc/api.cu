@@ -604,6 +604,13 @@ int accel_maxpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, 
   if (in_pitch < w || out_pitch < Wo) return fail(ACCEL_INVALID_CONFIG, "row pitch smaller than the row");
   const int64_t total = n_planes * Ho * ((Wo + 3) / 4);
   if (total <= 0) return ACCEL_OK;
+  if (pool == 3 && stride == 2 && pad == 1 && (in_pitch & 7) == 0 && (out_pitch & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+    accel::maxpool3x3s2_i8_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, out, n_planes, h, w, Ho, Wo, in_pitch, out_pitch);
+    CU(cudaGetLastError());
+    return ACCEL_OK;
+  }
   accel::maxpool_i8_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, out, n_planes, h, w, pool, stride, pad, Ho, Wo, in_pitch, out_pitch);
   CU(cudaGetLastError());

@@ -195,33 +195,52 @@ __device__ __forceinline__ void conv_extract(uint32_t (&w)[36], const uint32_t (
     conv_extract<KS, j, e + 1, NG>(w, g, sh8);
   }
 }
-template <int KS, int j>
-__device__ __forceinline__ void conv_group(uint32_t (&w)[36], uint32_t rp, uint32_t sh8, bool on) {
-  constexpr int NW = (KS + 3 + 3) / 4;      // words that can hold KS bytes at byte offset <= 3
-  uint32_t g[NW + 1];
+// Groups are processed in batches of kGB: all shared-memory loads of a batch are issued before the first
+// permute that consumes them, so the ~30-cycle load latency is paid once per batch instead of once per group.
+template <int KS>
+struct ConvBatch {
+  static constexpr int GPS = 126 / KS;
+  static constexpr int NW = (KS + 3 + 3) / 4;   // words that can hold KS bytes at byte offset <= 3
+  static constexpr int kGB = KS == 3 ? 7 : 3;   // 42 = 6 x 7 groups, 18 = 6 x 3 groups
+  static_assert(GPS % kGB == 0, "batch size must divide the groups of a stage");
+  template <int j0, int i>
+  static __device__ __forceinline__ void load(uint32_t (&g)[kGB][NW + 1], uint32_t& rp, uint32_t pitch, uint32_t cs, int& kh,
+                                              int groups_left) {
+    if constexpr (i < kGB) {
+      constexpr int j = j0 + i;
+      const bool on = j < groups_left;
 #pragma unroll
-  for (int i = 0; i < NW; ++i) g[i] = on ? lds32(rp + 4 * i) : 0u;
-  g[NW] = 0u;
-  conv_extract<KS, j, 0, NW + 1>(w, g, sh8);
-}
-
-template <int KS, int j>
-__device__ __forceinline__ void conv_groups(uint32_t (&w)[36], uint32_t xcol, uint32_t& rp, uint32_t sh8, uint32_t pitch,
-                                            uint32_t cs, int& kh, int groups_left) {
-  constexpr int GPS = 126 / KS;
-  if constexpr (j < GPS) {
-    conv_group<KS, j>(w, rp, sh8, j < groups_left);
-    // next group: next input row of this channel, or first row of the next channel plane
-    if constexpr (GPS % KS == 0) {          // stage-aligned channels (3x3): compile-time pattern
-      rp += ((j % KS) == KS - 1) ? (cs - (KS - 1) * pitch) : pitch;
-    } else {
-      ++kh;
-      if (kh == KS) { kh = 0; rp += cs - (KS - 1) * pitch; } else { rp += pitch; }
+      for (int q = 0; q < NW; ++q) g[i][q] = on ? lds32(rp + 4 * q) : 0u;
+      g[i][NW] = 0u;
+      if constexpr (GPS % KS == 0) {          // stage-aligned channels (3x3): compile-time pattern
+        rp += ((j % KS) == KS - 1) ? (cs - (KS - 1) * pitch) : pitch;
+      } else {
+        ++kh;
+        if (kh == KS) { kh = 0; rp += cs - (KS - 1) * pitch; } else { rp += pitch; }
+      }
+      load<j0, i + 1>(g, rp, pitch, cs, kh, groups_left);
     }
-    stream_flush<(j * KS) / 14, ((j + 1) * KS) / 14>(w, xcol);
-    conv_groups<KS, j + 1>(w, xcol, rp, sh8, pitch, cs, kh, groups_left);
   }
-}
+  template <int j0, int i>
+  static __device__ __forceinline__ void merge(uint32_t (&w)[36], const uint32_t (&g)[kGB][NW + 1], uint32_t sh8, uint32_t xcol) {
+    if constexpr (i < kGB) {
+      constexpr int j = j0 + i;
+      conv_extract<KS, j, 0, NW + 1>(w, g[i], sh8);
+      stream_flush<(j * KS) / 14, ((j + 1) * KS) / 14>(w, xcol);
+      merge<j0, i + 1>(w, g, sh8, xcol);
+    }
+  }
+  template <int j0>
+  static __device__ __forceinline__ void run(uint32_t (&w)[36], uint32_t xcol, uint32_t& rp, uint32_t sh8, uint32_t pitch,
+                                             uint32_t cs, int& kh, int groups_left) {
+    if constexpr (j0 < GPS) {
+      uint32_t g[kGB][NW + 1];
+      load<j0, 0>(g, rp, pitch, cs, kh, groups_left);
+      merge<j0, 0>(w, g, sh8, xcol);
+      run<j0 + kGB>(w, xcol, rp, sh8, pitch, cs, kh, groups_left);
+    }
+  }
+};
 
 // ---- GEMM: this thread's 144-byte window (9 x 16 B, the row's K range rounded down to 16) -> 9 tiles.
 template <int SHIFT>
@@ -254,9 +273,28 @@ struct EpiCtx {
   int lane;
 };
 
-template <int KIND>
+template <int KIND, bool SAT>
 __device__ __forceinline__ void epilogue_row(const TcParams& p, EpiCtx& ec, uint32_t (&v)[16], int cb, int n_ok,
                                              const float* sc, const int32_t* bi);
+
+// One activation stage by TMA: GEMM = rows [m0, m0+128) x 144 bytes from the 16-byte aligned column at or
+// before the stage's first k; conv = one [planes][rows][pitch] box per image the tile touches.
+template <int MODE>
+__device__ __forceinline__ void tma_stage(const TcLaunch& L, uint32_t dst, uint64_t* bar, int chunk, int64_t m0,
+                                          uint32_t n_seg, uint32_t img0, int ih_first) {
+  const TcParams& p = L.p;
+  if constexpr (MODE == kModeGemm) {
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(kGemmSlotBytes));
+    tma_load_2d(dst, &L.tmap, (chunk * kChunkTiles * kBlock) & ~15, static_cast<int>(m0), bar);
+  } else {
+    constexpr int KS = MODE == kModeConv7 ? 7 : 3;
+    mbar_arrive_expect_tx(bar, n_seg * static_cast<uint32_t>(p.box_bytes));
+    const int c_first = (chunk * (126 / KS)) / KS;
+    for (uint32_t sg = 0; sg < n_seg; ++sg)
+      tma_load_4d(dst + sg * p.seg_bytes, &L.tmap, -p.halo_lpad, sg == 0 ? ih_first : -p.pad, c_first,
+                  static_cast<int>(img0 + sg), bar);
+  }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_constant__ TcLaunch L) {
@@ -306,7 +344,8 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
     for (int s = 0; s < kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kIssuers); }
     mbar_init(acc_full, kIssuers);
     // h_full: 32 loader lanes arrive (cp.async / register path), or one arrival + transaction bytes (TMA)
-    for (int s = 0; s < kMaxRingSlots; ++s) { mbar_init(&h_full[s], p.use_tma ? 1 : 32); mbar_init(&h_empty[s], 4); }
+    if (!p.use_tma)
+      for (int s = 0; s < kMaxRingSlots; ++s) { mbar_init(&h_full[s], 32); mbar_init(&h_empty[s], 4); }
     fence_mbar_init();
   } else if (kHalo && !p.use_tma && threadIdx.x == 32) {
     int hb = 0;
@@ -322,6 +361,30 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
   if (warp == kProducerWarps) {
     tmem_alloc_dyn(tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  // TMA loader: owns the ring barriers and starts filling the ring before the rest of the CTA is set up
+  uint32_t n_seg = 1, img0 = 0;
+  int ih_first = 0;
+  if (kRing && p.use_tma && warp == kWarpALoad) {
+    if constexpr (kHalo) {
+      img0 = R0 / static_cast<uint32_t>(p.Ho);
+      const uint32_t m_last = static_cast<uint32_t>(m0 + kTileM - 1 < p.M ? m0 + kTileM - 1 : p.M - 1);
+      n_seg = m_last / static_cast<uint32_t>(p.Ho * p.Wo) - img0 + 1;
+      ih_first = static_cast<int>(R0 - img0 * p.Ho) * p.stride - p.pad;
+    }
+    if (elect_one()) {
+      for (int s = 0; s < kMaxRingSlots; ++s) { mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], 4); }
+      fence_mbar_init();
+      uint32_t step = 0;
+      for (uint32_t b = g_bb; b < g_be && step < static_cast<uint32_t>(p.ring_slots); ++b) {
+        const uint32_t bw = L.batches[b];
+        if (!(bw & kBatchFirst)) continue;
+        tma_stage<MODE>(L, smem_u32(smem + kSmemRing) + step * p.slot_bytes, &h_full[step], static_cast<int>(bw >> 16), m0,
+                        n_seg, img0, ih_first);
+        ++step;
+      }
+    }
+    __syncwarp();
   }
   // per-channel epilogue constants of this group
   if (threadIdx.x < g_rows * kBlock) {
@@ -448,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
         uint32_t w[36];
 #pragma unroll
         for (int i = 0; i < 36; ++i) w[i] = 0u;
-        conv_groups<KS, 0>(w, xcol, rp, sh8, p.halo_pitch, cs, kh, groups_left);
+        ConvBatch<KS>::template run<0>(w, xcol, rp, sh8, p.halo_pitch, cs, kh, groups_left);
       } else if (!p.conv) {
         // ---------------- DIRECT GEMM rows (unaligned base / leading dimension)
         const int8_t* src = p.x + m * p.lda + k_chunk0;
@@ -540,10 +603,12 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
     ec.sat = 0;
     ec.lane = lane;
     // one uniform decision per CTA: which specialised path handles every block-row of this tile
-    const bool plain = !p.epi.sat_count && !p.epi.chan_absmax;
+    const bool sat_on = p.epi.sat_count != nullptr;
     int kind = kEpiGeneric;
-    if (plain && (ec.flags & ACCEL_OUT_I8)) kind = !p.epi.residual ? kEpiI8 : (p.res_fast ? kEpiI8ResFast : kEpiI8Res);
-    else if (plain && (ec.flags & ACCEL_OUT_I32)) kind = kEpiI32;
+    if (!p.epi.chan_absmax && (ec.flags & ACCEL_OUT_I8))
+      kind = !p.epi.residual ? kEpiI8 : (p.res_fast ? kEpiI8ResFast : kEpiI8Res);
+    else if (!p.epi.chan_absmax && !sat_on && (ec.flags & ACCEL_OUT_I32)) kind = kEpiI32;
+    if (sat_on && kind != kEpiGeneric) kind += 8;
     for (uint32_t g = half; g < g_rows; g += 2) {
       uint32_t v[16];
       if (tl && threadIdx.x == 0 && g < 6) tl[14 + 3 * (g >> 1)] = clock64();
@@ -553,11 +618,14 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
       const float* sc = s_scale + g * kBlock;
       const int32_t* bi = s_bias + g * kBlock;
       switch (kind) {
-        case kEpiI8: epilogue_row<kEpiI8>(p, ec, v, cb, n_ok, sc, bi); break;
-        case kEpiI8ResFast: epilogue_row<kEpiI8ResFast>(p, ec, v, cb, n_ok, sc, bi); break;
-        case kEpiI8Res: epilogue_row<kEpiI8Res>(p, ec, v, cb, n_ok, sc, bi); break;
-        case kEpiI32: epilogue_row<kEpiI32>(p, ec, v, cb, n_ok, sc, bi); break;
-        default: epilogue_row<kEpiGeneric>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI8: epilogue_row<kEpiI8, false>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI8ResFast: epilogue_row<kEpiI8ResFast, false>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI8Res: epilogue_row<kEpiI8Res, false>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI8 + 8: epilogue_row<kEpiI8, true>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI8ResFast + 8: epilogue_row<kEpiI8ResFast, true>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI8Res + 8: epilogue_row<kEpiI8Res, true>(p, ec, v, cb, n_ok, sc, bi); break;
+        case kEpiI32: epilogue_row<kEpiI32, false>(p, ec, v, cb, n_ok, sc, bi); break;
+        default: epilogue_row<kEpiGeneric, false>(p, ec, v, cb, n_ok, sc, bi); break;
       }
       if (tl && threadIdx.x == 0 && g < 6) tl[15 + 3 * (g >> 1)] = clock64();
     }
@@ -633,15 +701,6 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
       // One elected thread, one TMA tensor tile per stage (GEMM) or per image the tile touches (conv); rows,
       // columns, channels and images outside the tensor arrive as zeros - that is the convolution's padding.
       if (elect_one()) {
-        uint32_t n_seg = 1, img0 = 0;
-        int ih_first = 0;
-        if constexpr (kHalo) {
-          img0 = R0 / static_cast<uint32_t>(p.Ho);
-          const uint32_t m_last = static_cast<uint32_t>(m0 + kTileM - 1 < p.M ? m0 + kTileM - 1 : p.M - 1);
-          n_seg = m_last / static_cast<uint32_t>(p.Ho * p.Wo) - img0 + 1;
-          ih_first = static_cast<int>(R0 - img0 * p.Ho) * p.stride - p.pad;
-        }
-        const uint32_t box_bytes = kHalo ? static_cast<uint32_t>(p.box_bytes) : static_cast<uint32_t>(kGemmSlotBytes);
         uint32_t step = 0;
         for (uint32_t b = g_bb; b < g_be; ++b) {
           const uint32_t bw = L.batches[b];
@@ -649,18 +708,10 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
           const uint32_t slot = step % static_cast<uint32_t>(p.ring_slots);
           const uint32_t sphase = (step / static_cast<uint32_t>(p.ring_slots)) & 1u;
           ++step;
+          if (step <= static_cast<uint32_t>(p.ring_slots)) continue;      // issued in the prologue
           mbar_wait(&h_empty[slot], sphase ^ 1u);
-          const int chunk = static_cast<int>(bw >> 16);
-          const uint32_t dst = ring_addr + slot * p.slot_bytes;
-          mbar_arrive_expect_tx(&h_full[slot], n_seg * box_bytes);
-          if constexpr (MODE == kModeGemm) {
-            tma_load_2d(dst, &L.tmap, (chunk * kChunkTiles * kBlock) & ~15, static_cast<int>(m0), &h_full[slot]);
-          } else {
-            const int c_first = (chunk * (126 / KS)) / KS;
-            for (uint32_t sg = 0; sg < n_seg; ++sg)
-              tma_load_4d(dst + sg * p.seg_bytes, &L.tmap, -p.halo_lpad, sg == 0 ? ih_first : -p.pad, c_first,
-                          static_cast<int>(img0 + sg), &h_full[slot]);
-          }
+          tma_stage<MODE>(L, ring_addr + slot * p.slot_bytes, &h_full[slot], static_cast<int>(bw >> 16), m0, n_seg, img0,
+                          ih_first);
         }
       }
       __syncwarp();
@@ -843,7 +894,7 @@ __global__ void __launch_bounds__(kThreads, 2) bsr_tc_kernel(const __grid_consta
   }
 }
 
-template <int KIND>
+template <int KIND, bool SAT>
 __device__ __forceinline__ void epilogue_row(const TcParams& p, EpiCtx& ec, uint32_t (&v)[16], int cb, int n_ok,
                                              const float* sc, const int32_t* bi) {
   const int64_t o0 = ec.out_base + static_cast<int64_t>(cb) * ec.cs;
@@ -867,7 +918,12 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, EpiCtx& ec, uint
 #pragma unroll
     for (int h = 0; h < kBlock; ++h) {
       const int acc = max(static_cast<int>(v[h]) + bia[h], ec.relu_lo);
-      int r8 = cvt_sat_s8(__fmul_rn(__int2float_rn(acc), scl[h]));
+      const float f = __fmul_rn(__int2float_rn(acc), scl[h]);
+      int r8 = cvt_sat_s8(f);
+      if constexpr (SAT) {
+        // round-half-even leaves [-128, 127] exactly when f >= 127.5 (-> 128) or f < -128.5 (-128.5 -> -128 stays)
+        ec.sat += (ec.row_ok && h < n_ok && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
+      }
       if constexpr (kRes) {
         const float a = __fmul_rn(__int2float_rn(r8), p.epi.res_scale_main);
         const float r = __fmul_rn(__int2float_rn(rv[h]), p.epi.res_scale_res);

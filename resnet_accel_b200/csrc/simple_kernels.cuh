@@ -297,6 +297,53 @@ __global__ void maxpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restri
     }
   }
 }
+// 3x3 / stride 2 / pad 1 (the ResNet stem pool) on 8-byte aligned rows: one thread = 4 adjacent outputs.  It
+// reads the 16 input columns [8q-8, 8q+8) of three rows with 8-byte loads, reduces vertically with packed byte
+// maxima (__vmaxs4), then horizontally on the even / odd / previous-odd columns.  HBM-bound byte work.
+__global__ void maxpool3x3s2_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out, int64_t n_planes, int32_t H,
+                                       int32_t W, int32_t Ho, int32_t Wo, int32_t in_pitch, int32_t out_pitch) {
+  const int wq = (Wo + 3) >> 2;
+  const int64_t total = n_planes * Ho * wq;
+  constexpr uint32_t kNeg = 0x80808080u;   // -128 in every byte: what padding contributes to a maximum
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(idx % wq), oh = static_cast<int>((idx / wq) % Ho);
+    const int64_t pl = idx / (static_cast<int64_t>(wq) * Ho);
+    const int c0 = 8 * q;                              // first input column of the "current" 8 columns
+    uint32_t v[4] = {kNeg, kNeg, kNeg, kNeg};          // columns c0-8 .. c0+7, vertical maximum
+    const int8_t* xp = x + pl * static_cast<int64_t>(H) * in_pitch;
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+      const int ih = 2 * oh - 1 + ph;
+      if (ih < 0 || ih >= H) continue;
+      const int8_t* row = xp + static_cast<int64_t>(ih) * in_pitch;
+      uint2 lo = make_uint2(kNeg, kNeg), hi = make_uint2(kNeg, kNeg);
+      if (c0 >= 8) lo = *reinterpret_cast<const uint2*>(row + c0 - 8);
+      if (c0 < W) hi = *reinterpret_cast<const uint2*>(row + c0);
+      uint32_t w4[4] = {lo.x, lo.y, hi.x, hi.y};
+      if (c0 + 8 > W) {                                // columns past the row's end (pitch padding) are padding
+#pragma unroll
+        for (int j = 2; j < 4; ++j)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (c0 + (j - 2) * 4 + b >= W) w4[j] = (w4[j] & ~(0xffu << (8 * b))) | (0x80u << (8 * b));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __vmaxs4(v[j], w4[j]);
+    }
+    // output o (0..3) = max over columns c0 + 2o - 1, c0 + 2o, c0 + 2o + 1
+    const uint32_t even = __byte_perm(v[2], v[3], 0x6420);        // columns c0+0, +2, +4, +6
+    const uint32_t odd = __byte_perm(v[2], v[3], 0x7531);         // columns c0+1, +3, +5, +7
+    const uint32_t podd = __byte_perm(v[1], odd, 0x6543);         // columns c0-1, +1, +3, +5
+    const uint32_t r = __vmaxs4(__vmaxs4(even, odd), podd);
+    int8_t* orow = out + (pl * Ho + oh) * static_cast<int64_t>(out_pitch) + 4 * q;
+    if (4 * q + 3 < Wo) {
+      *reinterpret_cast<uint32_t*>(orow) = r;
+    } else {
+      for (int o = 0; o < 4 && 4 * q + o < Wo; ++o) orow[o] = static_cast<int8_t>((r >> (8 * o)) & 0xffu);
+    }
+  }
+}
 // one warp per plane: (sum + HW/2) / HW with C truncating division (golden_models.cpp:619)
 __global__ void avgpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out, int64_t n_planes,
                                   int32_t H, int32_t W, int32_t in_pitch) {

@@ -64,3 +64,61 @@ def test_conv_layer_vs_oracle(B, Cin, H, W, Cout, k, s, p, density):
     ref32, _ = O.conv2d_bsr_layer(x[:1], bsr["indptr"], bsr["indices"], bsr["data"], Cout, k, s, p, bias=bias)
     out32 = plan.conv(xd[:1], k, s, p, Cout, out_kind="i32", bias=bias).cpu().numpy()
     assert np.array_equal(out32, ref32)
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k,s,p", [
+    (3, 3, 40, 48, 20, 7, 2, 3),        # stem family, rows already 16-byte aligned (dense, W % 16 == 0)
+    (2, 30, 28, 28, 40, 3, 1, 1),       # padded rows: TMA tiles, one image per tile
+    (6, 16, 7, 7, 32, 3, 1, 1),         # 49 positions per image: one tile spans three images (three TMA boxes)
+    (2, 20, 30, 30, 24, 3, 2, 1),       # stride 2
+    (1, 64, 56, 56, 64, 3, 1, 1),       # ResNet-18 layer1 geometry
+])
+def test_conv_padded_rows_tma_path(B, Cin, H, W, Cout, k, s, p):
+    """Activations with 16-byte aligned rows (ops.alloc_padded) take the TMA loader; output rows padded as well, and
+    the residual read through the same padded layout.  Bit-exact against the oracle, pad bytes stay zero."""
+    import torch
+    from resnet_accel_b200 import ops
+    rng = np.random.default_rng(B + Cin + H + Cout)
+    K = Cin * k * k
+    Wm = rng.integers(-128, 128, (Cout, K), dtype=np.int8)
+    nbr, nbc = -(-Cout // 14), -(-K // 14)
+    keep = rng.random((nbr, nbc)) < 0.4
+    Wm = Wm * np.repeat(np.repeat(keep, 14, 0), 14, 1)[:Cout, :K].astype(np.int8)
+    bsr = O.build_bsr_14x14_int8_direct(Wm)
+    x = rng.integers(-128, 128, (B, Cin, H, W), dtype=np.int8)
+    bias = rng.integers(-1000, 1000, Cout, dtype=np.int32)
+    sf = rng.uniform(1e-4, 2e-3, Cout).astype(np.float32)
+    Ho, Wo = O.conv_out_hw(H, W, k, s, p)
+    res = rng.integers(-128, 128, (B, Cout, Ho, Wo), dtype=np.int8)
+    plan = _plan(bsr)
+    xd = ops.alloc_padded(x.shape)
+    xd.copy_(torch.from_numpy(x).cuda())
+    rd = ops.alloc_padded(res.shape)
+    rd.copy_(torch.from_numpy(res).cuda())
+    out = ops.alloc_padded(res.shape)
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    plan.conv(xd, k, s, p, Cout, out_kind="i8", chan_scale=sf, bias=bias, relu=False, residual=rd,
+              res_scales=(0.05, 0.05, 0.05), sat_count=cnt, relu_out=True, out=out)
+    ref, sat = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, k, s, p, bias=bias,
+                                       relu=False, sf=sf, residual=res, res_scales=(0.05, 0.05, 0.05))
+    assert np.array_equal(out.cpu().numpy(), np.maximum(ref, 0))
+    assert int(cnt.item()) == sat
+    base = out._base if out._base is not None else out
+    assert int(base[..., Wo:].abs().sum().item()) == 0          # the epilogue never writes the row padding
+    ref32, _ = O.conv2d_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, k, s, p, bias=bias)
+    assert np.array_equal(plan.conv(xd, k, s, p, Cout, out_kind="i32", bias=bias).cpu().numpy(), ref32)
+
+
+def test_pools_padded_rows():
+    import torch
+    from resnet_accel_b200 import ops
+    rng = np.random.default_rng(5)
+    x = rng.integers(-128, 128, (3, 5, 30, 44), dtype=np.int8)
+    xd = ops.alloc_padded(x.shape)
+    xd.copy_(torch.from_numpy(x).cuda())
+    out = ops.alloc_padded((3, 5, 15, 22))
+    ops.maxpool_i8(xd, 3, 2, 1, out=out)                          # 3x3/2 pad 1: the vectorised stem pool
+    want = np.stack([O.maxpool2d_int8(x[b], 3, 2, 1) for b in range(3)])
+    assert np.array_equal(out.cpu().numpy(), want)
+    got = ops.avgpool_i8(xd).cpu().numpy()
+    assert np.array_equal(got, np.stack([O.avgpool_global_int8(x[b]) for b in range(3)]))
