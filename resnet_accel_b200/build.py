@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaccel_b200.so")
 SOURCES = ["api.cu", "plan.cpp"]
-DEPS = ["api.cu", "plan.cpp", "plan.h", "ptx.cuh", "bsr_tc.cuh", "simple_kernels.cuh",
+DEPS = ["api.cu", "plan.cpp", "plan.h", "ptx.cuh", "bsr_tc.cuh", "bsr_tcp.cuh", "simple_kernels.cuh",
         os.path.join("..", "..", "include", "accel_b200.h")]
 
 

@@ -14,6 +14,7 @@
 
 #include "../../include/accel_b200.h"
 #include "bsr_tc.cuh"
+#include "bsr_tcp.cuh"
 #include "plan.h"
 #include "simple_kernels.cuh"
 
@@ -53,10 +54,12 @@ int grid_for(int64_t work_items, int threads, int per_sm = 8) {
 
 long long* g_timeline = nullptr;   // accel_debug_set_timeline
 int g_dbg_flags = 0;
+bool g_no_persist = std::getenv("ACCEL_NO_PERSIST") != nullptr;   // developer switch: one-shot kernel everywhere
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
 constexpr int kSmemTwoCtas = 113 * 1024;    // per CTA when two CTAs share an SM (227 KB usable, 1 KB reserved each)
 constexpr int kSmemOneCta = 200 * 1024;
+constexpr int kSmemPersist = 220 * 1024;    // the persistent kernel owns its SM
 void set_kernel_attrs() {
   const void* fns[] = {reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeGemm>),
                        reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeConv3>),
@@ -65,6 +68,13 @@ void set_kernel_attrs() {
   for (const void* f : fns) {
     if (g_attr_err == cudaSuccess)
       g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOneCta);
+  }
+  const void* pfns[] = {reinterpret_cast<const void*>(accel::bsr_tcp_kernel<accel::kModeGemm>),
+                        reinterpret_cast<const void*>(accel::bsr_tcp_kernel<accel::kModeConv3>),
+                        reinterpret_cast<const void*>(accel::bsr_tcp_kernel<accel::kModeConv7>)};
+  for (const void* f : pfns) {
+    if (g_attr_err == cudaSuccess)
+      g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPersist);
   }
 }
 
@@ -149,6 +159,13 @@ bool encode_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* di
 }
 
 template <int MODE>
+cudaError_t launch_persistent(const accel::TcLaunch& L, unsigned items, int smem, cudaStream_t st) {
+  const unsigned ctas = items < static_cast<unsigned>(sm_count()) ? items : static_cast<unsigned>(sm_count());
+  accel::bsr_tcp_kernel<MODE><<<ctas, accel::kPThreads, smem, st>>>(L, items);
+  return cudaGetLastError();
+}
+
+template <int MODE>
 cudaError_t launch_mode(const accel::TcLaunch& L, unsigned ctas, int smem, cudaStream_t st) {
   accel::bsr_tc_kernel<MODE><<<ctas, accel::kThreads, smem, st>>>(L);
   return cudaGetLastError();
@@ -168,6 +185,16 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cu
   if (prm.epi.residual) {
     prm.res_fast = residual_fast_divide_ok(prm.epi.res_scale_main, prm.epi.res_scale_res, prm.epi.res_scale_out) ? 1 : 0;
     prm.res_rcp = 1.0f / prm.epi.res_scale_out;
+  }
+  // TMA-fed launches run the persistent kernel (one CTA per SM, every role keeps going across tiles)
+  bool persistent = prm.use_tma && tmap && mode != accel::kModeDirect && !g_no_persist;
+  int psmem = 0;
+  if (persistent) {
+    const int avail = kSmemPersist - accel::kPSmemRing - accel::kRingSlack;
+    int slots = avail / prm.slot_bytes;
+    if (slots > accel::kPMaxRingSlots) slots = accel::kPMaxRingSlots;
+    if (slots < 2) persistent = false;
+    else { prm.ring_slots = slots; psmem = accel::kPSmemRing + slots * prm.slot_bytes + accel::kRingSlack; }
   }
   static thread_local accel::TcLaunch L;    // 28 KB: keep it off the stack
   int g0 = 0;
@@ -196,6 +223,13 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cu
     const int64_t ctas = m_tiles * (g1 - g0);
     if (ctas > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "grid too large");
     cudaError_t e;
+    if (persistent) {
+      switch (mode) {
+        case accel::kModeGemm: e = launch_persistent<accel::kModeGemm>(L, static_cast<unsigned>(ctas), psmem, st); break;
+        case accel::kModeConv3: e = launch_persistent<accel::kModeConv3>(L, static_cast<unsigned>(ctas), psmem, st); break;
+        default: e = launch_persistent<accel::kModeConv7>(L, static_cast<unsigned>(ctas), psmem, st); break;
+      }
+    } else
     switch (mode) {
       case accel::kModeGemm: e = launch_mode<accel::kModeGemm>(L, static_cast<unsigned>(ctas), smem, st); break;
       case accel::kModeConv3: e = launch_mode<accel::kModeConv3>(L, static_cast<unsigned>(ctas), smem, st); break;

@@ -1,0 +1,358 @@
+// Persistent variant of the tcgen05 BSR kernel (bsr_tc.cuh) for activations that arrive by TMA.
+//
+// One CTA per SM owns all 512 TMEM columns and walks a static list of work items (128-row tile x block-row
+// group).  Every role keeps running across item boundaries, so the per-tile costs of the one-shot kernel -
+// TMEM allocation, barrier set-up, the first load's latency, the accumulator drain and the epilogue - overlap
+// with the next tile's main loop instead of serialising with it:
+//
+//     TMEM columns [0, 352)     two accumulator sets (11 block-rows x 16 columns each): the MMAs of item n+1
+//                               fill one set while the epilogue warps drain (and re-zero) the other
+//     TMEM columns [352, 496)   four activation stages of 9 K-tiles; producer half h owns stages h and h+2, so
+//                               it re-strides its next stage while the tensor core still reads the previous one
+//
+//   warps 0-7    activation producers (two halves, alternating stages): ring slot -> 14-in-16 tiles -> tcgen05.st
+//   warps 8-15   epilogue: tcgen05.ld, fused requant / ReLU / residual / saturation count, stores, re-zero
+//   warps 16-19  MMA issuers (one elected thread each, uniform datapath, schedule from the parameter bank)
+//   warp 20      weight loader (cp.async.bulk of B-tile batches)      warp 21   activation loader (TMA tensor tiles)
+#pragma once
+#include "bsr_tc.cuh"
+
+namespace accel {
+
+constexpr int kPProducerWarps = 8;
+constexpr int kPEpilogueWarps = 8;
+constexpr int kPWarpIssue = kPProducerWarps + kPEpilogueWarps;     // 16
+constexpr int kPWarpWLoad = kPWarpIssue + kIssuers;                // 20
+constexpr int kPWarpALoad = kPWarpWLoad + 1;                       // 21
+constexpr int kPThreads = (kPWarpALoad + 1) * 32;                  // 704
+constexpr int kPTmemCols = 512;
+constexpr int kPAccSets = 2;
+constexpr int kPXStages = 4;
+static_assert(kPAccSets * kAccCols + kPXStages * kXStageCols <= kPTmemCols, "TMEM budget");
+constexpr int kPMaxRingSlots = 4;
+// shared-memory map
+constexpr int kPSmemW = 0;
+constexpr int kPSmemBar = kPSmemW + kWStages * kWStageBytes;       // barriers (512 B)
+constexpr int kPSmemScale = kPSmemBar + 512;                       // float [176]
+constexpr int kPSmemBias = kPSmemScale + kAccCols * 4;             // int32 [176]
+constexpr int kPSmemRing = (kPSmemBias + kAccCols * 4 + 127) / 128 * 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_constant__ TcLaunch L, uint32_t n_items) {
+  static_assert(MODE == kModeGemm || MODE == kModeConv3 || MODE == kModeConv7, "TMA modes only");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcParams& p = L.p;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPSmemBar);
+  uint64_t* x_full = bars;                        // [4]  count 4 (one elected lane per producer warp of the half)
+  uint64_t* x_empty = x_full + kPXStages;         // [4]  count kIssuers
+  uint64_t* w_full = x_empty + kPXStages;         // [kWStages] count 1 (+tx bytes)
+  uint64_t* w_empty = w_full + kWStages;          // [kWStages] count kIssuers
+  uint64_t* acc_full = w_empty + kWStages;        // [2]  count kIssuers
+  uint64_t* acc_empty = acc_full + kPAccSets;     // [2]  count kPEpilogueWarps
+  uint64_t* h_full = acc_empty + kPAccSets;       // [kPMaxRingSlots] count 1 (+tx bytes)
+  uint64_t* h_empty = h_full + kPMaxRingSlots;    // [kPMaxRingSlots] count 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + kPMaxRingSlots);
+  float* s_scale = reinterpret_cast<float*>(smem + kPSmemScale);
+  int32_t* s_bias = reinterpret_cast<int32_t*>(smem + kPSmemBias);
+
+  constexpr bool kHalo = (MODE != kModeGemm);
+  constexpr int KS = MODE == kModeConv7 ? 7 : 3;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_groups = L.n_groups;
+  const uint32_t ring_slots = static_cast<uint32_t>(p.ring_slots);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPXStages; ++s) { mbar_init(&x_full[s], 4); mbar_init(&x_empty[s], kIssuers); }
+    for (int s = 0; s < kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kIssuers); }
+    for (int s = 0; s < kPAccSets; ++s) { mbar_init(&acc_full[s], kIssuers); mbar_init(&acc_empty[s], kPEpilogueWarps); }
+    for (int s = 0; s < kPMaxRingSlots; ++s) { mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == kPWarpIssue) {
+    tmem_alloc_dyn(tmem_slot, kPTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t ring_addr = smem_u32(smem + kPSmemRing);
+
+  if (warp < kPProducerWarps) {
+    // =================================================================== activation producers
+    const int half = warp >> 2;
+    const int tid = threadIdx.x & 127;          // activation row inside the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    uint32_t t = 0;                             // global stage counter (identical in every role)
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const uint32_t gi = it % n_groups;
+      const int64_t m0 = static_cast<int64_t>(it / n_groups) * kTileM;
+      const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
+      uint32_t thr_off = 0, sh8 = 0;
+      if constexpr (kHalo) {
+        const int64_t m = m0 + tid;
+        const uint32_t mm = static_cast<uint32_t>(m < p.M ? m : m0);
+        const uint32_t R = mm / static_cast<uint32_t>(p.Wo);
+        const int ow = static_cast<int>(mm - R * p.Wo);
+        const uint32_t img = R / static_cast<uint32_t>(p.Ho);
+        const int oh = static_cast<int>(R - img * p.Ho);
+        const uint32_t R0 = static_cast<uint32_t>(m0) / static_cast<uint32_t>(p.Wo);
+        const uint32_t img0 = R0 / static_cast<uint32_t>(p.Ho);
+        const uint32_t seg = img - img0;
+        const int ohf = seg == 0 ? static_cast<int>(R0 - img0 * p.Ho) : 0;
+        const uint32_t xb = static_cast<uint32_t>(ow * p.stride - p.pad + p.halo_lpad);
+        thr_off = seg * static_cast<uint32_t>(p.seg_bytes) + static_cast<uint32_t>((oh - ohf) * p.stride) * p.halo_pitch + (xb & ~3u);
+        sh8 = (xb & 3u) * 8u;
+      }
+      for (uint32_t b = g_bb; b < g_be; ++b) {
+        const uint32_t bw = L.batches[b];
+        if (!(bw & kBatchFirst)) continue;        // one activation stage per K chunk
+        const uint32_t a = t & 3u, slot = t % ring_slots, sphase = (t / ring_slots) & 1u, use = t >> 2;
+        const bool my = (t & 1u) == static_cast<uint32_t>(half);
+        ++t;
+        if (!my) continue;
+        const int chunk = static_cast<int>(bw >> 16);
+        const uint32_t xcol = tmem_base + lane_base + kPAccSets * kAccCols + a * kXStageCols;
+        mbar_wait(&h_full[slot], sphase);
+        mbar_wait(&x_empty[a], (use & 1u) ^ 1u);
+        tc_fence_after();
+        if constexpr (MODE == kModeGemm) {
+          const uint32_t src = ring_addr + slot * p.slot_bytes + tid * 144;
+          uint32_t r[37];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const uint4 v = lds128(src + i * 16);
+            r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+          }
+          r[36] = 0u;
+          switch ((chunk * kChunkTiles * kBlock) & 15) {
+            case 0: gemm_restride<0>(r, xcol); break;
+            case 2: gemm_restride<2>(r, xcol); break;
+            case 4: gemm_restride<4>(r, xcol); break;
+            case 6: gemm_restride<6>(r, xcol); break;
+            case 8: gemm_restride<8>(r, xcol); break;
+            case 10: gemm_restride<10>(r, xcol); break;
+            case 12: gemm_restride<12>(r, xcol); break;
+            default: gemm_restride<14>(r, xcol); break;
+          }
+        } else {
+          constexpr int GPS = 126 / KS;
+          const uint32_t cs = static_cast<uint32_t>(p.halo_rows) * p.halo_pitch;
+          const int g0 = chunk * GPS;
+          const int c_first = g0 / KS;
+          int kh = g0 - c_first * KS;
+          const int groups_left = p.C * KS - g0;
+          uint32_t rp = ring_addr + slot * p.slot_bytes + thr_off + kh * p.halo_pitch;
+          uint32_t w[36];
+#pragma unroll
+          for (int i = 0; i < 36; ++i) w[i] = 0u;
+          ConvBatch<KS>::template run<0>(w, xcol, rp, sh8, p.halo_pitch, cs, kh, groups_left);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&h_empty[slot]);
+          mbar_arrive(&x_full[a]);
+        }
+      }
+    }
+  } else if (warp < kPWarpIssue) {
+    // =================================================================== epilogue
+    const int ew = warp - kPProducerWarps;            // 0..7
+    const int ehalf = ew >> 2;                        // splits the block-rows of a tile between two warp sets
+    const int etid = threadIdx.x - kPProducerWarps * 32;   // 0..255
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    // both accumulator sets start out zero
+    for (uint32_t c = ehalf * 4u; c < static_cast<uint32_t>(kPAccSets * kAccCols); c += 8)
+      tmem_st4(tmem_base + lane_base + c, 0u, 0u, 0u, 0u);
+    tmem_st_wait();
+    tc_fence_before();
+    named_bar_sync(1, kPEpilogueWarps * 32);
+    if (lane == 0) { mbar_arrive(&acc_empty[0]); mbar_arrive(&acc_empty[1]); }
+    EpiCtx ec;
+    ec.flags = p.epi.flags;
+    ec.cs = p.lay.chan_stride;
+    ec.relu_lo = (ec.flags & ACCEL_RELU) ? 0 : INT_MIN;
+    ec.out_lo = (ec.flags & ACCEL_RELU_OUT) ? 0 : -128;
+    ec.sat = 0;
+    ec.lane = lane;
+    const bool sat_on = p.epi.sat_count != nullptr;
+    int kind = kEpiGeneric;
+    if (!p.epi.chan_absmax && (ec.flags & ACCEL_OUT_I8))
+      kind = !p.epi.residual ? kEpiI8 : (p.res_fast ? kEpiI8ResFast : kEpiI8Res);
+    else if (!p.epi.chan_absmax && !sat_on && (ec.flags & ACCEL_OUT_I32)) kind = kEpiI32;
+    if (sat_on && kind != kEpiGeneric) kind += 8;
+    uint32_t n = 0;
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+      const uint32_t gi = it % n_groups;
+      const int64_t m0 = static_cast<int64_t>(it / n_groups) * kTileM;
+      const uint32_t g_br0 = L.groups[gi].br0_rows & 0xffffu, g_rows = L.groups[gi].br0_rows >> 16;
+      const uint32_t ab = n & 1u;
+      // per-channel constants of this item's block-row group (the previous item's readers are done: barrier first)
+      named_bar_sync(1, kPEpilogueWarps * 32);
+      if (static_cast<uint32_t>(etid) < g_rows * kBlock) {
+        const int c = g_br0 * kBlock + etid;
+        const bool ok = c < p.epi.n_channels;
+        s_scale[etid] = (ok && p.epi.chan_scale) ? p.epi.chan_scale[c] : 0.f;
+        s_bias[etid] = (ok && p.epi.bias) ? p.epi.bias[c] : 0;
+      }
+      const int64_t m = m0 + (warp & 3) * 32 + lane;
+      ec.row_ok = m < p.M;
+      ec.out_base = 0;
+      if (ec.row_ok) {
+        const int64_t im = m / p.lay.rows_per_image;
+        const int64_t pix = m - im * p.lay.rows_per_image;
+        if (p.lay.row_len > 0) {
+          const int64_t r = pix / p.lay.row_len;
+          ec.out_base = im * p.lay.image_stride + r * p.lay.row_pitch + (pix - r * p.lay.row_len) * p.lay.row_stride;
+        } else {
+          ec.out_base = im * p.lay.image_stride + pix * p.lay.row_stride;
+        }
+      }
+      named_bar_sync(1, kPEpilogueWarps * 32);
+      mbar_wait(&acc_full[ab], (n >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + lane_base + ab * kAccCols;
+      for (uint32_t g = ehalf; g < g_rows; g += 2) {
+        uint32_t v[16];
+        tmem_ld16(acc0 + g * kTile, v);
+        const int cb = (g_br0 + g) * kBlock;
+        const int n_ok = min(kBlock, p.epi.n_channels - cb);
+        const float* sc = s_scale + g * kBlock;
+        const int32_t* bi = s_bias + g * kBlock;
+        switch (kind) {
+          case kEpiI8: epilogue_row<kEpiI8, false>(p, ec, v, cb, n_ok, sc, bi); break;
+          case kEpiI8ResFast: epilogue_row<kEpiI8ResFast, false>(p, ec, v, cb, n_ok, sc, bi); break;
+          case kEpiI8Res: epilogue_row<kEpiI8Res, false>(p, ec, v, cb, n_ok, sc, bi); break;
+          case kEpiI8 + 8: epilogue_row<kEpiI8, true>(p, ec, v, cb, n_ok, sc, bi); break;
+          case kEpiI8ResFast + 8: epilogue_row<kEpiI8ResFast, true>(p, ec, v, cb, n_ok, sc, bi); break;
+          case kEpiI8Res + 8: epilogue_row<kEpiI8Res, true>(p, ec, v, cb, n_ok, sc, bi); break;
+          case kEpiI32: epilogue_row<kEpiI32, false>(p, ec, v, cb, n_ok, sc, bi); break;
+          default: epilogue_row<kEpiGeneric, false>(p, ec, v, cb, n_ok, sc, bi); break;
+        }
+        // the accumulators of the next item that uses this set start from zero
+#pragma unroll
+        for (int c = 0; c < kTile; c += 4) tmem_st4(acc0 + g * kTile + c, 0u, 0u, 0u, 0u);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+    }
+    if (p.epi.sat_count) {
+      const uint32_t wsum = __reduce_add_sync(0xffffffffu, ec.sat);
+      if (lane == 0 && wsum) atomicAdd(p.epi.sat_count, static_cast<unsigned long long>(wsum));
+    }
+  } else if (warp < kPWarpWLoad) {
+    // =================================================================== MMA issuers (uniform datapath)
+    const uint32_t me = static_cast<uint32_t>(warp - kPWarpIssue);
+    if (elect_one()) {
+      const uint32_t idesc0 = idesc_i8(kTileM, 0);
+      const uint32_t w_addr = smem_u32(smem + kPSmemW);
+      const uint64_t bdesc0 = smem_desc_kmajor(0, 128, 256);
+      const uint32_t bdesc_hi = static_cast<uint32_t>(bdesc0 >> 32);
+      const uint32_t bdesc_lo0 = static_cast<uint32_t>(bdesc0);
+      uint32_t t = 0, wcount = 0, n = 0, a = 0;
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+        const uint32_t gi = it % n_groups;
+        const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
+        uint32_t opb = L.groups[gi].op_begin;
+        const uint32_t ab = n & 1u;
+        mbar_wait(&acc_empty[ab], (n >> 1) & 1u);      // drained and re-zeroed by the epilogue warps
+        tc_fence_after();
+        const uint32_t accb = tmem_base + ab * kAccCols;
+        for (uint32_t b = g_bb; b < g_be; ++b) {
+          const uint32_t bw = L.batches[b];
+          if (bw & kBatchFirst) {
+            a = t & 3u;
+            mbar_wait(&x_full[a], (t >> 2) & 1u);
+            ++t;
+          }
+          const uint32_t ws_i = wcount % kWStages;
+          mbar_wait(&w_full[ws_i], (wcount / kWStages) & 1u);
+          tc_fence_after();
+          const uint32_t n_runs = bw & 0xffu;
+          const uint32_t xa = tmem_base + kPAccSets * kAccCols + a * kXStageCols;
+          const uint32_t blo = bdesc_lo0 | (((w_addr + ws_i * kWStageBytes) >> 4) & 0x3FFFu);
+          for (uint32_t i = me; i < n_runs; i += kIssuers) {
+            const OpRec o = L.ops[opb + i];
+            const uint32_t d = accb + (o.d_n & 0x1ffu);
+            const uint32_t idesc = idesc0 | (o.d_n & 0x7E0000u);
+            const uint32_t aa = xa + (o.a_b & 0x1ffu);
+            const uint64_t bdesc = (static_cast<uint64_t>(bdesc_hi) << 32) | (blo + (o.a_b >> 16));
+            mma_i8_ts(d, aa, bdesc, idesc, 1u);
+          }
+          opb += n_runs;
+          mma_commit(&w_empty[ws_i]);
+          if (bw & kBatchLast) mma_commit(&x_empty[a]);
+          ++wcount;
+        }
+        mma_commit(&acc_full[ab]);    // with nothing in flight (a group without blocks) this arrives at once
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else if (warp == kPWarpWLoad) {
+    // =================================================================== weight loader
+    if (lane == 0) {
+      uint32_t wcount = 0;
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const uint32_t gi = it % n_groups;
+        const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
+        const uint8_t* src = p.blob + static_cast<size_t>(L.groups[gi].blob_off16) * 16;
+        for (uint32_t b = g_bb; b < g_be; ++b) {
+          const uint32_t bw = L.batches[b];
+          const uint32_t ws_i = wcount % kWStages;
+          mbar_wait(&w_empty[ws_i], ((wcount / kWStages) & 1u) ^ 1u);
+          const uint32_t bytes = (((bw >> 8) & 0x3fu) + 1u) * kBTileBytes;
+          mbar_arrive_expect_tx(&w_full[ws_i], bytes);
+          bulk_g2s(smem + kPSmemW + ws_i * kWStageBytes, src, bytes, &w_full[ws_i]);
+          src += bytes;
+          ++wcount;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================================================== activation loader (TMA)
+    if (elect_one()) {
+      uint32_t t = 0;
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const uint32_t gi = it % n_groups;
+        const int64_t m0 = static_cast<int64_t>(it / n_groups) * kTileM;
+        const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
+        uint32_t n_seg = 1, img0 = 0;
+        int ih_first = 0;
+        if constexpr (kHalo) {
+          const uint32_t R0 = static_cast<uint32_t>(m0) / static_cast<uint32_t>(p.Wo);
+          img0 = R0 / static_cast<uint32_t>(p.Ho);
+          const uint32_t m_last = static_cast<uint32_t>(m0 + kTileM - 1 < p.M ? m0 + kTileM - 1 : p.M - 1);
+          n_seg = m_last / static_cast<uint32_t>(p.Ho * p.Wo) - img0 + 1;
+          ih_first = static_cast<int>(R0 - img0 * p.Ho) * p.stride - p.pad;
+        }
+        for (uint32_t b = g_bb; b < g_be; ++b) {
+          const uint32_t bw = L.batches[b];
+          if (!(bw & kBatchFirst)) continue;
+          const uint32_t slot = t % ring_slots, sphase = (t / ring_slots) & 1u;
+          ++t;
+          mbar_wait(&h_empty[slot], sphase ^ 1u);
+          tma_stage<MODE>(L, ring_addr + slot * p.slot_bytes, &h_full[slot], static_cast<int>(bw >> 16), m0, n_seg, img0,
+                          ih_first);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kPWarpIssue) {
+    tc_fence_after();
+    tmem_dealloc_dyn(tmem_base, kPTmemCols);
+  }
+}
+
+}  // namespace accel
