@@ -180,6 +180,14 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cu
   const int64_t m_tiles = (prm.M + accel::kTileM - 1) / accel::kTileM;
   if (n_groups == 0 || m_tiles == 0) return ACCEL_OK;
   prm.blob = P->ws_dev + P->off_blob;
+  {  // largest element offset the epilogue can form: (images-1)*image_stride + channels*chan_stride + one plane
+    const accel_out_layout& l = prm.lay;
+    const int64_t images = (prm.M + l.rows_per_image - 1) / l.rows_per_image;
+    const int64_t plane = l.row_len > 0 ? (l.rows_per_image / l.row_len + 1) * l.row_pitch + l.row_len * l.row_stride
+                                        : l.rows_per_image * l.row_stride;
+    const int64_t span = images * l.image_stride + static_cast<int64_t>(prm.epi.n_channels + 14) * l.chan_stride + plane;
+    prm.out_small = span >= 0 && span < (1ll << 31) && l.chan_stride < (1ll << 27);
+  }
   prm.timeline = g_timeline;
   prm.dbg_flags = g_dbg_flags;
   if (prm.epi.residual) {

@@ -103,6 +103,7 @@ struct TcParams {
   float res_rcp;        // RN(1 / res_scale_out)
   void* out;
   accel_out_layout lay;
+  int32_t out_small;    // every output / residual element offset fits 31 bits
   long long* timeline;  // developer aid: per-CTA clock64 stamps (32 per CTA) when non-null
   int32_t dbg_flags;    // developer aid: bit 0 = skip the epilogue's global stores
 };

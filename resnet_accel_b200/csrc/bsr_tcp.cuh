@@ -37,6 +37,102 @@ constexpr int kPSmemScale = kPSmemBar + 512;                       // float [176
 constexpr int kPSmemBias = kPSmemScale + kAccCols * 4;             // int32 [176]
 constexpr int kPSmemRing = (kPSmemBias + kAccCols * 4 + 127) / 128 * 128;
 
+// ---- int8 epilogue of one block-row for the persistent kernel: 32-bit element offsets (checked on the host),
+// residual bytes prefetched by the caller, and an unpredicated variant for the common case "all 14 channels
+// exist and all 32 rows of the warp exist".
+template <bool RES, bool RES_FAST, bool SAT, bool FULL>
+__device__ __forceinline__ void epi_i8_row(const TcParams& p, EpiCtx& ec, const uint32_t (&v)[16], int n_ok, const float* sc,
+                                           const int32_t* bi, int8_t* o, int32_t cs, const int (&rv)[kBlock]) {
+  if (!FULL && !ec.row_ok) {
+    return;
+  }
+#pragma unroll
+  for (int h = 0; h < kBlock; ++h) {
+    const int acc = max(static_cast<int>(v[h]) + bi[h], ec.relu_lo);
+    const float f = __fmul_rn(__int2float_rn(acc), sc[h]);           // golden_models.cpp:378-411, per channel
+    int r8 = cvt_sat_s8(f);
+    if constexpr (SAT) {
+      // round-half-even leaves [-128, 127] exactly when f >= 127.5 (-> 128) or f < -128.5 (-128.5 -> -128 stays)
+      const bool counted = FULL || h < n_ok;
+      ec.sat += (counted && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
+    }
+    if constexpr (RES) {                                             // add_residual_int8, golden_models.cpp:465-490
+      const float a = __fmul_rn(__int2float_rn(r8), p.epi.res_scale_main);
+      const float r = __fmul_rn(__int2float_rn(rv[h]), p.epi.res_scale_res);
+      const float s = __fadd_rn(a, r);
+      float d;
+      if constexpr (RES_FAST) {    // correctly rounded for every (int8, int8) pair: verified on the host
+        const float q0 = __fmul_rn(s, p.res_rcp);
+        const float e = __fmaf_rn(-q0, p.epi.res_scale_out, s);
+        d = __fmaf_rn(e, p.res_rcp, q0);
+      } else {
+        d = __fdiv_rn(s, p.epi.res_scale_out);
+      }
+      r8 = cvt_sat_s8(d);
+    }
+    const int q = max(r8, ec.out_lo);                                // relu_int8 (golden_models.cpp:278-283) when requested
+    if (FULL || h < n_ok) o[h * cs] = static_cast<int8_t>(q);
+  }
+}
+template <bool FULL>
+__device__ __forceinline__ void epi_load_residual(const int8_t* __restrict__ r, int32_t cs, bool row_ok, int n_ok,
+                                                  int (&rv)[kBlock]) {
+#pragma unroll
+  for (int h = 0; h < kBlock; ++h) rv[h] = (FULL || (row_ok && h < n_ok)) ? static_cast<int>(r[h * cs]) : 0;
+}
+
+// One work item's int8 epilogue for one warp: block-rows g_first, g_first + 2, ...  RESMODE 0 = no residual,
+// 1 = residual with the exact 3-instruction divide, 2 = residual with the IEEE divide.  The residual bytes of a
+// block-row are requested before the previous one is processed (the first: before the MMAs have even finished).
+struct EpiItem {
+  uint32_t acc0, g_first, g_rows, g_br0, parity;
+  uint64_t* bar;
+  const float* s_scale;
+  const int32_t* s_bias;
+};
+template <int RESMODE, bool SAT>
+__device__ __forceinline__ void epi_i8_item(const TcParams& p, EpiCtx& ec, const EpiItem& ei) {
+  constexpr bool RES = RESMODE != 0;
+  const bool rows_all = __all_sync(0xffffffffu, ec.row_ok);
+  const int32_t cs32 = static_cast<int32_t>(ec.cs);
+  int rv[kBlock];
+#pragma unroll
+  for (int h = 0; h < kBlock; ++h) rv[h] = 0;
+  auto residual = [&](uint32_t g, int (&dst)[kBlock]) {
+    const int cb = (ei.g_br0 + g) * kBlock;
+    const int n_ok = min(kBlock, p.epi.n_channels - cb);
+    const int8_t* r = p.epi.residual + ec.out_base + static_cast<int64_t>(cb) * ec.cs;
+    if (rows_all && n_ok == kBlock) epi_load_residual<true>(r, cs32, true, n_ok, dst);
+    else epi_load_residual<false>(r, cs32, ec.row_ok, n_ok, dst);
+  };
+  if (RES && ei.g_first < ei.g_rows) residual(ei.g_first, rv);
+  mbar_wait(ei.bar, ei.parity);
+  tc_fence_after();
+  for (uint32_t g = ei.g_first; g < ei.g_rows; g += 2) {
+    uint32_t v[16];
+    tmem_ld16(ei.acc0 + g * kTile, v);
+    const int cb = (ei.g_br0 + g) * kBlock;
+    const int n_ok = min(kBlock, p.epi.n_channels - cb);
+    int rvn[kBlock];
+#pragma unroll
+    for (int h = 0; h < kBlock; ++h) rvn[h] = 0;
+    if (RES && g + 2 < ei.g_rows) residual(g + 2, rvn);
+    int8_t* o = reinterpret_cast<int8_t*>(p.out) + ec.out_base + static_cast<int64_t>(cb) * ec.cs;
+    const float* sc = ei.s_scale + g * kBlock;
+    const int32_t* bi = ei.s_bias + g * kBlock;
+    tmem_ld_wait();
+    if (rows_all && n_ok == kBlock) epi_i8_row<RES, RESMODE == 1, SAT, true>(p, ec, v, n_ok, sc, bi, o, cs32, rv);
+    else epi_i8_row<RES, RESMODE == 1, SAT, false>(p, ec, v, n_ok, sc, bi, o, cs32, rv);
+    // the accumulators of the next item that uses this set start from zero
+#pragma unroll
+    for (int c = 0; c < kTile; c += 4) tmem_st4(ei.acc0 + g * kTile + c, 0u, 0u, 0u, 0u);
+    if constexpr (RES) {
+#pragma unroll
+      for (int h = 0; h < kBlock; ++h) rv[h] = rvn[h];
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_constant__ TcLaunch L, uint32_t n_items) {
   static_assert(MODE == kModeGemm || MODE == kModeConv3 || MODE == kModeConv7, "TMA modes only");
@@ -213,29 +309,46 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
         }
       }
       named_bar_sync(1, kPEpilogueWarps * 32);
-      mbar_wait(&acc_full[ab], (n >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t acc0 = tmem_base + lane_base + ab * kAccCols;
-      for (uint32_t g = ehalf; g < g_rows; g += 2) {
-        uint32_t v[16];
-        tmem_ld16(acc0 + g * kTile, v);
-        const int cb = (g_br0 + g) * kBlock;
-        const int n_ok = min(kBlock, p.epi.n_channels - cb);
-        const float* sc = s_scale + g * kBlock;
-        const int32_t* bi = s_bias + g * kBlock;
-        switch (kind) {
-          case kEpiI8: epilogue_row<kEpiI8, false>(p, ec, v, cb, n_ok, sc, bi); break;
-          case kEpiI8ResFast: epilogue_row<kEpiI8ResFast, false>(p, ec, v, cb, n_ok, sc, bi); break;
-          case kEpiI8Res: epilogue_row<kEpiI8Res, false>(p, ec, v, cb, n_ok, sc, bi); break;
-          case kEpiI8 + 8: epilogue_row<kEpiI8, true>(p, ec, v, cb, n_ok, sc, bi); break;
-          case kEpiI8ResFast + 8: epilogue_row<kEpiI8ResFast, true>(p, ec, v, cb, n_ok, sc, bi); break;
-          case kEpiI8Res + 8: epilogue_row<kEpiI8Res, true>(p, ec, v, cb, n_ok, sc, bi); break;
-          case kEpiI32: epilogue_row<kEpiI32, false>(p, ec, v, cb, n_ok, sc, bi); break;
-          default: epilogue_row<kEpiGeneric, false>(p, ec, v, cb, n_ok, sc, bi); break;
+      const bool fast8 = p.out_small && (kind & 7) <= kEpiI8Res;      // int8 output with 32-bit element offsets
+      if (fast8) {
+        EpiItem ei;
+        ei.acc0 = tmem_base + lane_base + ab * kAccCols;
+        ei.g_first = static_cast<uint32_t>(ehalf); ei.g_rows = g_rows; ei.g_br0 = g_br0;
+        ei.bar = &acc_full[ab]; ei.parity = (n >> 1) & 1u;
+        ei.s_scale = s_scale; ei.s_bias = s_bias;
+        switch ((kind & 7) * 2 + (sat_on ? 1 : 0)) {
+          case 0: epi_i8_item<0, false>(p, ec, ei); break;
+          case 1: epi_i8_item<0, true>(p, ec, ei); break;
+          case 2: epi_i8_item<1, false>(p, ec, ei); break;
+          case 3: epi_i8_item<1, true>(p, ec, ei); break;
+          case 4: epi_i8_item<2, false>(p, ec, ei); break;
+          default: epi_i8_item<2, true>(p, ec, ei); break;
         }
-        // the accumulators of the next item that uses this set start from zero
+      } else {
+        mbar_wait(&acc_full[ab], (n >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + lane_base + ab * kAccCols;
+        for (uint32_t g = ehalf; g < g_rows; g += 2) {
+          uint32_t v[16];
+          tmem_ld16(acc0 + g * kTile, v);
+          const int cb = (g_br0 + g) * kBlock;
+          const int n_ok = min(kBlock, p.epi.n_channels - cb);
+          const float* sc = s_scale + g * kBlock;
+          const int32_t* bi = s_bias + g * kBlock;
+          switch (kind) {
+            case kEpiI8: epilogue_row<kEpiI8, false>(p, ec, v, cb, n_ok, sc, bi); break;
+            case kEpiI8ResFast: epilogue_row<kEpiI8ResFast, false>(p, ec, v, cb, n_ok, sc, bi); break;
+            case kEpiI8Res: epilogue_row<kEpiI8Res, false>(p, ec, v, cb, n_ok, sc, bi); break;
+            case kEpiI8 + 8: epilogue_row<kEpiI8, true>(p, ec, v, cb, n_ok, sc, bi); break;
+            case kEpiI8ResFast + 8: epilogue_row<kEpiI8ResFast, true>(p, ec, v, cb, n_ok, sc, bi); break;
+            case kEpiI8Res + 8: epilogue_row<kEpiI8Res, true>(p, ec, v, cb, n_ok, sc, bi); break;
+            case kEpiI32: epilogue_row<kEpiI32, false>(p, ec, v, cb, n_ok, sc, bi); break;
+            default: epilogue_row<kEpiGeneric, false>(p, ec, v, cb, n_ok, sc, bi); break;
+          }
+          // the accumulators of the next item that uses this set start from zero
 #pragma unroll
-        for (int c = 0; c < kTile; c += 4) tmem_st4(acc0 + g * kTile + c, 0u, 0u, 0u, 0u);
+          for (int c = 0; c < kTile; c += 4) tmem_st4(acc0 + g * kTile + c, 0u, 0u, 0u, 0u);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
