@@ -233,13 +233,44 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         sampler.start()
     # (1) kernel-only: inputs resident in HBM, graph replay
     ms_total = timed(lambda: net.replay(), args.steps, args.warmup)
-    # (2) end to end through the public API with host buffers
-    def e2e_step():
-        net.static_in.copy_(x_host, non_blocking=True)
-        net.graph.replay()
-        logits_host.copy_(net.buffers["fc"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    ms_e2e = timed(e2e_step, args.steps, args.warmup)
+    # (2) end to end through the public API with HOST buffers.  Two-deep pipeline, all inside the timed region:
+    #     copy stream: pinned host -> device staging buffer of step i+1   |  compute stream: staging -> network input,
+    #     graph replay, INT32 logits -> pinned host.  Events on the compute stream bracket all K steps.
+    copy_stream = torch.cuda.Stream()
+    staging = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    staged = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_run(K):
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        copy_stream.wait_event(e0)                                  # the first copy starts inside the timed region
+        for i in range(K):
+            b = i & 1
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(consumed[b])             # the staging buffer was read by step i-2
+                staging[b].copy_(x_host, non_blocking=True)
+                staged[b].record(copy_stream)
+            cur.wait_event(staged[b])
+            net.static_in.copy_(staging[b], non_blocking=True)
+            consumed[b].record(cur)
+            net.graph.replay()
+            logits_host.copy_(net.buffers["fc"], non_blocking=True)
+        e1.record(cur)
+        cur.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(2):
+        e2e_run(max(args.warmup, 3))
+    barrier()
+    ms_e2e = e2e_run(args.steps)
+    barrier()
+    if dist is not None:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
     # (3) dominant kernel: every conv/fc launch of one step, event-timed on the launching stream
@@ -274,9 +305,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "dtype": "int8", "data": "synthetic",
             "config": {"workload": "resnet18_full_bsr14_int8", "sparsity_pct": args.sparsity, "batch_per_gpu": B,
                        "image": 224, "block": 14, "parallelism": f"batch-shard x{world} (no collective)",
-                       "l2": "flushed between timed steps (256 MiB memset)", "graph": "one CUDA graph per step"},
+                       "l2": "value: flushed between timed steps (256 MiB memset); e2e: per-step working set 1.4 GB >> 126 MB L2",
+                       "graph": "one CUDA graph per step", "e2e_pipeline": "2-deep: H2D of step i+1 overlaps step i"},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_source": src, "kernel": "bsr_tc_kernel (20 conv + 1 fc launches per step)",
+                         "traffic": None, "peak_source": src, "kernel": "bsr_tcp_kernel / bsr_tc_kernel (20 conv + 1 fc launches per step)",
                          "useful_tops": ach_tops, "tensor_frac_of_2x_bf16_sustained": ach_tops / int8_peak_tops,
                          "kernel_ms_per_step": kms, "algorithmic_bytes_per_step": conv_bytes,
                          "useful_ops_per_step": conv_ops},
