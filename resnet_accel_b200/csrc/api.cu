@@ -219,6 +219,11 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cu
     if (g1 == g0) return fail(ACCEL_INVALID_CONFIG, "block-row group exceeds the launch tables");
     const uint32_t b0 = P->groups[g0].batch_begin, o0 = P->groups[g0].op_begin;
     L.p = prm;
+    L.p.d_wo = accel::make_fastdiv(static_cast<uint32_t>(prm.Wo));
+    L.p.d_ho = accel::make_fastdiv(static_cast<uint32_t>(prm.Ho));
+    L.p.d_groups = accel::make_fastdiv(static_cast<uint32_t>(g1 - g0));
+    L.p.d_rpi = accel::make_fastdiv(static_cast<uint32_t>(prm.lay.rows_per_image < (1ll << 31) ? prm.lay.rows_per_image : 0));
+    L.p.d_rowlen = accel::make_fastdiv(static_cast<uint32_t>(prm.lay.row_len));
     if (tmap) L.tmap = *tmap;
     L.n_groups = static_cast<uint32_t>(g1 - g0);
     for (int g = g0; g < g1; ++g) {

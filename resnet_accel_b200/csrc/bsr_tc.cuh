@@ -69,6 +69,27 @@ constexpr int kRingSlack = 32;                                  // the gathers r
 
 enum TcMode { kModeGemm = 0, kModeConv3 = 1, kModeConv7 = 2, kModeDirect = 3 };
 
+// Exact unsigned 32-bit division by a run-time constant (Granlund-Montgomery, the "round-up" variant): the host
+// computes (mul, shr) once, the device pays a multiply-high, a subtract and two shifts instead of ~25 instructions.
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d ? d : 1u, 0u, 0u};
+  if (f.d > 1) {
+    uint32_t l = 0;
+    while ((1ull << l) < f.d) ++l;                           // l = ceil(log2 d)
+    f.mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - f.d)) / f.d + 1);
+    f.shr = l - 1;
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  const uint32_t t = __umulhi(f.mul, n);
+  return (t + ((n - t) >> 1)) >> f.shr;
+}
+
 struct TcParams {
   // activation source
   const int8_t* x;
@@ -104,6 +125,7 @@ struct TcParams {
   void* out;
   accel_out_layout lay;
   int32_t out_small;    // every output / residual element offset fits 31 bits
+  FastDiv d_wo, d_ho, d_groups, d_rpi, d_rowlen;   // divisions by Wo, Ho, groups of this launch, rows_per_image, row_len
   long long* timeline;  // developer aid: per-CTA clock64 stamps (32 per CTA) when non-null
   int32_t dbg_flags;    // developer aid: bit 0 = skip the epilogue's global stores
 };
@@ -204,12 +226,12 @@ struct ConvBatch {
   static constexpr int NW = (KS + 3 + 3) / 4;   // words that can hold KS bytes at byte offset <= 3
   static constexpr int kGB = KS == 3 ? 7 : 3;   // 42 = 6 x 7 groups, 18 = 6 x 3 groups
   static_assert(GPS % kGB == 0, "batch size must divide the groups of a stage");
-  template <int j0, int i>
+  template <bool kFull, int j0, int i>
   static __device__ __forceinline__ void load(uint32_t (&g)[kGB][NW + 1], uint32_t& rp, uint32_t pitch, uint32_t cs, int& kh,
                                               int groups_left) {
     if constexpr (i < kGB) {
       constexpr int j = j0 + i;
-      const bool on = j < groups_left;
+      const bool on = kFull || j < groups_left;      // kFull: every group of the stage lies inside the tensor
 #pragma unroll
       for (int q = 0; q < NW; ++q) g[i][q] = on ? lds32(rp + 4 * q) : 0u;
       g[i][NW] = 0u;
@@ -219,7 +241,7 @@ struct ConvBatch {
         ++kh;
         if (kh == KS) { kh = 0; rp += cs - (KS - 1) * pitch; } else { rp += pitch; }
       }
-      load<j0, i + 1>(g, rp, pitch, cs, kh, groups_left);
+      load<kFull, j0, i + 1>(g, rp, pitch, cs, kh, groups_left);
     }
   }
   template <int j0, int i>
@@ -231,15 +253,21 @@ struct ConvBatch {
       merge<j0, i + 1>(w, g, sh8, xcol);
     }
   }
+  template <bool kFull, int j0>
+  static __device__ __forceinline__ void run_(uint32_t (&w)[36], uint32_t xcol, uint32_t& rp, uint32_t sh8, uint32_t pitch,
+                                              uint32_t cs, int& kh, int groups_left) {
+    if constexpr (j0 < GPS) {
+      uint32_t g[kGB][NW + 1];
+      load<kFull, j0, 0>(g, rp, pitch, cs, kh, groups_left);
+      merge<j0, 0>(w, g, sh8, xcol);
+      run_<kFull, j0 + kGB>(w, xcol, rp, sh8, pitch, cs, kh, groups_left);
+    }
+  }
   template <int j0>
   static __device__ __forceinline__ void run(uint32_t (&w)[36], uint32_t xcol, uint32_t& rp, uint32_t sh8, uint32_t pitch,
                                              uint32_t cs, int& kh, int groups_left) {
-    if constexpr (j0 < GPS) {
-      uint32_t g[kGB][NW + 1];
-      load<j0, 0>(g, rp, pitch, cs, kh, groups_left);
-      merge<j0, 0>(w, g, sh8, xcol);
-      run<j0 + kGB>(w, xcol, rp, sh8, pitch, cs, kh, groups_left);
-    }
+    if (groups_left >= GPS) run_<true, j0>(w, xcol, rp, sh8, pitch, cs, kh, groups_left);
+    else run_<false, j0>(w, xcol, rp, sh8, pitch, cs, kh, groups_left);
   }
 };
 

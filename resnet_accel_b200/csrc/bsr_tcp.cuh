@@ -182,20 +182,22 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
     const int tid = threadIdx.x & 127;          // activation row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     uint32_t t = 0;                             // global stage counter (identical in every role)
+    uint32_t slot = 0, sphase = 0;              // ring slot / phase of stage t, advanced without divisions
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const uint32_t gi = it % n_groups;
-      const int64_t m0 = static_cast<int64_t>(it / n_groups) * kTileM;
+      const uint32_t mt = fdiv(it, p.d_groups);
+      const uint32_t gi = it - mt * n_groups;
+      const int64_t m0 = static_cast<int64_t>(mt) * kTileM;
       const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
       uint32_t thr_off = 0, sh8 = 0;
       if constexpr (kHalo) {
         const int64_t m = m0 + tid;
         const uint32_t mm = static_cast<uint32_t>(m < p.M ? m : m0);
-        const uint32_t R = mm / static_cast<uint32_t>(p.Wo);
+        const uint32_t R = fdiv(mm, p.d_wo);
         const int ow = static_cast<int>(mm - R * p.Wo);
-        const uint32_t img = R / static_cast<uint32_t>(p.Ho);
+        const uint32_t img = fdiv(R, p.d_ho);
         const int oh = static_cast<int>(R - img * p.Ho);
-        const uint32_t R0 = static_cast<uint32_t>(m0) / static_cast<uint32_t>(p.Wo);
-        const uint32_t img0 = R0 / static_cast<uint32_t>(p.Ho);
+        const uint32_t R0 = fdiv(static_cast<uint32_t>(m0), p.d_wo);
+        const uint32_t img0 = fdiv(R0, p.d_ho);
         const uint32_t seg = img - img0;
         const int ohf = seg == 0 ? static_cast<int>(R0 - img0 * p.Ho) : 0;
         const uint32_t xb = static_cast<uint32_t>(ow * p.stride - p.pad + p.halo_lpad);
@@ -205,17 +207,18 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
       for (uint32_t b = g_bb; b < g_be; ++b) {
         const uint32_t bw = L.batches[b];
         if (!(bw & kBatchFirst)) continue;        // one activation stage per K chunk
-        const uint32_t a = t & 3u, slot = t % ring_slots, sphase = (t / ring_slots) & 1u, use = t >> 2;
+        const uint32_t a = t & 3u, use = t >> 2, my_slot = slot, my_phase = sphase;
         const bool my = (t & 1u) == static_cast<uint32_t>(half);
         ++t;
+        if (++slot == ring_slots) { slot = 0; sphase ^= 1u; }
         if (!my) continue;
         const int chunk = static_cast<int>(bw >> 16);
         const uint32_t xcol = tmem_base + lane_base + kPAccSets * kAccCols + a * kXStageCols;
-        mbar_wait(&h_full[slot], sphase);
+        mbar_wait(&h_full[my_slot], my_phase);
         mbar_wait(&x_empty[a], (use & 1u) ^ 1u);
         tc_fence_after();
         if constexpr (MODE == kModeGemm) {
-          const uint32_t src = ring_addr + slot * p.slot_bytes + tid * 144;
+          const uint32_t src = ring_addr + my_slot * p.slot_bytes + tid * 144;
           uint32_t r[37];
 #pragma unroll
           for (int i = 0; i < 9; ++i) {
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
           const int c_first = g0 / KS;
           int kh = g0 - c_first * KS;
           const int groups_left = p.C * KS - g0;
-          uint32_t rp = ring_addr + slot * p.slot_bytes + thr_off + kh * p.halo_pitch;
+          uint32_t rp = ring_addr + my_slot * p.slot_bytes + thr_off + kh * p.halo_pitch;
           uint32_t w[36];
 #pragma unroll
           for (int i = 0; i < 36; ++i) w[i] = 0u;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&h_empty[slot]);
+          mbar_arrive(&h_empty[my_slot]);
           mbar_arrive(&x_full[a]);
         }
       }
@@ -283,8 +286,9 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
     if (sat_on && kind != kEpiGeneric) kind += 8;
     uint32_t n = 0;
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-      const uint32_t gi = it % n_groups;
-      const int64_t m0 = static_cast<int64_t>(it / n_groups) * kTileM;
+      const uint32_t mt = fdiv(it, p.d_groups);
+      const uint32_t gi = it - mt * n_groups;
+      const int64_t m0 = static_cast<int64_t>(mt) * kTileM;
       const uint32_t g_br0 = L.groups[gi].br0_rows & 0xffffu, g_rows = L.groups[gi].br0_rows >> 16;
       const uint32_t ab = n & 1u;
       // per-channel constants of this item's block-row group (the previous item's readers are done: barrier first)
@@ -299,13 +303,16 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
       ec.row_ok = m < p.M;
       ec.out_base = 0;
       if (ec.row_ok) {
-        const int64_t im = m / p.lay.rows_per_image;
-        const int64_t pix = m - im * p.lay.rows_per_image;
+        // M < 2^31 (checked by the host) and rows_per_image < 2^31 whenever d_rpi.d is its divisor
+        const uint32_t mu = static_cast<uint32_t>(m);
+        const uint32_t im = p.lay.rows_per_image < (1ll << 31) ? fdiv(mu, p.d_rpi) : 0u;
+        const uint32_t pix = mu - im * static_cast<uint32_t>(p.lay.rows_per_image);
         if (p.lay.row_len > 0) {
-          const int64_t r = pix / p.lay.row_len;
-          ec.out_base = im * p.lay.image_stride + r * p.lay.row_pitch + (pix - r * p.lay.row_len) * p.lay.row_stride;
+          const uint32_t r = fdiv(pix, p.d_rowlen);
+          ec.out_base = static_cast<int64_t>(im) * p.lay.image_stride + static_cast<int64_t>(r) * p.lay.row_pitch +
+                        static_cast<int64_t>(pix - r * static_cast<uint32_t>(p.lay.row_len)) * p.lay.row_stride;
         } else {
-          ec.out_base = im * p.lay.image_stride + pix * p.lay.row_stride;
+          ec.out_base = static_cast<int64_t>(im) * p.lay.image_stride + static_cast<int64_t>(pix) * p.lay.row_stride;
         }
       }
       named_bar_sync(1, kPEpilogueWarps * 32);
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
       const uint32_t bdesc_lo0 = static_cast<uint32_t>(bdesc0);
       uint32_t t = 0, wcount = 0, n = 0, a = 0;
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-        const uint32_t gi = it % n_groups;
+        const uint32_t gi = it - fdiv(it, p.d_groups) * n_groups;
         const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
         uint32_t opb = L.groups[gi].op_begin;
         const uint32_t ab = n & 1u;
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
     if (lane == 0) {
       uint32_t wcount = 0;
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const uint32_t gi = it % n_groups;
+        const uint32_t gi = it - fdiv(it, p.d_groups) * n_groups;
         const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
         const uint8_t* src = p.blob + static_cast<size_t>(L.groups[gi].blob_off16) * 16;
         for (uint32_t b = g_bb; b < g_be; ++b) {
@@ -432,16 +439,17 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
   } else {
     // =================================================================== activation loader (TMA)
     if (elect_one()) {
-      uint32_t t = 0;
+      uint32_t slot = 0, sphase = 0;
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const uint32_t gi = it % n_groups;
-        const int64_t m0 = static_cast<int64_t>(it / n_groups) * kTileM;
+        const uint32_t mt = fdiv(it, p.d_groups);
+        const uint32_t gi = it - mt * n_groups;
+        const int64_t m0 = static_cast<int64_t>(mt) * kTileM;
         const uint32_t g_bb = L.groups[gi].batch_begin, g_be = L.groups[gi].batch_end;
         uint32_t n_seg = 1, img0 = 0;
         int ih_first = 0;
         if constexpr (kHalo) {
-          const uint32_t R0 = static_cast<uint32_t>(m0) / static_cast<uint32_t>(p.Wo);
-          img0 = R0 / static_cast<uint32_t>(p.Ho);
+          const uint32_t R0 = fdiv(static_cast<uint32_t>(m0), p.d_wo);
+          img0 = fdiv(R0, p.d_ho);
           const uint32_t m_last = static_cast<uint32_t>(m0 + kTileM - 1 < p.M ? m0 + kTileM - 1 : p.M - 1);
           n_seg = m_last / static_cast<uint32_t>(p.Ho * p.Wo) - img0 + 1;
           ih_first = static_cast<int>(R0 - img0 * p.Ho) * p.stride - p.pad;
@@ -449,11 +457,10 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
         for (uint32_t b = g_bb; b < g_be; ++b) {
           const uint32_t bw = L.batches[b];
           if (!(bw & kBatchFirst)) continue;
-          const uint32_t slot = t % ring_slots, sphase = (t / ring_slots) & 1u;
-          ++t;
           mbar_wait(&h_empty[slot], sphase ^ 1u);
           tma_stage<MODE>(L, ring_addr + slot * p.slot_bytes, &h_full[slot], static_cast<int>(bw >> 16), m0, n_seg, img0,
                           ih_first);
+          if (++slot == ring_slots) { slot = 0; sphase ^= 1u; }
         }
       }
     }

@@ -48,12 +48,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity
   return ok;
 }
 __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
-  const long long t0 = clock64();
-  while (!mbar_try_wait(addr, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("accel_b200: mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
-             blockIdx.y, threadIdx.x, addr, parity);
-      __trap();
+  // the suspended try_wait may return early: keep the loop body to three instructions and look at the clock
+  // (time-out = a protocol bug) only once every 4096 rounds
+  long long t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(addr, parity)) return;
+    if ((spins & 4095u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+        printf("accel_b200: mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
+               blockIdx.y, threadIdx.x, addr, parity);
+        __trap();
+      }
     }
   }
 }

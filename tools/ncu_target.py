@@ -31,13 +31,16 @@ if "conv" in which:
         sp = [s for s in specs if s.name == name][0]
         syn = L.synthetic_conv_weights(sp, 70.0, idx)
         lay = L.BsrLayer(sp, syn["w2"])
-        x = torch.randint(-128, 128, (batch, sp.c_in, sp.h, sp.w), dtype=torch.int8, device="cuda")
-        res = torch.randint(-128, 128, (batch, sp.c_out, sp.h_out, sp.w_out), dtype=torch.int8, device="cuda")
+        x = ops.alloc_padded((batch, sp.c_in, sp.h, sp.w))            # 16-byte aligned rows: the TMA / persistent path
+        x.copy_(torch.randint(-128, 128, (batch, sp.c_in, sp.h, sp.w), dtype=torch.int8, device="cuda"))
+        res = ops.alloc_padded((batch, sp.c_out, sp.h_out, sp.w_out))
+        res.copy_(torch.randint(-128, 128, (batch, sp.c_out, sp.h_out, sp.w_out), dtype=torch.int8, device="cuda"))
+        out = ops.alloc_padded((batch, sp.c_out, sp.h_out, sp.w_out))
         for _ in range(reps):
             if sp.residual:
                 y = lay.plan.conv(x, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=lay.sf, residual=res,
-                                  res_scales=(0.05, 0.05, 0.05), relu_out=True)
+                                  res_scales=(0.05, 0.05, 0.05), relu_out=True, out=out)
             else:
-                y = lay.plan.conv(x, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=lay.sf, relu=True)
+                y = lay.plan.conv(x, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=lay.sf, relu=True, out=out)
         torch.cuda.synchronize()
 print("ok")
