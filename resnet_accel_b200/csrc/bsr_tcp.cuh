@@ -33,9 +33,10 @@ constexpr int kPMaxRingSlots = 4;
 // shared-memory map
 constexpr int kPSmemW = 0;
 constexpr int kPSmemBar = kPSmemW + kWStages * kWStageBytes;       // barriers (512 B)
-constexpr int kPSmemScale = kPSmemBar + 512;                       // float [176]
-constexpr int kPSmemBias = kPSmemScale + kAccCols * 4;             // int32 [176]
-constexpr int kPSmemRing = (kPSmemBias + kAccCols * 4 + 127) / 128 * 128;
+constexpr int kPTabGroups = 8;                                      // block-row groups whose constants stay resident
+constexpr int kPSmemScale = kPSmemBar + 512;                       // float [kPTabGroups][176]
+constexpr int kPSmemBias = kPSmemScale + kPTabGroups * kAccCols * 4;   // int32 [kPTabGroups][176]
+constexpr int kPSmemRing = (kPSmemBias + kPTabGroups * kAccCols * 4 + 127) / 128 * 128;
 
 // ---- int8 epilogue of one block-row for the persistent kernel: 32-bit element offsets (checked on the host),
 // residual bytes prefetched by the caller, and an unpredicated variant for the common case "all 14 channels
@@ -284,6 +285,18 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
       kind = !p.epi.residual ? kEpiI8 : (p.res_fast ? kEpiI8ResFast : kEpiI8Res);
     else if (!p.epi.chan_absmax && !sat_on && (ec.flags & ACCEL_OUT_I32)) kind = kEpiI32;
     if (sat_on && kind != kEpiGeneric) kind += 8;
+    const bool tabs_resident = n_groups <= static_cast<uint32_t>(kPTabGroups);
+    if (tabs_resident) {
+      for (uint32_t i = etid; i < n_groups * kAccCols; i += kPEpilogueWarps * 32) {
+        const uint32_t g = i / kAccCols, j = i - g * kAccCols;
+        const uint32_t br0 = L.groups[g].br0_rows & 0xffffu, rows = L.groups[g].br0_rows >> 16;
+        const int c = br0 * kBlock + j;
+        const bool ok = j < rows * kBlock && c < p.epi.n_channels;
+        s_scale[i] = (ok && p.epi.chan_scale) ? p.epi.chan_scale[c] : 0.f;
+        s_bias[i] = (ok && p.epi.bias) ? p.epi.bias[c] : 0;
+      }
+      named_bar_sync(1, kPEpilogueWarps * 32);
+    }
     uint32_t n = 0;
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
       const uint32_t mt = fdiv(it, p.d_groups);
@@ -291,13 +304,17 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
       const int64_t m0 = static_cast<int64_t>(mt) * kTileM;
       const uint32_t g_br0 = L.groups[gi].br0_rows & 0xffffu, g_rows = L.groups[gi].br0_rows >> 16;
       const uint32_t ab = n & 1u;
-      // per-channel constants of this item's block-row group (the previous item's readers are done: barrier first)
-      named_bar_sync(1, kPEpilogueWarps * 32);
-      if (static_cast<uint32_t>(etid) < g_rows * kBlock) {
-        const int c = g_br0 * kBlock + etid;
-        const bool ok = c < p.epi.n_channels;
-        s_scale[etid] = (ok && p.epi.chan_scale) ? p.epi.chan_scale[c] : 0.f;
-        s_bias[etid] = (ok && p.epi.bias) ? p.epi.bias[c] : 0;
+      // per-channel constants: resident for every group of the launch when there are few groups (loaded once,
+      // above); otherwise reloaded per item into table 0 (the previous item's readers are done: barrier first)
+      const uint32_t tab = tabs_resident ? gi : 0u;
+      if (!tabs_resident) {
+        named_bar_sync(1, kPEpilogueWarps * 32);
+        if (static_cast<uint32_t>(etid) < g_rows * kBlock) {
+          const int c = g_br0 * kBlock + etid;
+          const bool ok = c < p.epi.n_channels;
+          s_scale[etid] = (ok && p.epi.chan_scale) ? p.epi.chan_scale[c] : 0.f;
+          s_bias[etid] = (ok && p.epi.bias) ? p.epi.bias[c] : 0;
+        }
       }
       const int64_t m = m0 + (warp & 3) * 32 + lane;
       ec.row_ok = m < p.M;
@@ -315,14 +332,14 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
           ec.out_base = static_cast<int64_t>(im) * p.lay.image_stride + static_cast<int64_t>(pix) * p.lay.row_stride;
         }
       }
-      named_bar_sync(1, kPEpilogueWarps * 32);
+      if (!tabs_resident) named_bar_sync(1, kPEpilogueWarps * 32);
       const bool fast8 = p.out_small && (kind & 7) <= kEpiI8Res;      // int8 output with 32-bit element offsets
       if (fast8) {
         EpiItem ei;
         ei.acc0 = tmem_base + lane_base + ab * kAccCols;
         ei.g_first = static_cast<uint32_t>(ehalf); ei.g_rows = g_rows; ei.g_br0 = g_br0;
         ei.bar = &acc_full[ab]; ei.parity = (n >> 1) & 1u;
-        ei.s_scale = s_scale; ei.s_bias = s_bias;
+        ei.s_scale = s_scale + tab * kAccCols; ei.s_bias = s_bias + tab * kAccCols;
         switch ((kind & 7) * 2 + (sat_on ? 1 : 0)) {
           case 0: epi_i8_item<0, false>(p, ec, ei); break;
           case 1: epi_i8_item<0, true>(p, ec, ei); break;
@@ -340,8 +357,8 @@ __global__ void __launch_bounds__(kPThreads, 1) bsr_tcp_kernel(const __grid_cons
           tmem_ld16(acc0 + g * kTile, v);
           const int cb = (g_br0 + g) * kBlock;
           const int n_ok = min(kBlock, p.epi.n_channels - cb);
-          const float* sc = s_scale + g * kBlock;
-          const int32_t* bi = s_bias + g * kBlock;
+          const float* sc = s_scale + tab * kAccCols + g * kBlock;
+          const int32_t* bi = s_bias + tab * kAccCols + g * kBlock;
           switch (kind) {
             case kEpiI8: epilogue_row<kEpiI8, false>(p, ec, v, cb, n_ok, sc, bi); break;
             case kEpiI8ResFast: epilogue_row<kEpiI8ResFast, false>(p, ec, v, cb, n_ok, sc, bi); break;
