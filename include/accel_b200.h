@@ -97,6 +97,8 @@ ACCEL_API int accel_device_check(void);
  * (kernel entry, prologue done, first activation stage acquired / published, main loop done by the producers,
  * accumulators complete, epilogue done, CTA exit).  The buffer must hold 8 int64 per CTA of the largest launch. */
 ACCEL_API void accel_debug_set_timeline(long long* dev_buffer);
+/* Developer aid: event counters of this process.  which = 0: launches of the weight-stationary convolution kernel. */
+ACCEL_API long long accel_debug_counter(int which);
 
 /* --- weight plan: replaces AccelDriver.load_sparse_weights (sw/host/accel.py:177-236) and
  *     AcceleratorDriver::set_layer_weights / load_weights_bsr (accelerator_driver.cpp:643-760).
@@ -132,6 +134,17 @@ ACCEL_API int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64
  * with the BSR weights of export_bsr_14x14.py).  Output NCHW through `layout`. */
 ACCEL_API int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const accel_conv_geom* geom,
                       const accel_epilogue* epi, void* out, const accel_out_layout* layout, accel_stream_t stream);
+
+/* --- weight-stationary re-layout for 3x3 stride-1 pad-1 convolutions (conv2d_int8_im2col, golden_models.cpp:883-933,
+ * K order (c_in, kh, kw) of im2col_int8 :801-842).  Optional: when a plan has been prepared for (c_in, c_out) and the
+ * tensors of an accel_conv_bsr_i8 call allow it (16-byte aligned rows, int8 output, width <= 62), that call runs the
+ * kernel of csrc/conv_ws.cuh: the stored blocks are scattered once into 128x32 K-major weight tiles per
+ * (channel group, 32-channel chunk, tap) and the activation tile is fed to the tensor core straight from TMA.
+ * conv_ws_bytes reports the workspace for that layout (0 = no such path for this geometry); conv_ws_prepare fills it
+ * (`workspace_dev` 1024-byte aligned, owned by the caller for the life of the plan; synchronises `stream`). */
+ACCEL_API int accel_plan_conv_ws_bytes(const accel_plan* plan, int32_t c_in, int32_t c_out, int32_t ksize, size_t* bytes);
+ACCEL_API int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32_t c_in, int32_t c_out, int32_t ksize,
+                               void* workspace_dev, size_t workspace_bytes, accel_stream_t stream);
 
 /* --- reference-shaped CUDA-core kernels: any block size (4/8/14/16 fixtures), Convention B or A.
  * Same arithmetic as above, used for the generic-block path and as an on-device cross-check.

@@ -50,6 +50,7 @@ SYMBOLS = {
     "accel_version": (C.c_char_p, []),
     "accel_device_check": (C.c_int, []),
     "accel_debug_set_timeline": (None, [_P]),
+    "accel_debug_counter": (C.c_longlong, [C.c_int]),
     "accel_plan_create": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, C.POINTER(_P), C.POINTER(_SZ)]),
     "accel_plan_upload": (C.c_int, [_P, _P, _P, _SZ, _P]),
     "accel_plan_destroy": (None, [_P]),
@@ -58,6 +59,8 @@ SYMBOLS = {
     "accel_plan_num_tiles": (_I64, [_P]),
     "accel_plan_export_ops": (_I64, [_P, _P, _I64]),
     "accel_plan_export_mma": (_I64, [_P, _P, _I64]),
+    "accel_plan_conv_ws_bytes": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_SZ)]),
+    "accel_plan_conv_ws_prepare": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _SZ, _P]),
     "accel_bsr_gemm_i8": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(Epilogue), _P, C.POINTER(OutLayout), _P]),
     "accel_conv_bsr_i8": (C.c_int, [_P, _P, C.POINTER(ConvGeom), C.POINTER(Epilogue), _P, C.POINTER(OutLayout), _P]),
     "accel_bsr_gemm_generic": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _P, _I64, _P]),

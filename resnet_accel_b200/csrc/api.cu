@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <array>
 #include <climits>
 #include <cmath>
@@ -11,10 +12,12 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/accel_b200.h"
 #include "bsr_tc.cuh"
 #include "bsr_tcp.cuh"
+#include "conv_ws.cuh"
 #include "plan.h"
 #include "simple_kernels.cuh"
 
@@ -55,11 +58,14 @@ int grid_for(int64_t work_items, int threads, int per_sm = 8) {
 long long* g_timeline = nullptr;   // accel_debug_set_timeline
 int g_dbg_flags = 0;
 bool g_no_persist = std::getenv("ACCEL_NO_PERSIST") != nullptr;   // developer switch: one-shot kernel everywhere
+long long g_ws_launches = 0;         // accel_debug_counter(0)
+bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
 constexpr int kSmemTwoCtas = 113 * 1024;    // per CTA when two CTAs share an SM (227 KB usable, 1 KB reserved each)
 constexpr int kSmemOneCta = 200 * 1024;
 constexpr int kSmemPersist = 220 * 1024;    // the persistent kernel owns its SM
+constexpr int kSmemWs = 227 * 1024;         // conv_ws_kernel: everything an SM has
 void set_kernel_attrs() {
   const void* fns[] = {reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeGemm>),
                        reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeConv3>),
@@ -76,6 +82,9 @@ void set_kernel_attrs() {
     if (g_attr_err == cudaSuccess)
       g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPersist);
   }
+  if (g_attr_err == cudaSuccess)
+    g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::conv_ws_kernel),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
 }
 
 int check_epilogue(const accel_epilogue* epi, const accel_out_layout* lay, const void* out, int32_t max_channels) {
@@ -146,7 +155,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 // int8 tensor, dims / box innermost first, strides in bytes for dims 1..rank-1 (multiples of 16)
 bool encode_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                 const uint32_t* box) {
+                 const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint64_t gd[4], gs[3];
@@ -154,7 +163,7 @@ bool encode_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* di
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs, bx, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -257,9 +266,126 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cu
 
 }  // namespace
 
+// weight-stationary convolution state of a plan (conv_ws.cuh): one prepared geometry
+struct WsState {
+  bool ready = false;
+  int32_t c_in = 0, c_out = 0, n_chunks = 0, n_groups = 0;
+  const uint8_t* blob = nullptr;
+  uint16_t masks[accel::kWsMaxGroups * accel::kWsMaxChunks] = {};
+};
+
 struct accel_plan {
   accel::Plan p;
+  std::vector<int32_t> row_ptr, col_idx;   // host copies of the BSR structure (for later re-layouts)
+  WsState ws;
 };
+
+namespace {
+
+bool ws_geometry_ok(const accel_plan* plan, int32_t c_in, int32_t c_out, int32_t ksize) {
+  if (ksize != 3 || c_in <= 0 || c_in % accel::kWsCk != 0 || c_in / accel::kWsCk > accel::kWsMaxChunks) return false;
+  if (c_out <= 0 || c_out > plan->p.nbr * accel::kBlock || (c_out + accel::kWsCo - 1) / accel::kWsCo > accel::kWsMaxGroups)
+    return false;
+  return (static_cast<int64_t>(c_in) * 9 + accel::kBlock - 1) / accel::kBlock <= plan->p.nbc;
+}
+size_t ws_blob_bytes(int32_t c_in, int32_t c_out) {
+  return static_cast<size_t>((c_out + accel::kWsCo - 1) / accel::kWsCo) * (c_in / accel::kWsCk) * accel::kWsChunkBytes;
+}
+
+constexpr int kWsNotApplicable = 1;
+
+// Route a convolution to conv_ws_kernel when geometry, layouts and alignment allow; kWsNotApplicable otherwise.
+int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_geom* g, const accel_epilogue* epi, void* out,
+                const accel_out_layout* lay, cudaStream_t st) {
+  const WsState& W = plan->ws;
+  if (g_no_ws || !W.ready || g->ksize != 3 || g->stride != 1 || g->pad != 1 || g->batch <= 0) return kWsNotApplicable;
+  if (g->c_in != W.c_in || epi->n_channels != W.c_out) return kWsNotApplicable;
+  if (!(epi->flags & ACCEL_OUT_I8) || epi->chan_absmax) return kWsNotApplicable;
+  const int Wd = g->w, H = g->h;
+  const int P = Wd <= 14 ? 16 : (Wd <= 30 ? 32 : (Wd <= 62 ? 64 : 0));     // two padding pixels end every staged row
+  if (!P) return kWsNotApplicable;
+  const int64_t in_pitch = g->in_row_pitch > 0 ? g->in_row_pitch : g->w;
+  if ((in_pitch & 15) || (reinterpret_cast<uintptr_t>(input) & 15)) return kWsNotApplicable;
+  // output (and residual): NCHW, 16-byte aligned rows that can take whole 16-pixel stores
+  const int w16 = (Wd + 15) / 16 * 16;
+  int64_t out_pitch;
+  if (lay->row_len == 0) {
+    out_pitch = Wd;
+    if (Wd % 16 || lay->chan_stride != static_cast<int64_t>(H) * Wd) return kWsNotApplicable;
+  } else {
+    out_pitch = lay->row_pitch;
+    if (lay->row_len != Wd || lay->chan_stride != static_cast<int64_t>(H) * out_pitch) return kWsNotApplicable;
+  }
+  if (lay->row_stride != 1 || out_pitch < w16 || (out_pitch & 15) || lay->rows_per_image != static_cast<int64_t>(H) * Wd ||
+      lay->image_stride != lay->chan_stride * W.c_out)
+    return kWsNotApplicable;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(epi->residual) & 15)) return kWsNotApplicable;
+  if (lay->image_stride * g->batch >= (1ll << 31) || in_pitch * H * g->c_in * g->batch >= (1ll << 40)) return kWsNotApplicable;
+
+  std::call_once(g_attr_once, set_kernel_attrs);
+  if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(smem)");
+  static thread_local accel::WsLaunch L;
+  accel::WsParams& p = L.p;
+  std::memset(&p, 0, sizeof(p));
+  p.C = g->c_in; p.H = H; p.W = Wd; p.B = g->batch; p.P = P;
+  int best_r = 1, best_cost = INT_MAX;
+  for (int r = 1; r <= 128 / P; ++r) {
+    const int cost = (H + r - 1) / r * r;
+    if (cost <= best_cost) { best_cost = cost; best_r = r; }
+  }
+  p.R = best_r; p.N = p.R * P;
+  p.n_chunks = W.n_chunks; p.n_groups = W.n_groups; p.c_out = W.c_out;
+  p.tiles_per_image = (H + p.R - 1) / p.R;
+  const int64_t n_tiles = static_cast<int64_t>(g->batch) * p.tiles_per_image;
+  if (n_tiles > INT_MAX) return kWsNotApplicable;
+  p.n_tiles = static_cast<int32_t>(n_tiles);
+  p.w_resident = W.n_chunks <= accel::kWsMaxWSlots ? 1 : 0;
+  p.w_slots = p.w_resident ? W.n_chunks : accel::kWsMaxWSlots;
+  p.a_box_bytes = accel::kWsCk * (p.R + 2) * P;
+  p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+  const int fixed = 1024 /* alignment slack */ + accel::kWsSmemBar + p.w_slots * accel::kWsChunkBytes;
+  int a_slots = (kSmemWs - fixed) / p.a_stage_bytes;
+  if (a_slots > accel::kWsMaxASlots) a_slots = accel::kWsMaxASlots;
+  if (a_slots < 2) return kWsNotApplicable;
+  p.a_slots = a_slots;
+  p.row_stride = static_cast<uint32_t>(accel::kWsCk * P);          // bytes between staged image rows
+  const uint32_t grp_stride = static_cast<uint32_t>(8 * P);        // bytes between 8-channel groups
+  p.b_layout = P == 64 ? 4u : (P == 32 ? 6u : 0u);
+  // swizzled: LBO = stride between pixel atoms (image rows), SBO = stride between 8-channel groups; unswizzled: swapped
+  p.b_lbo = p.b_layout ? p.row_stride : grp_stride;
+  p.b_sbo = p.b_layout ? grp_stride : p.row_stride;
+  p.d_tpi = accel::make_fastdiv(static_cast<uint32_t>(p.tiles_per_image));
+  p.wblob = W.blob;
+  p.epi = *epi;
+  if (epi->residual) {
+    p.res_fast = residual_fast_divide_ok(epi->res_scale_main, epi->res_scale_res, epi->res_scale_out) ? 1 : 0;
+    p.res_rcp = 1.0f / epi->res_scale_out;
+  }
+  p.out = static_cast<int8_t*>(out);
+  p.out_pitch = static_cast<int32_t>(out_pitch);
+  p.chan_stride = static_cast<int32_t>(lay->chan_stride);
+  p.x_store_end = w16;
+  p.image_stride = lay->image_stride;
+  std::memcpy(p.masks, W.masks, sizeof(p.masks));
+  const uint64_t dims[4] = {static_cast<uint64_t>(Wd), static_cast<uint64_t>(g->c_in), static_cast<uint64_t>(H),
+                            static_cast<uint64_t>(g->batch)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(in_pitch) * H, static_cast<uint64_t>(in_pitch),
+                               static_cast<uint64_t>(in_pitch) * H * g->c_in};
+  const uint32_t box[4] = {static_cast<uint32_t>(P), static_cast<uint32_t>(accel::kWsCk), static_cast<uint32_t>(p.R + 2), 1u};
+  const CUtensorMapSwizzle sw = P == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (P == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (!encode_tmap(&L.tmap, input, 4, dims, strides, box, sw)) return kWsNotApplicable;
+  int per_group = sm_count() / p.n_groups;
+  if (per_group > p.n_tiles) per_group = p.n_tiles;
+  if (per_group < 1) return kWsNotApplicable;
+  const int smem = fixed + p.a_slots * p.a_stage_bytes;
+  accel::conv_ws_kernel<<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "conv_ws_kernel launch");
+  ++g_ws_launches;
+  return ACCEL_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -271,6 +397,8 @@ void accel_debug_set_timeline(long long* dev_buffer) {
   const char* f = std::getenv("ACCEL_DBG_FLAGS");
   g_dbg_flags = f ? std::atoi(f) : 0;
 }
+
+long long accel_debug_counter(int which) { return which == 0 ? g_ws_launches : -1; }
 
 int accel_device_check(void) {
   int dev = 0;
@@ -295,8 +423,64 @@ int accel_plan_create(const int32_t* row_ptr_host, const int32_t* col_idx_host, 
     delete pl;
     return fail(ACCEL_INVALID_CONFIG, msg);
   }
+  pl->row_ptr.assign(row_ptr_host, row_ptr_host + n_block_rows + 1);
+  if (row_ptr_host[n_block_rows] > 0) pl->col_idx.assign(col_idx_host, col_idx_host + row_ptr_host[n_block_rows]);
   *plan_out = pl;
   *workspace_bytes = pl->p.ws_bytes;
+  return ACCEL_OK;
+}
+
+int accel_plan_conv_ws_bytes(const accel_plan* plan, int32_t c_in, int32_t c_out, int32_t ksize, size_t* bytes) {
+  if (!plan || !bytes) return fail(ACCEL_INVALID_CONFIG, "null argument");
+  *bytes = 0;
+  if (!ws_geometry_ok(plan, c_in, c_out, ksize)) return ACCEL_OK;          // 0 bytes: this geometry has no such path
+  *bytes = ws_blob_bytes(c_in, c_out) + (static_cast<size_t>(plan->p.nnz) * 8 + 255) / 256 * 256;
+  return ACCEL_OK;
+}
+
+int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32_t c_in, int32_t c_out, int32_t ksize,
+                               void* workspace_dev, size_t workspace_bytes, accel_stream_t stream) {
+  if (!plan || !workspace_dev) return fail(ACCEL_INVALID_CONFIG, "null plan / workspace");
+  if (!ws_geometry_ok(plan, c_in, c_out, ksize)) return fail(ACCEL_INVALID_CONFIG, "geometry has no weight-stationary path");
+  const size_t blob = ws_blob_bytes(c_in, c_out);
+  const int64_t nnz = plan->p.nnz;
+  if (workspace_bytes < blob + static_cast<size_t>(nnz) * 8) return fail(ACCEL_MEMORY_ERROR, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace_dev) & 1023) return fail(ACCEL_MEMORY_ERROR, "workspace not 1024-byte aligned");
+  if (nnz > 0 && !blocks_dev) return fail(ACCEL_INVALID_CONFIG, "null blocks");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WsState& W = plan->ws;
+  W.ready = false;
+  W.c_in = c_in; W.c_out = c_out; W.n_chunks = c_in / accel::kWsCk; W.n_groups = (c_out + accel::kWsCo - 1) / accel::kWsCo;
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  CU(cudaMemsetAsync(ws, 0, blob, st));
+  std::memset(W.masks, 0, sizeof(W.masks));
+  std::vector<int32_t> blk_row(static_cast<size_t>(nnz));
+  const int32_t K = c_in * 9;
+  for (int32_t br = 0; br < plan->p.nbr; ++br)
+    for (int32_t i = plan->row_ptr[br]; i < plan->row_ptr[br + 1]; ++i) {
+      blk_row[i] = br;
+      const int32_t bc = plan->col_idx[i];
+      const int co_lo = br * accel::kBlock, co_hi = std::min(co_lo + accel::kBlock, c_out) - 1;
+      if (co_hi < co_lo) continue;
+      for (int k = bc * accel::kBlock; k < std::min((bc + 1) * accel::kBlock, K); ++k) {
+        const int c = k / 9, tap = k % 9, j = c / accel::kWsCk;
+        W.masks[(co_lo / accel::kWsCo) * accel::kWsMaxChunks + j] |= static_cast<uint16_t>(1u << tap);
+        W.masks[(co_hi / accel::kWsCo) * accel::kWsMaxChunks + j] |= static_cast<uint16_t>(1u << tap);
+      }
+    }
+  // the first chunk always issues all nine taps: they initialise the accumulators in a fixed order
+  for (int gi = 0; gi < W.n_groups; ++gi) W.masks[gi * accel::kWsMaxChunks] = 0x1ff;
+  if (nnz > 0) {
+    int32_t* d_row = reinterpret_cast<int32_t*>(ws + blob);
+    int32_t* d_col = d_row + nnz;
+    CU(cudaMemcpyAsync(d_row, blk_row.data(), static_cast<size_t>(nnz) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_col, plan->col_idx.data(), static_cast<size_t>(nnz) * 4, cudaMemcpyHostToDevice, st));
+    accel::ws_scatter_kernel<<<static_cast<unsigned>(nnz), 64, 0, st>>>(blocks_dev, d_row, d_col, nnz, c_in, c_out, W.n_chunks, ws);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(st));     // blk_row is pageable host memory
+  W.blob = ws;
+  W.ready = true;
   return ACCEL_OK;
 }
 
@@ -421,6 +605,8 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
   if (g->batch > 0 && !input_nchw) return fail(ACCEL_INVALID_CONFIG, "Activations not loaded");
   int rc = check_epilogue(epi, layout, out, plan->p.nbr * accel::kBlock);
   if (rc) return rc;
+  rc = try_conv_ws(plan, input_nchw, g, epi, out, layout, static_cast<cudaStream_t>(stream));
+  if (rc != kWsNotApplicable) return rc;
   accel::TcParams prm;
   std::memset(&prm, 0, sizeof(prm));
   prm.Ho = (g->h + 2 * g->pad - g->ksize) / g->stride + 1;

@@ -103,6 +103,8 @@ class BsrPlan:
         self.num_blocks = int(L.accel_plan_num_blocks(self._h))
         self.num_mma = int(L.accel_plan_num_mma(self._h))
         self.row_ptr, self.col_idx = rp, ci
+        self._blocks = blk                      # kept for later re-layouts (conv_ws)
+        self._ws_conv = {}                      # (c_in, c_out, ksize) -> workspace tensor (None: no such path)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -112,6 +114,24 @@ class BsrPlan:
             except Exception:
                 pass
             self._h = None
+
+    def _prepare_conv_ws(self, c_in: int, c_out: int, ksize: int) -> None:
+        """Weight-stationary layout for 3x3 stride-1 convolutions (csrc/conv_ws.cuh), built once per geometry."""
+        key = (int(c_in), int(c_out), int(ksize))
+        if key in self._ws_conv:
+            return
+        self._ws_conv.clear()                   # the plan holds one prepared geometry at a time
+        L = _lib.lib()
+        nbytes = C.c_size_t()
+        check(L.accel_plan_conv_ws_bytes(self._h, key[0], key[1], key[2], C.byref(nbytes)))
+        if nbytes.value == 0:
+            self._ws_conv[key] = None
+            return
+        buf = torch.empty(int(nbytes.value) + 1024, dtype=torch.uint8, device=self.device)
+        ptr = buf.data_ptr() + (-buf.data_ptr()) % 1024
+        check(L.accel_plan_conv_ws_prepare(self._h, _ptr(self._blocks) if self.col_idx.size else None, key[0], key[1], key[2],
+                                           ptr, int(nbytes.value), _stream()))
+        self._ws_conv[key] = buf
 
     @property
     def n_out_padded(self) -> int:
@@ -199,6 +219,8 @@ class BsrPlan:
                     raise AcceleratorError(_lib.INVALID_CONFIG, "residual strides must equal the output strides")
         e, keep = self._epilogue(out_kind, c_out, chan_scale, bias, relu, residual, res_scales, sat_count, chan_absmax,
                                  relu_out)
+        if ksize == 3 and stride == 1 and pad == 1 and out_kind == "i8" and chan_absmax is None and W <= 62:
+            self._prepare_conv_ws(Cin, c_out, ksize)
         g = ConvGeom(B, Cin, H, W, ksize, stride, pad, in_pitch)
         P = max(Ho * Wo, 1)
         if out_pitch == Wo:

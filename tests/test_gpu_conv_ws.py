@@ -1,0 +1,103 @@
+"""GPU parity: the weight-stationary 3x3 / stride-1 convolution kernel (csrc/conv_ws.cuh) vs the C oracle. Bit-exact.
+
+The kernel is taken when activations have 16-byte aligned rows (ops.alloc_padded), Cin % 32 == 0 and W <= 62; every case
+checks that it really ran (accel_debug_counter) so a silent fall-back to the gather kernels cannot hide a failure."""
+import numpy as np
+import pytest
+
+from oracle import bsr_oracle as O
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(B, Cin, H, W, Cout, density, seed, residual=True, relu=False, relu_out=True, bias_on=True):
+    import torch
+    from resnet_accel_b200 import _lib, ops
+    from resnet_accel_b200.ops import BsrPlan
+    rng = np.random.default_rng(seed)
+    K = Cin * 9
+    Wm = rng.integers(-128, 128, (Cout, K), dtype=np.int8)
+    nbr, nbc = -(-Cout // 14), -(-K // 14)
+    keep = rng.random((nbr, nbc)) < density
+    Wm = Wm * np.repeat(np.repeat(keep, 14, 0), 14, 1)[:Cout, :K].astype(np.int8)
+    bsr = O.build_bsr_14x14_int8_direct(Wm)
+    x = rng.integers(-128, 128, (B, Cin, H, W), dtype=np.int8)
+    bias = rng.integers(-1000, 1000, Cout, dtype=np.int32) if bias_on else None
+    sf = rng.uniform(1e-4, 2e-3, Cout).astype(np.float32)
+    res = rng.integers(-128, 128, (B, Cout, H, W), dtype=np.int8) if residual else None
+    plan = BsrPlan(bsr["indptr"], bsr["indices"], bsr["data"], n_block_cols=bsr["num_block_cols"])
+    xd = ops.alloc_padded(x.shape)
+    xd.copy_(torch.from_numpy(x).cuda())
+    # garbage in the row padding of the INPUT must not matter: TMA zero-fills beyond W
+    base_in = xd._base if xd._base is not None else xd
+    if base_in.shape[-1] > W:
+        base_in[..., W:] = 77
+    rd = None
+    if residual:
+        rd = ops.alloc_padded(res.shape)
+        rd.copy_(torch.from_numpy(res).cuda())
+    out = ops.alloc_padded((B, Cout, H, W))
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    before = _lib.lib().accel_debug_counter(0)
+    plan.conv(xd, 3, 1, 1, Cout, out_kind="i8", chan_scale=sf, bias=bias, relu=relu, residual=rd,
+              res_scales=(0.05, 0.02, 0.04), sat_count=cnt, relu_out=relu_out, out=out)
+    torch.cuda.synchronize()
+    assert _lib.lib().accel_debug_counter(0) == before + 1, "the weight-stationary kernel did not run"
+    ref, sat = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, 3, 1, 1, bias=bias,
+                                       relu=relu, sf=sf, residual=res, res_scales=(0.05, 0.02, 0.04))
+    if relu_out:
+        ref = np.maximum(ref, 0)
+    got = out.cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    assert int(cnt.item()) == sat
+    base = out._base if out._base is not None else out
+    assert int(base[..., W:].abs().sum().item()) == 0          # row padding of the output stays zero
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,density", [
+    (2, 64, 56, 56, 64, 0.3),        # ResNet-18 layer1: 64-byte rows, 2 output rows per tile, weights resident
+    (3, 128, 28, 28, 128, 0.3),      # layer2: 32-byte rows, 4 rows per tile, weights resident (4 chunks)
+    (3, 256, 14, 14, 256, 0.3),      # layer3: 16-byte rows, 7 rows per tile, two channel groups, weights streamed
+    (5, 512, 7, 7, 512, 0.3),        # layer4: one tile per image, four channel groups, 16 chunks streamed
+    (2, 32, 9, 20, 40, 0.5),         # ragged last tile (9 rows in tiles of 4), Cout not a multiple of 14
+    (2, 64, 13, 37, 200, 0.4),       # two channel groups, the second partial; odd sizes
+    (1, 96, 5, 3, 10, 1.0),          # tiny image, dense weights
+    (2, 64, 30, 62, 70, 0.2),        # widest supported row (62 + 2 padding pixels)
+    (2, 64, 12, 12, 30, 0.0),        # no stored blocks at all
+    (2, 160, 11, 14, 129, 0.05),     # very sparse: some (chunk, tap) weight tiles are empty and skipped
+])
+def test_conv_ws_vs_oracle(B, Cin, H, W, Cout, density):
+    _case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W + Cout)
+
+
+def test_conv_ws_epilogue_variants():
+    _case(2, 64, 14, 14, 64, 0.3, seed=1, residual=False, relu=True, relu_out=False)
+    _case(2, 64, 14, 14, 64, 0.3, seed=2, residual=False, relu=False, relu_out=False, bias_on=False)
+    _case(2, 64, 14, 14, 64, 0.3, seed=3, residual=True, relu=True, relu_out=False)
+
+
+def test_conv_ws_many_tiles_persistent():
+    """More tiles than CTAs: every CTA walks several tiles (accumulator double-buffering, ring wrap-around)."""
+    _case(40, 64, 28, 28, 64, 0.3, seed=11)
+    _case(24, 256, 14, 14, 128, 0.3, seed=12)
+
+
+def test_conv_ws_dense_layout_and_fallback():
+    """W % 16 == 0 tensors are accepted without padding; unaligned tensors fall back to the gather kernels."""
+    import torch
+    from resnet_accel_b200 import _lib
+    from resnet_accel_b200.ops import BsrPlan
+    rng = np.random.default_rng(9)
+    B, Cin, H, W, Cout = 2, 32, 10, 30, 20
+    Wm = rng.integers(-128, 128, (Cout, Cin * 9), dtype=np.int8)
+    bsr = O.build_bsr_14x14_int8_direct(Wm)
+    x = rng.integers(-128, 128, (B, Cin, H, W), dtype=np.int8)
+    sf = rng.uniform(1e-4, 2e-3, Cout).astype(np.float32)
+    plan = BsrPlan(bsr["indptr"], bsr["indices"], bsr["data"], n_block_cols=bsr["num_block_cols"])
+    before = _lib.lib().accel_debug_counter(0)
+    got = plan.conv(torch.from_numpy(x).cuda(), 3, 1, 1, Cout, out_kind="i8", chan_scale=sf).cpu().numpy()   # rows of 30 bytes
+    assert _lib.lib().accel_debug_counter(0) == before
+    ref, _ = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, 3, 1, 1, sf=sf)
+    assert np.array_equal(got, ref)
