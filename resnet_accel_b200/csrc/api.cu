@@ -321,6 +321,7 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
     return kWsNotApplicable;
   if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(epi->residual) & 15)) return kWsNotApplicable;
   if (lay->image_stride * g->batch >= (1ll << 31) || in_pitch * H * g->c_in * g->batch >= (1ll << 40)) return kWsNotApplicable;
+  if (in_pitch * H * accel::kWsCk >= (1ll << 31)) return kWsNotApplicable;
 
   std::call_once(g_attr_once, set_kernel_attrs);
   if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(smem)");
@@ -346,7 +347,7 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   const int fixed = 1024 /* alignment slack */ + accel::kWsSmemBar + p.w_slots * accel::kWsChunkBytes;
   int a_slots = (kSmemWs - fixed) / p.a_stage_bytes;
   if (a_slots > accel::kWsMaxASlots) a_slots = accel::kWsMaxASlots;
-  if (a_slots < 2) return kWsNotApplicable;
+  if (a_slots < 3) return kWsNotApplicable;
   p.a_slots = a_slots;
   p.row_stride = static_cast<uint32_t>(accel::kWsCk * P);          // bytes between staged image rows
   const uint32_t grp_stride = static_cast<uint32_t>(8 * P);        // bytes between 8-channel groups
@@ -356,6 +357,7 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   p.b_sbo = p.b_layout ? grp_stride : p.row_stride;
   p.d_tpi = accel::make_fastdiv(static_cast<uint32_t>(p.tiles_per_image));
   p.wblob = W.blob;
+  p.x = input; p.in_pitch = static_cast<int32_t>(in_pitch);
   p.epi = *epi;
   if (epi->residual) {
     p.res_fast = residual_fast_divide_ok(epi->res_scale_main, epi->res_scale_res, epi->res_scale_out) ? 1 : 0;
@@ -367,6 +369,7 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   p.x_store_end = w16;
   p.image_stride = lay->image_stride;
   std::memcpy(p.masks, W.masks, sizeof(p.masks));
+  p.dbg = g_dbg_flags;
   const uint64_t dims[4] = {static_cast<uint64_t>(Wd), static_cast<uint64_t>(g->c_in), static_cast<uint64_t>(H),
                             static_cast<uint64_t>(g->batch)};
   const uint64_t strides[3] = {static_cast<uint64_t>(in_pitch) * H, static_cast<uint64_t>(in_pitch),
@@ -374,8 +377,10 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   const uint32_t box[4] = {static_cast<uint32_t>(P), static_cast<uint32_t>(accel::kWsCk), static_cast<uint32_t>(p.R + 2), 1u};
   const CUtensorMapSwizzle sw = P == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (P == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
   if (!encode_tmap(&L.tmap, input, 4, dims, strides, box, sw)) return kWsNotApplicable;
+  p.dual = W.c_out <= 64 ? 1 : 0;
+  const int n_items = p.dual ? (p.n_tiles + 1) / 2 : p.n_tiles;
   int per_group = sm_count() / p.n_groups;
-  if (per_group > p.n_tiles) per_group = p.n_tiles;
+  if (per_group > n_items) per_group = n_items;
   if (per_group < 1) return kWsNotApplicable;
   const int smem = fixed + p.a_slots * p.a_stage_bytes;
   accel::conv_ws_kernel<<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);

@@ -29,10 +29,15 @@
 
 namespace accel {
 
-constexpr int kWsEpiWarps = 8;
-constexpr int kWsWarpIssue = kWsEpiWarps;          // 8
-constexpr int kWsWarpLoad = kWsWarpIssue + 1;      // 9
-constexpr int kWsThreads = (kWsWarpLoad + 1) * 32; // 320
+constexpr int kWsEpiWarps = 8;                     // warps 0-7: epilogue
+constexpr int kWsWarpIssue = kWsEpiWarps;          // 8: MMA issuer (+ TMEM allocation)
+constexpr int kWsWarpWeights = kWsWarpIssue + 1;   // 9: weight tiles by bulk copy (its own warp: it must never hold back
+                                                   //    the activation loaders, or the two rings deadlock)
+constexpr int kWsWarpLoad = kWsWarpWeights + 1;    // 10, 11: activation loaders (LDGSTS)
+constexpr int kWsLoadWarps = 6;
+constexpr int kWsLoadThreads = kWsLoadWarps * 32;  // 64
+constexpr int kWsThreads = (kWsWarpLoad + kWsLoadWarps) * 32;   // 384
+constexpr int kWsLoadOps = 3;                      // 16-byte copies per loader thread and stage (<= 512 per stage)
 constexpr int kWsCo = 128;                         // output channels per group (TMEM lanes)
 constexpr int kWsCk = 32;                          // input channels per chunk (one MMA K)
 constexpr int kWsTapBytes = kWsCo * kWsCk;         // 4096
@@ -50,6 +55,9 @@ struct WsParams {
   int32_t n_chunks, n_groups, c_out;
   int32_t tiles_per_image, n_tiles;   // row tiles per image, B * tiles_per_image
   int32_t w_slots, w_resident, a_slots, a_stage_bytes, a_box_bytes;
+  const int8_t* x;             // input tensor, rows of in_pitch bytes
+  int32_t in_pitch;
+  int32_t dual;                // c_out <= 64: items are pairs of pixel tiles, two interleaved M = 64 accumulators
   uint32_t b_layout, b_lbo, b_sbo, row_stride;
   FastDiv d_tpi;
   const uint8_t* wblob;        // [group][chunk][tap][4096]
@@ -61,6 +69,7 @@ struct WsParams {
   int32_t chan_stride;         // H * out_pitch
   int32_t x_store_end;         // pixels of a row that are stored (W rounded up to 16)
   int64_t image_stride;        // c_out * chan_stride
+  int32_t dbg;                 // developer aid: bit 0 = epilogue does no work, bit 1 = issuer issues no MMAs
   uint16_t masks[kWsMaxGroups * kWsMaxChunks];
 };
 struct WsLaunch {
@@ -112,38 +121,205 @@ __device__ __forceinline__ void stg128(void* p, const uint4& v) {
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ uint32_t pack4_s8(int a, int b, int c, int d) {
+  return __byte_perm(__byte_perm(static_cast<uint32_t>(a), static_cast<uint32_t>(b), 0x0040),
+                     __byte_perm(static_cast<uint32_t>(c), static_cast<uint32_t>(d), 0x0040), 0x5410);
+}
+template <int B>
+__device__ __forceinline__ float i2f_s8_byte(uint32_t w) {     // float(int8 at byte B of w): one I2F with a byte selector
+  float f;
+  if constexpr (B == 0) asm("cvt.rn.f32.s8 %0, %1;" : "=f"(f) : "r"(w));
+  else asm("{\n\t.reg .b32 t;\n\tshr.u32 t, %1, %2;\n\tcvt.rn.f32.s8 %0, t;\n\t}" : "=f"(f) : "r"(w), "n"(8 * B));
+  return f;
+}
+
+// Accumulator range [lo, hi] of one channel inside which the requant does not clip: f = RN(float(acc)) * sf with
+// -128.5 <= f < 127.5 (the counting rule of the gather kernels' epilogue).  f is monotone in acc for sf > 0.
+__device__ __forceinline__ void ws_sat_bounds(float sf, int& lo, int& hi) {
+  if (!(sf > 0.f) || !(sf < 3.0e38f)) { lo = INT_MAX; hi = INT_MIN; return; }   // always take the exact count
+  long long a = 0, b = INT_MAX;
+  while (a < b) {
+    const long long m = (a + b + 1) >> 1;
+    if (__fmul_rn(__int2float_rn(static_cast<int>(m)), sf) < 127.5f) a = m; else b = m - 1;
+  }
+  hi = static_cast<int>(a);
+  a = INT_MIN; b = 0;
+  while (a < b) {
+    const long long m = (a + b) >> 1;
+    if (__fmul_rn(__int2float_rn(static_cast<int>(m)), sf) >= -128.5f) b = m; else a = m + 1;
+  }
+  lo = static_cast<int>(b);
+}
+
 // 16 pixels of one output channel: accumulators -> int8, optional residual add
-// (golden_models.cpp:465-490), optional ReLU on the int8 value, zero for pixels >= n_valid.
-template <bool RES, bool RES_FAST, bool SAT>
+// (golden_models.cpp:465-490), optional ReLU on the int8 value.  SAT: track the accumulator range of the chunk.
+template <int RESMODE, bool SAT>
 __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)[16], const uint32_t (&u)[16], int bias, float sf,
-                                          int relu_lo, int out_lo, const uint4& rbytes, int n_valid, uint32_t& sat) {
-  uint32_t packed[4] = {0u, 0u, 0u, 0u};
+                                          int relu_lo, int out_lo, const uint4& rbytes, int& amin, int& amax) {
+  uint32_t packed[4];
   const uint32_t rw[4] = {rbytes.x, rbytes.y, rbytes.z, rbytes.w};
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    int q[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int e = 4 * w + b;
+      const int acc = max(static_cast<int>(z[e] + u[e]) + bias, relu_lo);
+      if constexpr (SAT) {
+        amax = max(amax, acc);
+        amin = min(amin, acc);
+      }
+      const float f = __fmul_rn(__int2float_rn(acc), sf);
+      int r8 = cvt_sat_s8(f);
+      if constexpr (RESMODE != 0) {
+        const float rf = b == 0 ? i2f_s8_byte<0>(rw[w]) : b == 1 ? i2f_s8_byte<1>(rw[w]) : b == 2 ? i2f_s8_byte<2>(rw[w])
+                                                                                                     : i2f_s8_byte<3>(rw[w]);
+        const float a = __fmul_rn(__int2float_rn(r8), p.epi.res_scale_main);
+        const float r = __fmul_rn(rf, p.epi.res_scale_res);
+        const float sm = __fadd_rn(a, r);
+        float d;
+        if constexpr (RESMODE == 1) {      // exact for every (int8, int8) pair: verified on the host
+          const float q0 = __fmul_rn(sm, p.res_rcp);
+          const float er = __fmaf_rn(-q0, p.epi.res_scale_out, sm);
+          d = __fmaf_rn(er, p.res_rcp, q0);
+        } else {
+          d = __fdiv_rn(sm, p.epi.res_scale_out);
+        }
+        r8 = cvt_sat_s8(d);
+      }
+      q[b] = max(r8, out_lo);
+    }
+    packed[w] = pack4_s8(q[0], q[1], q[2], q[3]);
+  }
+  return make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+// exact count of clipped values among the first n_valid pixels of a chunk (rare path)
+__device__ __forceinline__ uint32_t ws_sat_recount(const uint32_t (&z)[16], const uint32_t (&u)[16], int bias, float sf, int relu_lo,
+                                                   int n_valid) {
+  uint32_t c = 0;
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     const int acc = max(static_cast<int>(z[e] + u[e]) + bias, relu_lo);
     const float f = __fmul_rn(__int2float_rn(acc), sf);
-    int r8 = cvt_sat_s8(f);
-    if constexpr (SAT) sat += (e < n_valid && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
-    if constexpr (RES) {
-      const int rv = static_cast<int>(static_cast<int8_t>((rw[e >> 2] >> (8 * (e & 3))) & 0xffu));
-      const float a = __fmul_rn(__int2float_rn(r8), p.epi.res_scale_main);
-      const float r = __fmul_rn(__int2float_rn(rv), p.epi.res_scale_res);
-      const float s = __fadd_rn(a, r);
-      float d;
-      if constexpr (RES_FAST) {
-        const float q0 = __fmul_rn(s, p.res_rcp);
-        const float er = __fmaf_rn(-q0, p.epi.res_scale_out, s);
-        d = __fmaf_rn(er, p.res_rcp, q0);
-      } else {
-        d = __fdiv_rn(s, p.epi.res_scale_out);
-      }
-      r8 = cvt_sat_s8(d);
-    }
-    const int q = e < n_valid ? max(r8, out_lo) : 0;
-    packed[e >> 2] |= (static_cast<uint32_t>(q) & 0xffu) << (8 * (e & 3));
+    c += (e < n_valid && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
   }
-  return make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  return c;
+}
+
+struct WsChunk {           // one 16-pixel chunk of this thread's channel
+  int p0;                  // first pixel (TMEM column) of the chunk inside the tile
+  int n_valid;             // pixels of the chunk inside the image row
+  bool live;               // warp-uniform: somebody stores it
+  bool lane_ok;            // this thread stores it
+  int64_t off;             // element offset of the chunk in the output / residual tensor
+};
+__device__ __forceinline__ void ws_chunk_load(const WsParams& p, uint32_t acc, const WsChunk& c, uint32_t (&z)[16], uint32_t (&u)[16]) {
+  tmem_ld16(acc + c.p0, z);
+  tmem_ld16(acc + (p.N - 2) + 1 + c.p0, u);
+}
+struct WsEpiConst {        // per-thread (= per-channel) constants of the epilogue
+  int bias, relu_lo, out_lo, lo_c, hi_c;
+  float sf;
+};
+template <int RESMODE, bool SAT>
+__device__ __forceinline__ void ws_chunk_finish(const WsParams& p, const WsChunk& c, const uint32_t (&z)[16], const uint32_t (&u)[16],
+                                                const uint4& rb, const WsEpiConst& k, uint32_t& sat) {
+  int amin = INT_MAX, amax = INT_MIN;
+  uint4 o = ws_epi16<RESMODE, SAT>(p, z, u, k.bias, k.sf, k.relu_lo, k.out_lo, rb, amin, amax);
+  if constexpr (SAT) {
+    if (c.lane_ok && (amax > k.hi_c || amin < k.lo_c)) sat += ws_sat_recount(z, u, k.bias, k.sf, k.relu_lo, c.n_valid);
+  }
+  if (c.n_valid < 16) {      // pixels beyond the image width are stored as zeros (the row padding stays zero)
+    uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int nv = c.n_valid - 4 * w;
+      ow[w] = nv >= 4 ? ow[w] : (nv <= 0 ? 0u : (ow[w] & ((1u << (8 * nv)) - 1u)));
+    }
+    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  if (c.lane_ok) stg128(p.out + c.off, o);
+}
+
+// this warp's k-th chunk of a tile: chunk pairs alternate between the two warp sets (32 contiguous bytes per thread)
+struct WsEpiGeom {
+  int n_c16, psh, half, y0;
+  bool ch_ok, t_ok;
+  int64_t obase;
+};
+__device__ __forceinline__ bool ws_chunk_at(const WsParams& p, const WsEpiGeom& g, int k, WsChunk& c) {
+  const int i = 2 * (g.half + 2 * (k >> 1)) + (k & 1);
+  if (i >= g.n_c16) return false;
+  c.p0 = i << 4;
+  const int r = c.p0 >> g.psh, x0 = c.p0 & (p.P - 1);
+  c.lane_ok = g.ch_ok && g.t_ok && (g.y0 + r) < p.H && x0 < p.x_store_end;
+  c.live = __any_sync(0xffffffffu, c.lane_ok);
+  c.off = g.obase + static_cast<int64_t>(g.y0 + r) * p.out_pitch + x0;
+  c.n_valid = max(0, min(16, p.W - x0));
+  return true;
+}
+
+// All chunks of one tile for this warp.  The TMEM loads of chunk k + 1 (and its residual bytes) are in flight while
+// chunk k is converted and stored.
+template <int RESMODE, bool SAT>
+__device__ __forceinline__ void ws_epi_tile(const WsParams& p, uint32_t acc, const WsEpiGeom& g, const WsEpiConst& kc, uint32_t& sat) {
+  uint32_t za[16], ua[16], zb[16], ub[16];
+  uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+  WsChunk ca, cb;
+  bool has_a = ws_chunk_at(p, g, 0, ca), has_b = false;
+  if (has_a) {
+    ws_chunk_load(p, acc, ca, za, ua);
+    if (RESMODE != 0 && ca.lane_ok) ra = ldg128(p.epi.residual + ca.off);
+  }
+  for (int k = 0; has_a; k += 2) {
+    tmem_ld_wait();
+    has_b = ws_chunk_at(p, g, k + 1, cb);
+    if (has_b) {
+      ws_chunk_load(p, acc, cb, zb, ub);
+      if (RESMODE != 0 && cb.lane_ok) rb = ldg128(p.epi.residual + cb.off);
+    }
+    if (ca.live) ws_chunk_finish<RESMODE, SAT>(p, ca, za, ua, ra, kc, sat);
+    if (!has_b) break;
+    tmem_ld_wait();
+    has_a = ws_chunk_at(p, g, k + 2, ca);
+    if (has_a) {
+      ws_chunk_load(p, acc, ca, za, ua);
+      if (RESMODE != 0 && ca.lane_ok) ra = ldg128(p.epi.residual + ca.off);
+    }
+    if (cb.live) ws_chunk_finish<RESMODE, SAT>(p, cb, zb, ub, rb, kc, sat);
+  }
+  tmem_ld_wait();
+}
+
+// The epilogue role of one warp for the whole launch (instantiated per variant: the variant is chosen once, outside the loop).
+struct WsEpiRole {
+  uint32_t item0, item_step, n_items, n_tiles, dual, sub, tmem_acc;   // tmem_acc: TMEM address of accumulator set 0, this warp's lanes
+  int co, half, n_c16, psh;
+  bool ch_ok, warp_has_ch;
+  uint64_t* acc_full;
+  uint64_t* acc_empty;
+};
+template <int RESMODE, bool SAT>
+__device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, int lane) {
+  uint32_t sat = 0, n = 0;
+  for (uint32_t it = r.item0; it < r.n_items; it += r.item_step, ++n) {
+    const uint32_t tt = r.dual ? 2u * it + r.sub : it;
+    const bool t_ok = tt < r.n_tiles;
+    const uint32_t tc = t_ok ? tt : r.n_tiles - 1u;
+    const uint32_t img = fdiv(tc, p.d_tpi);
+    const uint32_t ab = n & 1u;
+    WsEpiGeom eg;
+    eg.n_c16 = r.n_c16; eg.psh = r.psh; eg.half = r.half; eg.ch_ok = r.ch_ok; eg.t_ok = t_ok;
+    eg.y0 = static_cast<int>(tc - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
+    eg.obase = static_cast<int64_t>(img) * p.image_stride + static_cast<int64_t>(r.co) * p.chan_stride;
+    mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
+    tc_fence_after();
+    if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_tile<RESMODE, SAT>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, sat);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&r.acc_empty[ab]);
+  }
+  return sat;
 }
 
 __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_constant__ WsLaunch L) {
@@ -167,12 +343,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const uint32_t G = static_cast<uint32_t>(p.n_groups);
   const uint32_t g = blockIdx.x % G;                               // channel group of this CTA (weights stay put)
-  const uint32_t tile0 = blockIdx.x / G, tile_step = gridDim.x / G;
+  const uint32_t item0 = blockIdx.x / G, item_step = gridDim.x / G;
   const uint32_t n_tiles = static_cast<uint32_t>(p.n_tiles);
   const uint32_t n_chunks = static_cast<uint32_t>(p.n_chunks);
+  // dual: <= 64 output channels.  An item is a PAIR of pixel tiles; each is an M = 64 accumulator that occupies
+  // 16 lanes of every TMEM lane quadrant (tile s at lanes 16 s .. 16 s + 15): all 128 lanes carry results.
+  const uint32_t dual = static_cast<uint32_t>(p.dual);
+  const uint32_t n_items = dual ? (n_tiles + 1u) >> 1 : n_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWsMaxASlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kWsMaxASlots; ++s) { mbar_init(&a_full[s], kWsLoadThreads); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kWsMaxChunks; ++s) mbar_init(&w_full[s], 1);
     for (int s = 0; s < kWsMaxWSlots; ++s) mbar_init(&w_empty[s], 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kWsEpiWarps); }
@@ -191,64 +371,44 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     // =================================================================== epilogue: thread = output channel
     const int q = warp & 3, half = warp >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const int co = static_cast<int>(g) * kWsCo + q * 32 + lane;
+    const uint32_t sub = dual ? static_cast<uint32_t>(lane >> 4) : 0u;          // which tile of the pair
+    const int co = dual ? q * 16 + (lane & 15) : static_cast<int>(g) * kWsCo + q * 32 + lane;
     const bool ch_ok = co < p.c_out;
     const float sf = ch_ok ? p.epi.chan_scale[co] : 0.f;
     const int bias = (ch_ok && p.epi.bias) ? p.epi.bias[co] : 0;
-    const int relu_lo = (p.epi.flags & ACCEL_RELU) ? 0 : INT_MIN;
-    const int out_lo = (p.epi.flags & ACCEL_RELU_OUT) ? 0 : -128;
     const bool sat_on = p.epi.sat_count != nullptr;
+    WsEpiConst kc;
+    kc.bias = bias; kc.sf = sf;
+    kc.relu_lo = (p.epi.flags & ACCEL_RELU) ? 0 : INT_MIN;
+    kc.out_lo = (p.epi.flags & ACCEL_RELU_OUT) ? 0 : -128;
+    kc.lo_c = INT_MIN; kc.hi_c = INT_MAX;
+    if (sat_on && ch_ok) ws_sat_bounds(sf, kc.lo_c, kc.hi_c);
     const int resmode = !p.epi.residual ? 0 : (p.res_fast ? 1 : 2);
-    const int n_c16 = p.N >> 4;                       // 16-pixel chunks per tile
-    const int psh = p.P == 64 ? 6 : (p.P == 32 ? 5 : 4);
-    const bool warp_has_ch = static_cast<int>(g) * kWsCo + q * 32 < p.c_out;
-    uint32_t sat = 0, n = 0;
-    for (uint32_t tt = tile0; tt < n_tiles; tt += tile_step, ++n) {
-      const uint32_t img = fdiv(tt, p.d_tpi);
-      const int y0 = static_cast<int>(tt - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
-      const uint32_t ab = n & 1u;
-      const uint32_t acc = tmem_base + lane_base + ab * kWsAccCols;
-      const int64_t obase = static_cast<int64_t>(img) * p.image_stride + static_cast<int64_t>(co) * p.chan_stride;
-      mbar_wait(&acc_full[ab], (n >> 1) & 1u);
-      tc_fence_after();
-      // chunk pairs alternate between the two warp sets: every thread stores 32 contiguous bytes
-      for (int i = 0; i < n_c16 && warp_has_ch; ++i) {
-        if (((i >> 1) & 1) != half) continue;
-        const int p0 = i << 4;
-        const int r = p0 >> psh, x0 = p0 & (p.P - 1);
-        const int y = y0 + r;
-        if (y >= p.H || x0 >= p.x_store_end) continue;     // warp-uniform
-        uint32_t z[16], u[16];
-        tmem_ld16(acc + p0, z);
-        tmem_ld16(acc + (p.N - 2) + 1 + p0, u);
-        const int64_t off = obase + static_cast<int64_t>(y) * p.out_pitch + x0;
-        uint4 rb = make_uint4(0u, 0u, 0u, 0u);
-        if (resmode && ch_ok) rb = ldg128(p.epi.residual + off);
-        tmem_ld_wait();
-        const int n_valid = min(16, p.W - x0);
-        uint4 o;
-        switch (resmode * 2 + (sat_on ? 1 : 0)) {
-          case 0: o = ws_epi16<false, false, false>(p, z, u, bias, sf, relu_lo, out_lo, rb, n_valid, sat); break;
-          case 1: o = ws_epi16<false, false, true>(p, z, u, bias, sf, relu_lo, out_lo, rb, n_valid, sat); break;
-          case 2: o = ws_epi16<true, true, false>(p, z, u, bias, sf, relu_lo, out_lo, rb, n_valid, sat); break;
-          case 3: o = ws_epi16<true, true, true>(p, z, u, bias, sf, relu_lo, out_lo, rb, n_valid, sat); break;
-          case 4: o = ws_epi16<true, false, false>(p, z, u, bias, sf, relu_lo, out_lo, rb, n_valid, sat); break;
-          default: o = ws_epi16<true, false, true>(p, z, u, bias, sf, relu_lo, out_lo, rb, n_valid, sat); break;
-        }
-        if (ch_ok) stg128(p.out + off, o);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+    const int variant = resmode * 2 + (sat_on ? 1 : 0);
+    WsEpiRole er;
+    er.item0 = item0; er.item_step = item_step; er.n_items = n_items; er.n_tiles = n_tiles; er.dual = dual; er.sub = sub;
+    er.tmem_acc = tmem_base + lane_base;
+    er.co = co; er.half = half; er.n_c16 = p.N >> 4; er.psh = p.P == 64 ? 6 : (p.P == 32 ? 5 : 4);
+    er.ch_ok = ch_ok;
+    er.warp_has_ch = dual ? (q * 16 < p.c_out) : (static_cast<int>(g) * kWsCo + q * 32 < p.c_out);
+    er.acc_full = acc_full; er.acc_empty = acc_empty;
+    uint32_t sat;
+    switch (variant) {
+      case 0: sat = ws_epi_loop<0, false>(p, er, kc, lane); break;
+      case 1: sat = ws_epi_loop<0, true>(p, er, kc, lane); break;
+      case 2: sat = ws_epi_loop<1, false>(p, er, kc, lane); break;
+      case 3: sat = ws_epi_loop<1, true>(p, er, kc, lane); break;
+      case 4: sat = ws_epi_loop<2, false>(p, er, kc, lane); break;
+      default: sat = ws_epi_loop<2, true>(p, er, kc, lane); break;
     }
     if (sat_on) {
-      const uint32_t wsum = __reduce_add_sync(0xffffffffu, ch_ok ? sat : 0u);
+      const uint32_t wsum = __reduce_add_sync(0xffffffffu, sat);
       if (lane == 0 && wsum) atomicAdd(p.epi.sat_count, static_cast<unsigned long long>(wsum));
     }
   } else if (warp == kWsWarpIssue) {
     // =================================================================== MMA issuer
     if (elect_one()) {
-      const uint32_t idesc = idesc_i8_bmn(kWsCo, static_cast<uint32_t>(p.N));
+      const uint32_t idesc = idesc_i8_bmn(dual ? 64u : static_cast<uint32_t>(kWsCo), static_cast<uint32_t>(p.N));
       const uint64_t adesc0 = smem_desc_kmajor(0, 128, 256);
       const uint64_t bdesc0 = smem_desc_any(0, p.b_lbo, p.b_sbo, p.b_layout);
       const uint32_t a_hi = static_cast<uint32_t>(adesc0 >> 32), b_hi = static_cast<uint32_t>(bdesc0 >> 32);
@@ -257,48 +417,50 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       const uint32_t row16 = p.row_stride >> 4;
       const uint32_t u_off = static_cast<uint32_t>(p.N - 2);
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0;
-      for (uint32_t tt = tile0; tt < n_tiles; tt += tile_step, ++n) {
+      for (uint32_t it = item0; it < n_items; it += item_step, ++n) {
         const uint32_t ab = n & 1u;
         mbar_wait(&acc_empty[ab], ((n >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t z1 = tmem_base + ab * kWsAccCols;
-        uint32_t z_on = 0u, u_on = 0u;                // first MMA into Z1 / U overwrites, the rest accumulate
-        for (uint32_t j = 0; j < n_chunks; ++j) {
-          uint32_t wslot;
-          if (p.w_resident) {
-            wslot = j;
-            if (n == 0) mbar_wait(&w_full[j], 0u);
-          } else {
-            wslot = ws;
-            mbar_wait(&w_full[ws], wph);
-          }
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t mask = p.masks[g * kWsMaxChunks + j];
-          const uint32_t wl = a_lo0 | (((w_addr + wslot * kWsChunkBytes) >> 4) & 0x3FFFu);
-          const uint32_t xl = b_lo0 | (((a_addr + as * static_cast<uint32_t>(p.a_stage_bytes)) >> 4) & 0x3FFFu);
+        const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
+        for (uint32_t sub = 0; sub < n_sub; ++sub) {
+          const uint32_t z1 = tmem_base + ab * kWsAccCols + ((sub * 16u) << 16);
+          uint32_t z_on = 0u, u_on = 0u;                // first MMA into Z1 / U overwrites, the rest accumulate
+          for (uint32_t j = 0; j < n_chunks; ++j) {
+            uint32_t wslot;
+            if (p.w_resident) {
+              wslot = j;
+              if (n == 0 && sub == 0) mbar_wait(&w_full[j], 0u);
+            } else {
+              wslot = ws;
+              mbar_wait(&w_full[ws], wph);
+            }
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            const uint32_t mask = (p.dbg & 2) ? 0u : p.masks[g * kWsMaxChunks + j];
+            const uint32_t wl = a_lo0 | (((w_addr + wslot * kWsChunkBytes) >> 4) & 0x3FFFu);
+            const uint32_t xl = b_lo0 | (((a_addr + as * static_cast<uint32_t>(p.a_stage_bytes)) >> 4) & 0x3FFFu);
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (xl + kh * row16);
-            // order kw = 1, 2, 0: the first U-type MMA of a tile is the unshifted one (covers U's first columns)
-            if (mask & (1u << (kh * 3 + 1))) {
-              mma_i8_ss(z1, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 1) * (kWsTapBytes >> 4)), bd, idesc, z_on);
-              z_on = 1u;
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (xl + kh * row16);
+              // order kw = 1, 0, 2 (chunk 0 issues all nine taps): Z1's first MMA zeroes [0, N), the first kw = 0 MMA
+              // zeroes U + 2 + [0, N), and kw = 2 accumulates into U + [0, N) whose first two columns alias Z1's tail
+              if (mask & (1u << (kh * 3 + 1))) {
+                mma_i8_ss(z1, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 1) * (kWsTapBytes >> 4)), bd, idesc, z_on);
+                z_on = 1u;
+              }
+              if (mask & (1u << (kh * 3 + 0))) {
+                mma_i8_ss(z1 + u_off + 2, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 0) * (kWsTapBytes >> 4)), bd, idesc, u_on);
+                u_on = 1u;
+              }
+              if (mask & (1u << (kh * 3 + 2)))
+                mma_i8_ss(z1 + u_off, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 2) * (kWsTapBytes >> 4)), bd, idesc, 1u);
             }
-            if (mask & (1u << (kh * 3 + 2))) {
-              mma_i8_ss(z1 + u_off, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 2) * (kWsTapBytes >> 4)), bd, idesc, u_on);
-              u_on = 1u;
+            mma_commit(&a_empty[as]);
+            if (++as == static_cast<uint32_t>(p.a_slots)) { as = 0; aph ^= 1u; }
+            if (!p.w_resident) {
+              mma_commit(&w_empty[ws]);
+              if (++ws == static_cast<uint32_t>(p.w_slots)) { ws = 0; wph ^= 1u; }
             }
-            if (mask & (1u << (kh * 3 + 0))) {
-              mma_i8_ss(z1 + u_off + 2, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 0) * (kWsTapBytes >> 4)), bd, idesc, u_on);
-              u_on = 1u;
-            }
-          }
-          mma_commit(&a_empty[as]);
-          if (++as == static_cast<uint32_t>(p.a_slots)) { as = 0; aph ^= 1u; }
-          if (!p.w_resident) {
-            mma_commit(&w_empty[ws]);
-            if (++ws == static_cast<uint32_t>(p.w_slots)) { ws = 0; wph ^= 1u; }
           }
         }
         mma_commit(&acc_full[ab]);
@@ -306,38 +468,92 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     }
     __syncwarp();
     tc_fence_before();
-  } else {
-    // =================================================================== loader: weights (bulk) + activation tiles (TMA)
-    if (elect_one()) {
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0;
-      const uint8_t* wsrc = p.wblob + static_cast<size_t>(g) * n_chunks * kWsChunkBytes;
-      for (uint32_t tt = tile0; tt < n_tiles; tt += tile_step, ++n) {
+  } else if (warp >= kWsWarpLoad) {
+    // =================================================================== loaders: activation tiles by LDGSTS
+    // A staged tile is [R+2 input rows][32 channels][P pixels] with the 8-channel x P-byte swizzle atoms the B descriptor
+    // names.  TMA tensor tiles deliver exactly this layout too, but their rows are 16-64 bytes and the TMA unit retires
+    // about one row per 4 cycles (measured: 685 cycles per 8 KB stage); 16-byte LDGSTS copies issued by two warps are
+    // several times faster and zero-fill the padding just the same.
+    const int lt = static_cast<int>(threadIdx.x) - kWsWarpLoad * 32;           // 0..191
+    const int x16s = p.P >> 4, rows = p.R + 2;
+    const int n_ops = kWsCk * rows * x16s;
+    uint32_t soff[kWsLoadOps];
+    int32_t goff[kWsLoadOps], yrow[kWsLoadOps], nbytes[kWsLoadOps];
+#pragma unroll
+    for (int k = 0; k < kWsLoadOps; ++k) {
+      const int o = lt + kWsLoadThreads * k;
+      const int xq = o % x16s, y = (o / x16s) % rows, c = o / (x16s * rows);
+      uint32_t so = static_cast<uint32_t>(y) * p.row_stride + static_cast<uint32_t>(c * p.P + xq * 16);
+      if (p.b_layout == 4u) so ^= ((so >> 7) & 3u) << 4;           // 64-byte swizzle
+      else if (p.b_layout == 6u) so ^= ((so >> 7) & 1u) << 4;      // 32-byte swizzle
+      soff[k] = so;
+      goff[k] = (c * p.H + y) * p.in_pitch + xq * 16;       // + (y0 - 1) * pitch >= 0 whenever the row is inside the image
+      yrow[k] = y;
+      nbytes[k] = o < n_ops ? max(0, min(16, p.W - xq * 16)) : -1;
+    }
+    uint32_t as = 0, aph = 0;
+    const int64_t chunk_stride = static_cast<int64_t>(kWsCk) * p.H * p.in_pitch;
+    for (uint32_t it = item0; it < n_items; it += item_step) {
+      const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
+      for (uint32_t sub = 0; sub < n_sub; ++sub) {
+        const uint32_t tt = dual ? 2u * it + sub : it;
         const uint32_t img = fdiv(tt, p.d_tpi);
         const int y0 = static_cast<int>(tt - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
-        for (uint32_t j = 0; j < n_chunks; ++j) {
-          if (!p.w_resident || n == 0) {
-            uint32_t wslot;
-            if (p.w_resident) {
-              wslot = j;
-            } else {
-              wslot = ws;
-              mbar_wait(&w_empty[ws], wph ^ 1u);
-              if (++ws == static_cast<uint32_t>(p.w_slots)) { ws = 0; wph ^= 1u; }
-            }
-            uint64_t* bar = p.w_resident ? &w_full[j] : &w_full[wslot];
-            mbar_arrive_expect_tx(bar, kWsChunkBytes);
-            const uint8_t* src = wsrc + static_cast<size_t>(j) * kWsChunkBytes;
-            uint8_t* dst = smem + kWsSmemBar + wslot * kWsChunkBytes;
+        // per tile: which of this thread's copies read an input row inside the image (the others zero-fill: 0 bytes
+        // from offset 0), so that the per-stage loop is one LDGSTS and one address add per copy
+        uint32_t go[kWsLoadOps];
+        int nb[kWsLoadOps];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) bulk_g2s(dst + i * (kWsChunkBytes / 3), src + i * (kWsChunkBytes / 3), kWsChunkBytes / 3, bar);
-          }
+        for (int k = 0; k < kWsLoadOps; ++k) {
+          const int yy = y0 - 1 + yrow[k];
+          const bool ok = yy >= 0 && yy < p.H && nbytes[k] > 0;
+          nb[k] = ok ? nbytes[k] : min(nbytes[k], 0);
+          go[k] = ok ? static_cast<uint32_t>(goff[k] + (y0 - 1) * p.in_pitch) : 0u;
+        }
+        const int8_t* src0 = p.x + static_cast<int64_t>(img) * p.C * p.H * p.in_pitch;
+        for (uint32_t j = 0; j < n_chunks; ++j) {
           mbar_wait(&a_empty[as], aph ^ 1u);
-          mbar_arrive_expect_tx(&a_full[as], static_cast<uint32_t>(p.a_box_bytes));
-          tma_load_4d(a_addr + as * static_cast<uint32_t>(p.a_stage_bytes), &L.tmap, 0, static_cast<int>(j * kWsCk), y0 - 1,
-                      static_cast<int>(img), &a_full[as]);
+          const uint32_t dst0 = a_addr + as * static_cast<uint32_t>(p.a_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < kWsLoadOps; ++k)
+            if (nb[k] >= 0) cp_async16_zfill_s(dst0 + soff[k], src0 + go[k], nb[k]);
+          src0 += chunk_stride;
+          // arrives once this thread's copies have landed; like CUTLASS's sm100 cp.async mainloop, the consumer's
+          // mbarrier wait is the only synchronisation between these copies and tcgen05.mma (a fence.proxy.async
+          // per stage measured ~1000 cycles on either side)
+          cp_async_mbar_arrive(&a_full[as]);
           if (++as == static_cast<uint32_t>(p.a_slots)) { as = 0; aph ^= 1u; }
         }
       }
+    }
+  }
+  else {
+    // =================================================================== weight loader (bulk copies)
+    if (elect_one()) {
+      uint32_t ws = 0, wph = 0;
+      const uint8_t* wsrc = p.wblob + static_cast<size_t>(g) * n_chunks * kWsChunkBytes;
+      const uint32_t my_items = item0 < n_items ? (n_items - item0 + item_step - 1) / item_step : 0u;
+      uint32_t passes = 0;                       // resident: one pass over the chunks; streamed: one per pixel tile
+      if (p.w_resident) passes = my_items ? 1u : 0u;
+      else
+        for (uint32_t it = item0; it < n_items; it += item_step) passes += (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
+      for (uint32_t ps = 0; ps < passes; ++ps)
+        for (uint32_t j = 0; j < n_chunks; ++j) {
+          uint32_t wslot;
+          if (p.w_resident) {
+            wslot = j;
+          } else {
+            wslot = ws;
+            mbar_wait(&w_empty[ws], wph ^ 1u);
+            if (++ws == static_cast<uint32_t>(p.w_slots)) { ws = 0; wph ^= 1u; }
+          }
+          uint64_t* bar = &w_full[wslot];
+          mbar_arrive_expect_tx(bar, kWsChunkBytes);
+          const uint8_t* src = wsrc + static_cast<size_t>(j) * kWsChunkBytes;
+          uint8_t* dst = smem + kWsSmemBar + wslot * kWsChunkBytes;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) bulk_g2s(dst + i * (kWsChunkBytes / 3), src + i * (kWsChunkBytes / 3), kWsChunkBytes / 3, bar);
+        }
     }
     __syncwarp();
   }
