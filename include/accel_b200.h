@@ -135,9 +135,19 @@ ACCEL_API int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64
 ACCEL_API int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const accel_conv_geom* geom,
                       const accel_epilogue* epi, void* out, const accel_out_layout* layout, accel_stream_t stream);
 
+/* --- a 3x3 / stride 2 / pad 1 convolution and the 1x1 / stride 2 / pad 0 convolution of the SAME input in one call: the
+ * first convolution of a ResNet stage and its downsample branch (two run_layer calls in the reference,
+ * resnet_inference.cpp:61-127; the downsample convolutions are named in export_resnet18_bsr.py:72,79,86).  Both outputs
+ * share `layout`.  When both plans carry a weight-stationary layout (below) the 1x1 convolution rides along as one more
+ * tap of the staged activation tiles; otherwise this is the two accel_conv_bsr_i8 calls in sequence. */
+ACCEL_API int accel_conv_bsr_i8_dual(const accel_plan* plan, const accel_plan* plan_ds, const int8_t* input_nchw,
+                           const accel_conv_geom* geom, const accel_epilogue* epi, void* out, const accel_epilogue* epi_ds,
+                           void* out_ds, const accel_out_layout* layout, accel_stream_t stream);
+
 /* --- weight-stationary re-layout for 3x3 stride-1 pad-1 convolutions (conv2d_int8_im2col, golden_models.cpp:883-933,
  * K order (c_in, kh, kw) of im2col_int8 :801-842).  Optional: when a plan has been prepared for (c_in, c_out) and the
- * tensors of an accel_conv_bsr_i8 call allow it (16-byte aligned rows, int8 output, width <= 62), that call runs the
+ * tensors of an accel_conv_bsr_i8 call allow it (16-byte aligned rows, int8 output, width <= 62; ksize 3 with stride 1
+ * or 2, and ksize 1 as the second plan of accel_conv_bsr_i8_dual), that call runs the
  * kernel of csrc/conv_ws.cuh: the stored blocks are scattered once into 128x32 K-major weight tiles per
  * (channel group, 32-channel chunk, tap) and the activation tile is fed to the tensor core straight from TMA.
  * conv_ws_bytes reports the workspace for that layout (0 = no such path for this geometry); conv_ws_prepare fills it

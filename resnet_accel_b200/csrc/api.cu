@@ -269,7 +269,7 @@ int launch_tc(const accel::Plan* P, accel::TcParams& prm, int mode, int smem, cu
 // weight-stationary convolution state of a plan (conv_ws.cuh): one prepared geometry
 struct WsState {
   bool ready = false;
-  int32_t c_in = 0, c_out = 0, n_chunks = 0, n_groups = 0;
+  int32_t c_in = 0, c_out = 0, taps = 0, n_chunks = 0, n_groups = 0;
   const uint8_t* blob = nullptr;
   uint16_t masks[accel::kWsMaxGroups * accel::kWsMaxChunks] = {};
 };
@@ -283,40 +283,54 @@ struct accel_plan {
 namespace {
 
 bool ws_geometry_ok(const accel_plan* plan, int32_t c_in, int32_t c_out, int32_t ksize) {
-  if (ksize != 3 || c_in <= 0 || c_in % accel::kWsCk != 0 || c_in / accel::kWsCk > accel::kWsMaxChunks) return false;
+  if ((ksize != 3 && ksize != 1) || c_in <= 0 || c_in % accel::kWsCk != 0 || c_in / accel::kWsCk > accel::kWsMaxChunks) return false;
   if (c_out <= 0 || c_out > plan->p.nbr * accel::kBlock || (c_out + accel::kWsCo - 1) / accel::kWsCo > accel::kWsMaxGroups)
     return false;
-  return (static_cast<int64_t>(c_in) * 9 + accel::kBlock - 1) / accel::kBlock <= plan->p.nbc;
+  return (static_cast<int64_t>(c_in) * ksize * ksize + accel::kBlock - 1) / accel::kBlock <= plan->p.nbc;
 }
-size_t ws_blob_bytes(int32_t c_in, int32_t c_out) {
-  return static_cast<size_t>((c_out + accel::kWsCo - 1) / accel::kWsCo) * (c_in / accel::kWsCk) * accel::kWsChunkBytes;
+size_t ws_blob_bytes(int32_t c_in, int32_t c_out, int32_t taps) {
+  return static_cast<size_t>((c_out + accel::kWsCo - 1) / accel::kWsCo) * (c_in / accel::kWsCk) * taps * accel::kWsTapBytes;
 }
 
 constexpr int kWsNotApplicable = 1;
 
 // Route a convolution to conv_ws_kernel when geometry, layouts and alignment allow; kWsNotApplicable otherwise.
+// 3x3 pad 1, stride 1 or 2.  plan_ds / epi_ds / out_ds (stride 2 only, may be null): the 1x1 / stride 2 / pad 0 convolution of
+// the same input (the ResNet downsample), fused as one more tap of the same staged tiles.
 int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_geom* g, const accel_epilogue* epi, void* out,
-                const accel_out_layout* lay, cudaStream_t st) {
+                const accel_out_layout* lay, cudaStream_t st, const accel_plan* plan_ds = nullptr,
+                const accel_epilogue* epi_ds = nullptr, void* out_ds = nullptr) {
   const WsState& W = plan->ws;
-  if (g_no_ws || !W.ready || g->ksize != 3 || g->stride != 1 || g->pad != 1 || g->batch <= 0) return kWsNotApplicable;
+  if (g_no_ws || !W.ready || W.taps != 9 || g->ksize != 3 || (g->stride != 1 && g->stride != 2) || g->pad != 1 || g->batch <= 0)
+    return kWsNotApplicable;
   if (g->c_in != W.c_in || epi->n_channels != W.c_out) return kWsNotApplicable;
   if (!(epi->flags & ACCEL_OUT_I8) || epi->chan_absmax) return kWsNotApplicable;
+  const int stride = g->stride;
+  if (stride == 2 && ((g->h | g->w) & 1 || epi->residual)) return kWsNotApplicable;
+  if (plan_ds) {
+    const WsState& D = plan_ds->ws;
+    if (stride != 2 || !D.ready || D.taps != 1 || D.c_in != W.c_in || D.c_out != W.c_out || !epi_ds || !out_ds) return kWsNotApplicable;
+    if (epi_ds->n_channels != W.c_out || !(epi_ds->flags & ACCEL_OUT_I8) || epi_ds->chan_absmax || epi_ds->residual ||
+        !epi_ds->chan_scale || (reinterpret_cast<uintptr_t>(out_ds) & 15))
+      return kWsNotApplicable;
+  }
   const int Wd = g->w, H = g->h;
+  const int Ho = stride == 2 ? H / 2 : H, Wo = stride == 2 ? Wd / 2 : Wd;
   const int P = Wd <= 14 ? 16 : (Wd <= 30 ? 32 : (Wd <= 62 ? 64 : 0));     // two padding pixels end every staged row
   if (!P) return kWsNotApplicable;
   const int64_t in_pitch = g->in_row_pitch > 0 ? g->in_row_pitch : g->w;
   if ((in_pitch & 15) || (reinterpret_cast<uintptr_t>(input) & 15)) return kWsNotApplicable;
   // output (and residual): NCHW, 16-byte aligned rows that can take whole 16-pixel stores
-  const int w16 = (Wd + 15) / 16 * 16;
+  const int w16 = stride == 2 ? (Wo + 7) / 8 * 8 : (Wo + 15) / 16 * 16;     // whole 16-byte (stride 2: 8-byte) stores
   int64_t out_pitch;
   if (lay->row_len == 0) {
-    out_pitch = Wd;
-    if (Wd % 16 || lay->chan_stride != static_cast<int64_t>(H) * Wd) return kWsNotApplicable;
+    out_pitch = Wo;
+    if (Wo % 16 || lay->chan_stride != static_cast<int64_t>(Ho) * Wo) return kWsNotApplicable;
   } else {
     out_pitch = lay->row_pitch;
-    if (lay->row_len != Wd || lay->chan_stride != static_cast<int64_t>(H) * out_pitch) return kWsNotApplicable;
+    if (lay->row_len != Wo || lay->chan_stride != static_cast<int64_t>(Ho) * out_pitch) return kWsNotApplicable;
   }
-  if (lay->row_stride != 1 || out_pitch < w16 || (out_pitch & 15) || lay->rows_per_image != static_cast<int64_t>(H) * Wd ||
+  if (lay->row_stride != 1 || out_pitch < w16 || (out_pitch & 15) || lay->rows_per_image != static_cast<int64_t>(Ho) * Wo ||
       lay->image_stride != lay->chan_stride * W.c_out)
     return kWsNotApplicable;
   if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(epi->residual) & 15)) return kWsNotApplicable;
@@ -330,21 +344,25 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   std::memset(&p, 0, sizeof(p));
   p.C = g->c_in; p.H = H; p.W = Wd; p.B = g->batch; p.P = P;
   int best_r = 1, best_cost = INT_MAX;
-  for (int r = 1; r <= 128 / P; ++r) {
-    const int cost = (H + r - 1) / r * r;
+  for (int r = 1; r <= (stride == 2 ? 64 : 128) / P; ++r) {       // stride 2: N <= 64 (three accumulators per set)
+    const int cost = (Ho + r - 1) / r * r;
     if (cost <= best_cost) { best_cost = cost; best_r = r; }
   }
   p.R = best_r; p.N = p.R * P;
+  p.stride = stride; p.Ho = Ho; p.Wo = Wo;
+  p.rows_in = stride == 2 ? 2 * p.R + 1 : p.R + 2;
+  p.has_ds = plan_ds ? 1 : 0;
+  p.w_chunk_bytes = accel::kWsChunkBytes + (plan_ds ? accel::kWsTapBytes : 0);
   p.n_chunks = W.n_chunks; p.n_groups = W.n_groups; p.c_out = W.c_out;
-  p.tiles_per_image = (H + p.R - 1) / p.R;
+  p.tiles_per_image = (Ho + p.R - 1) / p.R;
   const int64_t n_tiles = static_cast<int64_t>(g->batch) * p.tiles_per_image;
   if (n_tiles > INT_MAX) return kWsNotApplicable;
   p.n_tiles = static_cast<int32_t>(n_tiles);
   p.w_resident = W.n_chunks <= accel::kWsMaxWSlots ? 1 : 0;
   p.w_slots = p.w_resident ? W.n_chunks : accel::kWsMaxWSlots;
-  p.a_box_bytes = accel::kWsCk * (p.R + 2) * P;
+  p.a_box_bytes = accel::kWsCk * p.rows_in * P;
   p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
-  const int fixed = 1024 /* alignment slack */ + accel::kWsSmemBar + p.w_slots * accel::kWsChunkBytes;
+  const int fixed = 1024 /* alignment slack */ + accel::kWsSmemBar + p.w_slots * p.w_chunk_bytes;
   int a_slots = (kSmemWs - fixed) / p.a_stage_bytes;
   if (a_slots > accel::kWsMaxASlots) a_slots = accel::kWsMaxASlots;
   if (a_slots < 3) return kWsNotApplicable;
@@ -353,8 +371,8 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   const uint32_t grp_stride = static_cast<uint32_t>(8 * P);        // bytes between 8-channel groups
   p.b_layout = P == 64 ? 4u : (P == 32 ? 6u : 0u);
   // swizzled: LBO = stride between pixel atoms (image rows), SBO = stride between 8-channel groups; unswizzled: swapped
-  p.b_lbo = p.b_layout ? p.row_stride : grp_stride;
-  p.b_sbo = p.b_layout ? grp_stride : p.row_stride;
+  p.b_lbo = p.b_layout ? p.row_stride * stride : grp_stride;     // stride 2: the window takes every second staged row
+  p.b_sbo = p.b_layout ? grp_stride : p.row_stride * stride;
   p.d_tpi = accel::make_fastdiv(static_cast<uint32_t>(p.tiles_per_image));
   p.wblob = W.blob;
   p.x = input; p.in_pitch = static_cast<int32_t>(in_pitch);
@@ -370,14 +388,13 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   p.image_stride = lay->image_stride;
   std::memcpy(p.masks, W.masks, sizeof(p.masks));
   p.dbg = g_dbg_flags;
-  const uint64_t dims[4] = {static_cast<uint64_t>(Wd), static_cast<uint64_t>(g->c_in), static_cast<uint64_t>(H),
-                            static_cast<uint64_t>(g->batch)};
-  const uint64_t strides[3] = {static_cast<uint64_t>(in_pitch) * H, static_cast<uint64_t>(in_pitch),
-                               static_cast<uint64_t>(in_pitch) * H * g->c_in};
-  const uint32_t box[4] = {static_cast<uint32_t>(P), static_cast<uint32_t>(accel::kWsCk), static_cast<uint32_t>(p.R + 2), 1u};
-  const CUtensorMapSwizzle sw = P == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (P == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
-  if (!encode_tmap(&L.tmap, input, 4, dims, strides, box, sw)) return kWsNotApplicable;
-  p.dual = W.c_out <= 64 ? 1 : 0;
+  p.dual = (W.c_out <= 64 && stride == 1) ? 1 : 0;
+  if (plan_ds) {
+    p.wblob2 = plan_ds->ws.blob;
+    p.epi2 = *epi_ds;
+    p.out2 = static_cast<int8_t*>(out_ds);
+    std::memcpy(p.masks2, plan_ds->ws.masks, sizeof(p.masks2));
+  }
   const int n_items = p.dual ? (p.n_tiles + 1) / 2 : p.n_tiles;
   int per_group = sm_count() / p.n_groups;
   if (per_group > n_items) per_group = n_items;
@@ -439,7 +456,7 @@ int accel_plan_conv_ws_bytes(const accel_plan* plan, int32_t c_in, int32_t c_out
   if (!plan || !bytes) return fail(ACCEL_INVALID_CONFIG, "null argument");
   *bytes = 0;
   if (!ws_geometry_ok(plan, c_in, c_out, ksize)) return ACCEL_OK;          // 0 bytes: this geometry has no such path
-  *bytes = ws_blob_bytes(c_in, c_out) + (static_cast<size_t>(plan->p.nnz) * 8 + 255) / 256 * 256;
+  *bytes = ws_blob_bytes(c_in, c_out, ksize * ksize) + (static_cast<size_t>(plan->p.nnz) * 8 + 255) / 256 * 256;
   return ACCEL_OK;
 }
 
@@ -447,7 +464,8 @@ int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32
                                void* workspace_dev, size_t workspace_bytes, accel_stream_t stream) {
   if (!plan || !workspace_dev) return fail(ACCEL_INVALID_CONFIG, "null plan / workspace");
   if (!ws_geometry_ok(plan, c_in, c_out, ksize)) return fail(ACCEL_INVALID_CONFIG, "geometry has no weight-stationary path");
-  const size_t blob = ws_blob_bytes(c_in, c_out);
+  const int32_t taps = ksize * ksize;
+  const size_t blob = ws_blob_bytes(c_in, c_out, taps);
   const int64_t nnz = plan->p.nnz;
   if (workspace_bytes < blob + static_cast<size_t>(nnz) * 8) return fail(ACCEL_MEMORY_ERROR, "workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace_dev) & 1023) return fail(ACCEL_MEMORY_ERROR, "workspace not 1024-byte aligned");
@@ -455,12 +473,12 @@ int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   WsState& W = plan->ws;
   W.ready = false;
-  W.c_in = c_in; W.c_out = c_out; W.n_chunks = c_in / accel::kWsCk; W.n_groups = (c_out + accel::kWsCo - 1) / accel::kWsCo;
+  W.c_in = c_in; W.c_out = c_out; W.taps = taps; W.n_chunks = c_in / accel::kWsCk; W.n_groups = (c_out + accel::kWsCo - 1) / accel::kWsCo;
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   CU(cudaMemsetAsync(ws, 0, blob, st));
   std::memset(W.masks, 0, sizeof(W.masks));
   std::vector<int32_t> blk_row(static_cast<size_t>(nnz));
-  const int32_t K = c_in * 9;
+  const int32_t K = c_in * taps;
   for (int32_t br = 0; br < plan->p.nbr; ++br)
     for (int32_t i = plan->row_ptr[br]; i < plan->row_ptr[br + 1]; ++i) {
       blk_row[i] = br;
@@ -468,19 +486,19 @@ int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32
       const int co_lo = br * accel::kBlock, co_hi = std::min(co_lo + accel::kBlock, c_out) - 1;
       if (co_hi < co_lo) continue;
       for (int k = bc * accel::kBlock; k < std::min((bc + 1) * accel::kBlock, K); ++k) {
-        const int c = k / 9, tap = k % 9, j = c / accel::kWsCk;
+        const int c = k / taps, tap = k % taps, j = c / accel::kWsCk;
         W.masks[(co_lo / accel::kWsCo) * accel::kWsMaxChunks + j] |= static_cast<uint16_t>(1u << tap);
         W.masks[(co_hi / accel::kWsCo) * accel::kWsMaxChunks + j] |= static_cast<uint16_t>(1u << tap);
       }
     }
   // the first chunk always issues all nine taps: they initialise the accumulators in a fixed order
-  for (int gi = 0; gi < W.n_groups; ++gi) W.masks[gi * accel::kWsMaxChunks] = 0x1ff;
+  for (int gi = 0; gi < W.n_groups; ++gi) W.masks[gi * accel::kWsMaxChunks] = static_cast<uint16_t>((1u << taps) - 1u);
   if (nnz > 0) {
     int32_t* d_row = reinterpret_cast<int32_t*>(ws + blob);
     int32_t* d_col = d_row + nnz;
     CU(cudaMemcpyAsync(d_row, blk_row.data(), static_cast<size_t>(nnz) * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_col, plan->col_idx.data(), static_cast<size_t>(nnz) * 4, cudaMemcpyHostToDevice, st));
-    accel::ws_scatter_kernel<<<static_cast<unsigned>(nnz), 64, 0, st>>>(blocks_dev, d_row, d_col, nnz, c_in, c_out, W.n_chunks, ws);
+    accel::ws_scatter_kernel<<<static_cast<unsigned>(nnz), 64, 0, st>>>(blocks_dev, d_row, d_col, nnz, c_in, c_out, W.n_chunks, taps, ws);
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(st));     // blk_row is pageable host memory
@@ -691,6 +709,29 @@ int accel_conv_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const ac
     }
   }
   return launch_tc(&plan->p, prm, accel::kModeDirect, accel::kSmemRing, st);
+}
+
+int accel_conv_bsr_i8_dual(const accel_plan* plan, const accel_plan* plan_ds, const int8_t* input_nchw,
+                           const accel_conv_geom* g, const accel_epilogue* epi, void* out, const accel_epilogue* epi_ds,
+                           void* out_ds, const accel_out_layout* layout, accel_stream_t stream) {
+  if (!plan || !plan_ds || !g || !epi || !epi_ds) return fail(ACCEL_INVALID_CONFIG, "null plan / geometry / epilogue");
+  if (!plan->p.uploaded || !plan_ds->p.uploaded) return fail(ACCEL_NOT_READY, "Weights not loaded");
+  if (g->ksize != 3 || g->stride != 2 || g->pad != 1)
+    return fail(ACCEL_INVALID_CONFIG, "the dual call is a 3x3 / stride 2 / pad 1 convolution plus the 1x1 / stride 2 one");
+  int rc = check_epilogue(epi, layout, out, plan->p.nbr * accel::kBlock);
+  if (rc) return rc;
+  rc = check_epilogue(epi_ds, layout, out_ds, plan_ds->p.nbr * accel::kBlock);
+  if (rc) return rc;
+  if (g->batch > 0 && input_nchw && g->c_in > 0 && g->h > 0 && g->w > 0) {
+    rc = try_conv_ws(plan, input_nchw, g, epi, out, layout, static_cast<cudaStream_t>(stream), plan_ds, epi_ds, out_ds);
+    if (rc != kWsNotApplicable) return rc;
+  }
+  // not fusable for these tensors: the two convolutions one after the other
+  rc = accel_conv_bsr_i8(plan, input_nchw, g, epi, out, layout, stream);
+  if (rc) return rc;
+  accel_conv_geom g1 = *g;
+  g1.ksize = 1; g1.pad = 0;
+  return accel_conv_bsr_i8(plan_ds, input_nchw, &g1, epi_ds, out_ds, layout, stream);
 }
 
 int accel_bsr_gemm_generic(const int8_t* act, int64_t M, int64_t K, int64_t lda, const int32_t* row_ptr,

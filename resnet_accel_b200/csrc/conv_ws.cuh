@@ -71,7 +71,17 @@ struct WsParams {
   int64_t image_stride;        // c_out * chan_stride
   int32_t dbg;                 // developer aid: bit 0 = epilogue does no work, bit 1 = issuer issues no MMAs
   uint16_t masks[kWsMaxGroups * kWsMaxChunks];
+  // stride-2 mode (3x3 / stride 2 / pad 1, optionally fused with the 1x1 / stride 2 convolution that reads the same input:
+  // the ResNet downsample).  Rows: the loader stages 2R+1 input rows and the B window of tap kh takes every second one.
+  // Columns: computed at full resolution, the epilogue keeps the even ones.  The 1x1 convolution is one more tap on the
+  // kh = 1 window, accumulated into V (columns [128, 128 + N), N <= 64) and written through its own epilogue.
+  int32_t stride, rows_in, Ho, Wo, w_chunk_bytes, has_ds;
+  const uint8_t* wblob2;       // [group][chunk][4096]
+  accel_epilogue epi2;
+  int8_t* out2;
+  uint16_t masks2[kWsMaxGroups * kWsMaxChunks];
 };
+constexpr uint32_t kWsVCol = 128;
 struct WsLaunch {
   alignas(64) CUtensorMap tmap;
   WsParams p;
@@ -96,17 +106,17 @@ __device__ __forceinline__ uint64_t smem_desc_any(uint32_t saddr, uint32_t lbo_b
 // blk_row[b] = block-row of stored block b; K index k = c * 9 + tap (golden_models.cpp:801-842).
 __global__ void ws_scatter_kernel(const int8_t* __restrict__ blocks, const int32_t* __restrict__ blk_row,
                                   const int32_t* __restrict__ col_idx, int64_t nnz, int32_t c_in, int32_t c_out, int32_t n_chunks,
-                                  uint8_t* __restrict__ blob) {
+                                  int32_t taps, uint8_t* __restrict__ blob) {
   const int64_t b = blockIdx.x;
   if (b >= nnz) return;
   const int br = blk_row[b], bc = col_idx[b];
   for (int i = threadIdx.x; i < kBlock * kBlock; i += blockDim.x) {
     const int h = i / kBlock, w = i - h * kBlock;
     const int co = br * kBlock + h, k = bc * kBlock + w;
-    if (co >= c_out || k >= c_in * 9) continue;
-    const int c = k / 9, tap = k - c * 9;
+    if (co >= c_out || k >= c_in * taps) continue;
+    const int c = k / taps, tap = k - c * taps;
     const int g = co / kWsCo, row = co - g * kWsCo, j = c / kWsCk, kk = c - j * kWsCk;
-    const size_t dst = (static_cast<size_t>(g * n_chunks + j) * 9 + tap) * kWsTapBytes + (row >> 3) * 256 + (kk >> 4) * 128 +
+    const size_t dst = (static_cast<size_t>(g * n_chunks + j) * taps + tap) * kWsTapBytes + (row >> 3) * 256 + (kk >> 4) * 128 +
                        (row & 7) * 16 + (kk & 15);
     blob[dst] = static_cast<uint8_t>(blocks[b * 196 + i]);
   }
@@ -259,36 +269,60 @@ __device__ __forceinline__ bool ws_chunk_at(const WsParams& p, const WsEpiGeom& 
   return true;
 }
 
-// All chunks of one tile for this warp.  The TMEM loads of chunk k + 1 (and its residual bytes) are in flight while
-// chunk k is converted and stored.
+// All chunks of one tile for this warp (at most kWsMaxMyChunks).  The residual bytes were requested before the tile's
+// accumulators were complete (ws_epi_prefetch); the TMEM loads of chunk k + 1 are in flight while chunk k is
+// converted and stored.
+constexpr int kWsMaxMyChunks = 4;          // N <= 128: 8 chunks of 16 pixels, split between the two warp sets
+template <int RESMODE>
+__device__ __forceinline__ void ws_epi_prefetch(const WsParams& p, const WsEpiGeom& g, uint4 (&rpre)[kWsMaxMyChunks]) {
+#pragma unroll
+  for (int k = 0; k < kWsMaxMyChunks; ++k) {
+    rpre[k] = make_uint4(0u, 0u, 0u, 0u);
+    if constexpr (RESMODE != 0) {
+      WsChunk c;
+      if (ws_chunk_at(p, g, k, c) && c.lane_ok) rpre[k] = ldg128(p.epi.residual + c.off);
+    }
+  }
+}
 template <int RESMODE, bool SAT>
-__device__ __forceinline__ void ws_epi_tile(const WsParams& p, uint32_t acc, const WsEpiGeom& g, const WsEpiConst& kc, uint32_t& sat) {
+__device__ __forceinline__ void ws_epi_tile(const WsParams& p, uint32_t acc, const WsEpiGeom& g, const WsEpiConst& kc,
+                                            const uint4 (&rpre)[kWsMaxMyChunks], uint32_t& sat) {
   uint32_t za[16], ua[16], zb[16], ub[16];
-  uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
   WsChunk ca, cb;
   bool has_a = ws_chunk_at(p, g, 0, ca), has_b = false;
-  if (has_a) {
-    ws_chunk_load(p, acc, ca, za, ua);
-    if (RESMODE != 0 && ca.lane_ok) ra = ldg128(p.epi.residual + ca.off);
-  }
-  for (int k = 0; has_a; k += 2) {
+  if (has_a) ws_chunk_load(p, acc, ca, za, ua);
+#pragma unroll
+  for (int k = 0; k < kWsMaxMyChunks; k += 2) {
+    if (!has_a) break;
     tmem_ld_wait();
     has_b = ws_chunk_at(p, g, k + 1, cb);
-    if (has_b) {
-      ws_chunk_load(p, acc, cb, zb, ub);
-      if (RESMODE != 0 && cb.lane_ok) rb = ldg128(p.epi.residual + cb.off);
-    }
-    if (ca.live) ws_chunk_finish<RESMODE, SAT>(p, ca, za, ua, ra, kc, sat);
+    if (has_b) ws_chunk_load(p, acc, cb, zb, ub);
+    if (ca.live) ws_chunk_finish<RESMODE, SAT>(p, ca, za, ua, rpre[k], kc, sat);
     if (!has_b) break;
     tmem_ld_wait();
-    has_a = ws_chunk_at(p, g, k + 2, ca);
-    if (has_a) {
-      ws_chunk_load(p, acc, ca, za, ua);
-      if (RESMODE != 0 && ca.lane_ok) ra = ldg128(p.epi.residual + ca.off);
-    }
-    if (cb.live) ws_chunk_finish<RESMODE, SAT>(p, cb, zb, ub, rb, kc, sat);
+    has_a = k + 2 < kWsMaxMyChunks && ws_chunk_at(p, g, k + 2, ca);
+    if (has_a) ws_chunk_load(p, acc, ca, za, ua);
+    if (cb.live) ws_chunk_finish<RESMODE, SAT>(p, cb, zb, ub, rpre[k + 1], kc, sat);
   }
   tmem_ld_wait();
+}
+
+// ---- stride-2 epilogue: 16 full-resolution pixels -> the 8 even ones -> 8 output bytes
+template <bool SAT>
+__device__ __forceinline__ uint2 ws_epi8_even(const uint32_t (&z)[16], const uint32_t* u, const WsEpiConst& k, int n_valid, bool lane_ok,
+                                              uint32_t& sat) {
+  int q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int acc = max(static_cast<int>(z[2 * e] + (u ? u[2 * e] : 0u)) + k.bias, k.relu_lo);
+    const float f = __fmul_rn(__int2float_rn(acc), k.sf);
+    if constexpr (SAT) sat += (lane_ok && e < n_valid && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
+    q[e] = e < n_valid ? max(static_cast<int>(cvt_sat_s8(f)), k.out_lo) : 0;
+  }
+  return make_uint2(pack4_s8(q[0], q[1], q[2], q[3]), pack4_s8(q[4], q[5], q[6], q[7]));
+}
+__device__ __forceinline__ void stg64(void* p, const uint2& v) {
+  asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
 // The epilogue role of one warp for the whole launch (instantiated per variant: the variant is chosen once, outside the loop).
@@ -312,9 +346,52 @@ __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRo
     eg.n_c16 = r.n_c16; eg.psh = r.psh; eg.half = r.half; eg.ch_ok = r.ch_ok; eg.t_ok = t_ok;
     eg.y0 = static_cast<int>(tc - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
     eg.obase = static_cast<int64_t>(img) * p.image_stride + static_cast<int64_t>(r.co) * p.chan_stride;
+    uint4 rpre[kWsMaxMyChunks];
+    if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_prefetch<RESMODE>(p, eg, rpre);      // residual bytes: before the MMAs are done
     mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
     tc_fence_after();
-    if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_tile<RESMODE, SAT>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, sat);
+    if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_tile<RESMODE, SAT>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, rpre, sat);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&r.acc_empty[ab]);
+  }
+  return sat;
+}
+
+template <bool SAT>
+__device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, const WsEpiConst& kc2,
+                                                   int lane) {
+  uint32_t sat = 0, n = 0;
+  for (uint32_t it = r.item0; it < r.n_items; it += r.item_step, ++n) {
+    const uint32_t img = fdiv(it, p.d_tpi);
+    const int y0 = static_cast<int>(it - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
+    const uint32_t ab = n & 1u;
+    const uint32_t acc = r.tmem_acc + ab * kWsAccCols;
+    const int64_t obase = static_cast<int64_t>(img) * p.image_stride + static_cast<int64_t>(r.co) * p.chan_stride;
+    mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
+    tc_fence_after();
+    if (r.warp_has_ch && !(p.dbg & 1)) {
+      for (int k = 0; k < kWsMaxMyChunks; ++k) {
+        const int i = 2 * (r.half + 2 * (k >> 1)) + (k & 1);
+        if (i >= r.n_c16) break;
+        const int p0 = i << 4;
+        const int row = p0 >> r.psh, x0 = (p0 & (p.P - 1)) >> 1;              // output column of the chunk's first pixel
+        if (y0 + row >= p.Ho || x0 >= p.x_store_end) continue;                // warp-uniform
+        uint32_t z[16], u[16], v[16];
+        tmem_ld16(acc + p0, z);
+        tmem_ld16(acc + (p.N - 2) + 1 + p0, u);
+        if (p.has_ds) tmem_ld16(acc + kWsVCol + p0, v);
+        tmem_ld_wait();
+        const int n_valid = max(0, min(8, p.Wo - x0));
+        const int64_t off = obase + static_cast<int64_t>(y0 + row) * p.out_pitch + x0;
+        const uint2 o = ws_epi8_even<SAT>(z, u, kc, n_valid, r.ch_ok, sat);
+        if (r.ch_ok) stg64(p.out + off, o);
+        if (p.has_ds) {
+          const uint2 o2 = ws_epi8_even<SAT>(v, nullptr, kc2, n_valid, r.ch_ok, sat);
+          if (r.ch_ok) stg64(p.out2 + off, o2);
+        }
+      }
+    }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&r.acc_empty[ab]);
@@ -337,7 +414,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
   uint64_t* acc_empty = acc_full + 2;               // [2] count kWsEpiWarps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const uint32_t w_addr = base + kWsSmemBar;
-  const uint32_t a_addr = w_addr + static_cast<uint32_t>(p.w_slots) * kWsChunkBytes;
+  const uint32_t a_addr = w_addr + static_cast<uint32_t>(p.w_slots) * static_cast<uint32_t>(p.w_chunk_bytes);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -393,6 +470,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     er.warp_has_ch = dual ? (q * 16 < p.c_out) : (static_cast<int>(g) * kWsCo + q * 32 < p.c_out);
     er.acc_full = acc_full; er.acc_empty = acc_empty;
     uint32_t sat;
+    if (p.stride == 2) {
+      WsEpiConst kc2 = kc;
+      if (p.has_ds) {
+        kc2.sf = ch_ok ? p.epi2.chan_scale[co] : 0.f;
+        kc2.bias = (ch_ok && p.epi2.bias) ? p.epi2.bias[co] : 0;
+        kc2.relu_lo = (p.epi2.flags & ACCEL_RELU) ? 0 : INT_MIN;
+        kc2.out_lo = (p.epi2.flags & ACCEL_RELU_OUT) ? 0 : -128;
+      }
+      sat = sat_on ? ws_epi_loop_s2<true>(p, er, kc, kc2, lane) : ws_epi_loop_s2<false>(p, er, kc, kc2, lane);
+    } else
     switch (variant) {
       case 0: sat = ws_epi_loop<0, false>(p, er, kc, lane); break;
       case 1: sat = ws_epi_loop<0, true>(p, er, kc, lane); break;
@@ -424,7 +511,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
         const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
         for (uint32_t sub = 0; sub < n_sub; ++sub) {
           const uint32_t z1 = tmem_base + ab * kWsAccCols + ((sub * 16u) << 16);
-          uint32_t z_on = 0u, u_on = 0u;                // first MMA into Z1 / U overwrites, the rest accumulate
+          uint32_t z_on = 0u, u_on = 0u, v_on = 0u;     // first MMA into Z1 / U / V overwrites, the rest accumulate
           for (uint32_t j = 0; j < n_chunks; ++j) {
             uint32_t wslot;
             if (p.w_resident) {
@@ -437,7 +524,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
             mbar_wait(&a_full[as], aph);
             tc_fence_after();
             const uint32_t mask = (p.dbg & 2) ? 0u : p.masks[g * kWsMaxChunks + j];
-            const uint32_t wl = a_lo0 | (((w_addr + wslot * kWsChunkBytes) >> 4) & 0x3FFFu);
+            const uint32_t wl = a_lo0 | (((w_addr + wslot * static_cast<uint32_t>(p.w_chunk_bytes)) >> 4) & 0x3FFFu);
             const uint32_t xl = b_lo0 | (((a_addr + as * static_cast<uint32_t>(p.a_stage_bytes)) >> 4) & 0x3FFFu);
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
@@ -454,6 +541,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
               }
               if (mask & (1u << (kh * 3 + 2)))
                 mma_i8_ss(z1 + u_off, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 2) * (kWsTapBytes >> 4)), bd, idesc, 1u);
+              if (kh == 1 && p.has_ds && (p.masks2[g * kWsMaxChunks + j] & 1u) && !(p.dbg & 2)) {   // fused 1x1 / stride 2
+                mma_i8_ss(z1 + kWsVCol, (static_cast<uint64_t>(a_hi) << 32) | (wl + 9 * (kWsTapBytes >> 4)), bd, idesc, v_on);
+                v_on = 1u;
+              }
             }
             mma_commit(&a_empty[as]);
             if (++as == static_cast<uint32_t>(p.a_slots)) { as = 0; aph ^= 1u; }
@@ -475,7 +566,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     // about one row per 4 cycles (measured: 685 cycles per 8 KB stage); 16-byte LDGSTS copies issued by two warps are
     // several times faster and zero-fill the padding just the same.
     const int lt = static_cast<int>(threadIdx.x) - kWsWarpLoad * 32;           // 0..191
-    const int x16s = p.P >> 4, rows = p.R + 2;
+    const int x16s = p.P >> 4, rows = p.rows_in;
     const int n_ops = kWsCk * rows * x16s;
     uint32_t soff[kWsLoadOps];
     int32_t goff[kWsLoadOps], yrow[kWsLoadOps], nbytes[kWsLoadOps];
@@ -505,10 +596,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
         int nb[kWsLoadOps];
 #pragma unroll
         for (int k = 0; k < kWsLoadOps; ++k) {
-          const int yy = y0 - 1 + yrow[k];
+          const int yy = p.stride * y0 - 1 + yrow[k];
           const bool ok = yy >= 0 && yy < p.H && nbytes[k] > 0;
           nb[k] = ok ? nbytes[k] : min(nbytes[k], 0);
-          go[k] = ok ? static_cast<uint32_t>(goff[k] + (y0 - 1) * p.in_pitch) : 0u;
+          go[k] = ok ? static_cast<uint32_t>(goff[k] + (p.stride * y0 - 1) * p.in_pitch) : 0u;
         }
         const int8_t* src0 = p.x + static_cast<int64_t>(img) * p.C * p.H * p.in_pitch;
         for (uint32_t j = 0; j < n_chunks; ++j) {
@@ -548,11 +639,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
             if (++ws == static_cast<uint32_t>(p.w_slots)) { ws = 0; wph ^= 1u; }
           }
           uint64_t* bar = &w_full[wslot];
-          mbar_arrive_expect_tx(bar, kWsChunkBytes);
+          mbar_arrive_expect_tx(bar, static_cast<uint32_t>(p.w_chunk_bytes));
           const uint8_t* src = wsrc + static_cast<size_t>(j) * kWsChunkBytes;
-          uint8_t* dst = smem + kWsSmemBar + wslot * kWsChunkBytes;
+          uint8_t* dst = smem + kWsSmemBar + wslot * static_cast<uint32_t>(p.w_chunk_bytes);
 #pragma unroll
           for (int i = 0; i < 3; ++i) bulk_g2s(dst + i * (kWsChunkBytes / 3), src + i * (kWsChunkBytes / 3), kWsChunkBytes / 3, bar);
+          if (p.has_ds)
+            bulk_g2s(dst + kWsChunkBytes, p.wblob2 + (static_cast<size_t>(g) * n_chunks + j) * kWsTapBytes, kWsTapBytes, bar);
         }
     }
     __syncwarp();

@@ -181,7 +181,21 @@ class BsrNetwork:
                 self.buffers[sp.name] = ops.alloc_padded((batch, sp.c_out, sp.h_out, sp.w_out))
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_in: Optional[torch.Tensor] = None
-        self.n_launches = sum(1 for _ in specs)
+        # a 3x3 / stride 2 convolution and the 1x1 / stride 2 downsample of the same tensor run as one call
+        self.fused_ds: Dict[str, str] = {}
+        by_name = {sp.name: sp for sp in specs}
+        prev = "input"
+        for sp in specs:
+            if sp.kind == "conv" and sp.k == 1 and sp.stride == 2 and sp.pad == 0 and not sp.residual:
+                for cand in specs:
+                    if (cand.kind == "conv" and cand.k == 3 and cand.stride == 2 and cand.pad == 1 and not cand.residual
+                            and (cand.src or None) == (sp.src or None) and cand.src and cand.c_in == sp.c_in
+                            and cand.c_out == sp.c_out and cand.name not in self.fused_ds
+                            and specs.index(cand) < specs.index(sp)):
+                        self.fused_ds[cand.name] = sp.name
+                        break
+            prev = sp.name
+        self.n_launches = sum(1 for _ in specs) - len(self.fused_ds)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         prev = "input"
@@ -190,7 +204,14 @@ class BsrNetwork:
         for sp in self.specs:
             src = t[sp.src] if sp.src else t[prev]
             out = self.buffers[sp.name]
-            if sp.kind == "conv":
+            if sp.kind == "conv" and sp.name in self.fused_ds.values():
+                pass                                   # written by the stride-2 convolution it is fused with
+            elif sp.kind == "conv" and sp.name in self.fused_ds:
+                L, D = self.layers[sp.name], self.layers[self.fused_ds[sp.name]]
+                dsp = D.spec
+                ops.conv_dual(L.plan, D.plan, src, sp.c_out, chan_scale=L.sf, chan_scale_ds=D.sf, bias=L.bias, bias_ds=D.bias,
+                              relu=sp.relu, relu_ds=dsp.relu, out=out, out_ds=self.buffers[dsp.name], sat_count=self.sat)
+            elif sp.kind == "conv":
                 L = self.layers[sp.name]
                 if sp.residual:
                     # conv -> requant -> + identity -> ReLU on the int8 sum

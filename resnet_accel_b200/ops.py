@@ -219,7 +219,7 @@ class BsrPlan:
                     raise AcceleratorError(_lib.INVALID_CONFIG, "residual strides must equal the output strides")
         e, keep = self._epilogue(out_kind, c_out, chan_scale, bias, relu, residual, res_scales, sat_count, chan_absmax,
                                  relu_out)
-        if ksize == 3 and stride == 1 and pad == 1 and out_kind == "i8" and chan_absmax is None and W <= 62:
+        if ksize == 3 and stride in (1, 2) and pad == 1 and out_kind == "i8" and chan_absmax is None and W <= 62:
             self._prepare_conv_ws(Cin, c_out, ksize)
         g = ConvGeom(B, Cin, H, W, ksize, stride, pad, in_pitch)
         P = max(Ho * Wo, 1)
@@ -229,6 +229,42 @@ class BsrPlan:
             lay = OutLayout(P, c_out * Ho * out_pitch, Ho * out_pitch, 1, Wo, out_pitch)
         check(_lib.lib().accel_conv_bsr_i8(self._h, _ptr(x), C.byref(g), C.byref(e), _ptr(out), C.byref(lay), _stream()))
         return out
+
+
+def conv_dual(plan: BsrPlan, plan_ds: BsrPlan, x: torch.Tensor, c_out: int, *, chan_scale, chan_scale_ds, bias=None, bias_ds=None,
+              relu: bool = True, relu_ds: bool = False, out: Optional[torch.Tensor] = None,
+              out_ds: Optional[torch.Tensor] = None, sat_count: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """First convolution of a ResNet stage (3x3 / stride 2 / pad 1, ``plan``) and its downsample branch (1x1 / stride 2,
+    ``plan_ds``) from the same input in one call: both int8 NCHW outputs ``[B, c_out, H/2, W/2]`` with the same strides."""
+    if x.dtype != torch.int8 or x.dim() != 4 or not x.is_cuda:
+        raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 4-D INT8 CUDA tensor (NCHW)")
+    in_pitch = _row_pitch(x)
+    if in_pitch is None:
+        x = x.contiguous()
+        in_pitch = x.shape[3]
+    B, Cin, H, W = x.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    if out is None:
+        out = alloc_padded((B, c_out, Ho, Wo))
+    if out_ds is None:
+        out_ds = alloc_padded((B, c_out, Ho, Wo))
+    out_pitch = _row_pitch(out)
+    if out_pitch is None or _row_pitch(out_ds) != out_pitch or tuple(out.shape) != tuple(out_ds.shape):
+        raise AcceleratorError(_lib.INVALID_CONFIG, "both outputs must be NCHW with the same shape and row pitch")
+    if W <= 62:
+        plan._prepare_conv_ws(Cin, c_out, 3)
+        plan_ds._prepare_conv_ws(Cin, c_out, 1)
+    e, keep = plan._epilogue("i8", c_out, chan_scale, bias, relu, None, None, sat_count, None)
+    e2, keep2 = plan_ds._epilogue("i8", c_out, chan_scale_ds, bias_ds, relu_ds, None, None, sat_count, None)
+    g = ConvGeom(B, Cin, H, W, 3, 2, 1, in_pitch)
+    P = max(Ho * Wo, 1)
+    if out_pitch == Wo:
+        lay = OutLayout(P, c_out * Ho * Wo, Ho * Wo, 1, 0, 0)
+    else:
+        lay = OutLayout(P, c_out * Ho * out_pitch, Ho * out_pitch, 1, Wo, out_pitch)
+    check(_lib.lib().accel_conv_bsr_i8_dual(plan._h, plan_ds._h, _ptr(x), C.byref(g), C.byref(e), _ptr(out), C.byref(e2),
+                                            _ptr(out_ds), C.byref(lay), _stream()))
+    return out, out_ds
 
 
 def _is_cuda(a) -> bool:

@@ -101,3 +101,71 @@ def test_conv_ws_dense_layout_and_fallback():
     assert _lib.lib().accel_debug_counter(0) == before
     ref, _ = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, 3, 1, 1, sf=sf)
     assert np.array_equal(got, ref)
+
+
+def _s2_case(B, Cin, H, W, Cout, density, seed, with_ds=True):
+    import torch
+    from resnet_accel_b200 import _lib, ops
+    from resnet_accel_b200.ops import BsrPlan
+    rng = np.random.default_rng(seed)
+
+    def make(k):
+        K = Cin * k * k
+        Wm = rng.integers(-128, 128, (Cout, K), dtype=np.int8)
+        nbr, nbc = -(-Cout // 14), -(-K // 14)
+        keep = rng.random((nbr, nbc)) < density
+        Wm = Wm * np.repeat(np.repeat(keep, 14, 0), 14, 1)[:Cout, :K].astype(np.int8)
+        bsr = O.build_bsr_14x14_int8_direct(Wm)
+        return bsr, BsrPlan(bsr["indptr"], bsr["indices"], bsr["data"], n_block_cols=bsr["num_block_cols"])
+
+    bsr3, plan3 = make(3)
+    bsr1, plan1 = make(1)
+    x = rng.integers(-128, 128, (B, Cin, H, W), dtype=np.int8)
+    bias3 = rng.integers(-1000, 1000, Cout, dtype=np.int32)
+    bias1 = rng.integers(-300, 300, Cout, dtype=np.int32)
+    sf3 = rng.uniform(1e-4, 2e-3, Cout).astype(np.float32)
+    sf1 = rng.uniform(1e-3, 8e-3, Cout).astype(np.float32)
+    xd = ops.alloc_padded(x.shape)
+    xd.copy_(torch.from_numpy(x).cuda())
+    base_in = xd._base if xd._base is not None else xd
+    if base_in.shape[-1] > W:
+        base_in[..., W:] = -5
+    Ho, Wo = H // 2, W // 2
+    out3, out1 = ops.alloc_padded((B, Cout, Ho, Wo)), ops.alloc_padded((B, Cout, Ho, Wo))
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    before = _lib.lib().accel_debug_counter(0)
+    if with_ds:
+        ops.conv_dual(plan3, plan1, xd, Cout, chan_scale=sf3, chan_scale_ds=sf1, bias=bias3, bias_ds=bias1, relu=True,
+                      relu_ds=False, out=out3, out_ds=out1, sat_count=cnt)
+    else:
+        plan3.conv(xd, 3, 2, 1, Cout, "i8", chan_scale=sf3, bias=bias3, relu=True, out=out3, sat_count=cnt)
+    torch.cuda.synchronize()
+    assert _lib.lib().accel_debug_counter(0) == before + 1, "the weight-stationary kernel did not run"
+    ref3, sat3 = c_oracle.conv_bsr_layer(x, bsr3["indptr"], bsr3["indices"], bsr3["data"], Cout, 3, 2, 1, bias=bias3, relu=True, sf=sf3)
+    assert np.array_equal(out3.cpu().numpy(), ref3)
+    sat = sat3
+    if with_ds:
+        ref1, sat1 = c_oracle.conv_bsr_layer(x, bsr1["indptr"], bsr1["indices"], bsr1["data"], Cout, 1, 2, 0, bias=bias1, relu=False,
+                                             sf=sf1)
+        assert np.array_equal(out1.cpu().numpy(), ref1)
+        sat += sat1
+    assert int(cnt.item()) == sat
+    for o in (out3, out1) if with_ds else (out3,):
+        base = o._base if o._base is not None else o
+        assert int(base[..., Wo:].abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,density", [
+    (2, 64, 56, 56, 128, 0.3),       # layer2.0: conv1 + downsample, one output row per tile
+    (3, 128, 28, 28, 256, 0.3),      # layer3.0: two output rows per tile, two channel groups
+    (5, 256, 14, 14, 512, 0.3),      # layer4.0: four rows per tile (7 rows: ragged), streamed weights
+    (2, 32, 10, 20, 40, 0.6),        # small / odd channel count
+    (2, 64, 12, 60, 70, 0.1),        # wide rows, very sparse
+])
+def test_conv_ws_stride2_with_downsample(B, Cin, H, W, Cout, density):
+    _s2_case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W)
+
+
+def test_conv_ws_stride2_alone():
+    _s2_case(2, 64, 28, 28, 96, 0.4, seed=5, with_ds=False)
+    _s2_case(9, 128, 28, 28, 128, 0.3, seed=6, with_ds=False)
