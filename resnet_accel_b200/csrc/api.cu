@@ -883,6 +883,18 @@ int accel_maxpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, 
   if (in_pitch < w || out_pitch < Wo) return fail(ACCEL_INVALID_CONFIG, "row pitch smaller than the row");
   const int64_t total = n_planes * Ho * ((Wo + 3) / 4);
   if (total <= 0) return ACCEL_OK;
+  if (pool == 3 && stride == 2 && pad == 1 && (in_pitch & 15) == 0 && (out_pitch & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int wq = (Wo + 15) / 16;
+    const int64_t total16 = n_planes * Ho * wq;
+    if (total16 < (1ll << 31)) {
+      accel::maxpool3x3s2_i8_x16_kernel<<<grid_for(total16, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          x, out, static_cast<uint32_t>(total16), h, w, Ho, Wo, in_pitch, out_pitch,
+          accel::make_fastdiv(static_cast<uint32_t>(wq)), accel::make_fastdiv(static_cast<uint32_t>(Ho)));
+      CU(cudaGetLastError());
+      return ACCEL_OK;
+    }
+  }
   if (pool == 3 && stride == 2 && pad == 1 && (in_pitch & 7) == 0 && (out_pitch & 3) == 0 &&
       (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
     accel::maxpool3x3s2_i8_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -344,6 +344,77 @@ __global__ void maxpool3x3s2_i8_kernel(const int8_t* __restrict__ x, int8_t* __r
     }
   }
 }
+// Same pooling, 16 outputs per thread: rows 16-byte aligned, six 16-byte loads (three input rows x 32 columns) and
+// one 16-byte store per thread; the column left of the window comes from the previous 16 bytes' last byte.
+__device__ __forceinline__ uint4 ldg_nc_128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__global__ void __launch_bounds__(256) maxpool3x3s2_i8_x16_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out,
+                                                                  uint32_t total, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
+                                                                  int32_t in_pitch, int32_t out_pitch, FastDiv d_wq, FastDiv d_ho) {
+  constexpr uint32_t kNeg = 0x80808080u;
+  // 32-bit index arithmetic with exact multiply-shift divisions: 64-bit / and % cost more than the pooling itself
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t t1 = fdiv(idx, d_wq);
+    const int q = static_cast<int>(idx - t1 * d_wq.d);
+    const uint32_t upl = fdiv(t1, d_ho);
+    const int oh = static_cast<int>(t1 - upl * d_ho.d);
+    const int64_t pl = upl;
+    const int c0 = 32 * q;                             // first input column of this thread's 32
+    const int8_t* xp = x + pl * static_cast<int64_t>(H) * in_pitch;
+    uint4 a[3], b[3];
+    uint32_t l[3];
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+      const int ih = 2 * oh - 1 + ph;
+      const bool ok = ih >= 0 && ih < H;
+      const int8_t* row = xp + static_cast<int64_t>(ok ? ih : 0) * in_pitch + c0;
+      a[ph] = make_uint4(kNeg, kNeg, kNeg, kNeg); b[ph] = a[ph]; l[ph] = kNeg;
+      if (ok) {
+        a[ph] = ldg_nc_128(row);                                   // c0 < W always (wq covers Wo)
+        if (c0 + 16 < in_pitch) b[ph] = ldg_nc_128(row + 16);
+        if (c0 > 0) l[ph] = *reinterpret_cast<const uint32_t*>(row - 4);
+      }
+    }
+    // vertical maximum of the three rows (rows outside the image are all -128)
+    uint32_t v[8];
+    v[0] = __vmaxs4(__vmaxs4(a[0].x, a[1].x), a[2].x); v[1] = __vmaxs4(__vmaxs4(a[0].y, a[1].y), a[2].y);
+    v[2] = __vmaxs4(__vmaxs4(a[0].z, a[1].z), a[2].z); v[3] = __vmaxs4(__vmaxs4(a[0].w, a[1].w), a[2].w);
+    v[4] = __vmaxs4(__vmaxs4(b[0].x, b[1].x), b[2].x); v[5] = __vmaxs4(__vmaxs4(b[0].y, b[1].y), b[2].y);
+    v[6] = __vmaxs4(__vmaxs4(b[0].z, b[1].z), b[2].z); v[7] = __vmaxs4(__vmaxs4(b[0].w, b[1].w), b[2].w);
+    const uint32_t left = __vmaxs4(__vmaxs4(l[0], l[1]), l[2]);    // byte 3 = column c0 - 1
+    if (c0 + 32 > W) {                                 // columns past the row's end (pitch padding) count as padding
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int nv = W - (c0 + 4 * j);
+        const uint32_t keep = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
+        v[j] = (v[j] & keep) | (kNeg & ~keep);
+      }
+    }
+    // output o (0..15) = max over columns c0 + 2o - 1, c0 + 2o, c0 + 2o + 1
+    uint32_t r[4];
+    uint32_t prev_odd_hi = left;                       // byte 3: column just left of the current 8
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t even = __byte_perm(v[2 * g], v[2 * g + 1], 0x6420);
+      const uint32_t odd = __byte_perm(v[2 * g], v[2 * g + 1], 0x7531);
+      const uint32_t podd = __byte_perm(prev_odd_hi, odd, 0x6543);   // columns -1, +1, +3, +5 of this group of 8
+      r[g] = __vmaxs4(__vmaxs4(even, odd), podd);
+      prev_odd_hi = v[2 * g + 1];
+    }
+    int8_t* orow = out + (pl * Ho + oh) * static_cast<int64_t>(out_pitch) + 16 * q;
+    const int n_ok = Wo - 16 * q;
+    if (n_ok >= 16) {
+      *reinterpret_cast<uint4*>(orow) = make_uint4(r[0], r[1], r[2], r[3]);
+    } else {
+      int o = 0;
+      if (n_ok >= 8) { *reinterpret_cast<uint2*>(orow) = make_uint2(r[0], r[1]); o = 8; }
+      for (; o < n_ok; ++o) orow[o] = static_cast<int8_t>((r[o >> 2] >> (8 * (o & 3))) & 0xffu);
+    }
+  }
+}
 // one warp per plane: (sum + HW/2) / HW with C truncating division (golden_models.cpp:619)
 __global__ void avgpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out, int64_t n_planes,
                                   int32_t H, int32_t W, int32_t in_pitch) {
@@ -351,11 +422,24 @@ __global__ void avgpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restri
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int hw = H * W;
+  // rows that are 4-byte aligned words: one 32-bit load per 4 columns, packed byte sums by dp4a
+  const bool words = (in_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0;
+  const int wpr = (W + 3) >> 2;                        // words per row
   for (int64_t pl = warp0; pl < n_planes; pl += nwarps) {
     int s = 0;
-    for (int i = lane; i < hw; i += 32) {
-      const int r = i / W;
-      s += x[(pl * H + r) * in_pitch + (i - r * W)];
+    if (words) {
+      for (int i = lane; i < H * wpr; i += 32) {
+        const int r = i / wpr, wi = i - r * wpr;
+        uint32_t v = *reinterpret_cast<const uint32_t*>(x + (pl * H + r) * in_pitch + 4 * wi);
+        const int nv = W - 4 * wi;
+        if (nv < 4) v &= (1u << (8 * nv)) - 1u;
+        s = __dp4a(static_cast<int>(v), 0x01010101, s);
+      }
+    } else {
+      for (int i = lane; i < hw; i += 32) {
+        const int r = i / W;
+        s += x[(pl * H + r) * in_pitch + (i - r * W)];
+      }
     }
     s = __reduce_add_sync(0xffffffffu, s);
     if (lane == 0) out[pl] = static_cast<int8_t>(min(127, max(-128, (s + hw / 2) / hw)));
