@@ -13,8 +13,10 @@ by GPU (weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
              between timed steps, CUDA-event time, max over ranks.
   e2e        same metric through the public API with HOST buffers: pinned-host -> device copy of
              the int8 images and device -> host read of the INT32 logits inside the timed region.
-  roofline   the dominant kernel (bsr_tc_kernel, all conv launches of one step): algorithmic
-             bytes / event-timed duration vs the measured HBM peak (MEASURED_PEAKS.json).
+  roofline   the tensor-core convolution / FC launches of one step (conv_ws_kernel for the 3x3 layers, bsr_tcp_kernel /
+             bsr_tc_kernel for the stem and the FC): algorithmic bytes / event-timed duration vs the measured HBM
+             peak (MEASURED_PEAKS.json); `traffic` = DRAM bytes of the same launches from the committed ncu capture
+             (profiles/r01_traffic.json, written by tools/ncu_launches.py).
   cpu_baseline  the reference's C++ golden path (oracle/_ref: conv2d_int8_im2col + relu_int32 +
              requantize_int32_to_int8 + add_residual_int8, hw/sim/cpp/src/golden_models.cpp) on a
              bounded sample of the same workload on the host cores.
@@ -41,6 +43,16 @@ UNIT = "images/s"
 
 
 # ----------------------------------------------------------------------------------------- helpers
+def measured_traffic():
+    """DRAM bytes (read + write) of the conv / fc launches of one step, from the committed ncu capture of this command."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -200,7 +212,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     work = net.work()
     conv_names = [sp.name for sp in net.specs if sp.kind in ("conv", "fc")]
-    n_launch_step = len(net.specs)
+    n_launch_step = net.n_launches
 
     def barrier():
         if dist is not None:
@@ -276,7 +288,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # (3) dominant kernel: every conv/fc launch of one step, event-timed on the launching stream
     def conv_only():
         net.forward(net.static_in)
-    # eager forward = same launches as the graph; pools are < 4 % of the step
+    # eager forward = same launches as the graph (the two pools are ~5 % of the step and carry no algorithmic conv bytes)
     for _ in range(2):
         conv_only()
     torch.cuda.synchronize()
@@ -294,6 +306,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     if rank == 0:
         hbm_peak, int8_peak_tops, src = measured_peaks()
+        traffic = measured_traffic()
         ms_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total / 1e3)
         e2e_val = world * B * args.steps / (ms_e2e / 1e3)
@@ -308,7 +321,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "l2": "value: flushed between timed steps (256 MiB memset); e2e: per-step working set 1.4 GB >> 126 MB L2",
                        "graph": "one CUDA graph per step", "e2e_pipeline": "2-deep: H2D of step i+1 overlaps step i"},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_source": src, "kernel": "bsr_tcp_kernel / bsr_tc_kernel (20 conv + 1 fc launches per step)",
+                         "traffic": (traffic or {}).get("conv_fc_dram_bytes_per_step"),
+                         "traffic_source": (traffic or {}).get("source"), "peak_source": src,
+                         "kernel": f"conv_ws_kernel (3x3 layers) + bsr_tcp_kernel / bsr_tc_kernel (stem, fc): "
+                                   f"{sum(1 for n in conv_names if n not in net.fused_ds.values())} launches per step, "
+                                   "algorithmic bytes and time summed over them",
                          "useful_tops": ach_tops, "tensor_frac_of_2x_bf16_sustained": ach_tops / int8_peak_tops,
                          "kernel_ms_per_step": kms, "algorithmic_bytes_per_step": conv_bytes,
                          "useful_ops_per_step": conv_ops},
