@@ -144,10 +144,23 @@ ACCEL_API int accel_conv_bsr_i8_dual(const accel_plan* plan, const accel_plan* p
                            const accel_conv_geom* geom, const accel_epilogue* epi, void* out, const accel_epilogue* epi_ds,
                            void* out_ds, const accel_out_layout* layout, accel_stream_t stream);
 
+/* --- the ResNet stem in one call: 7x7 / stride 2 / pad 3 convolution (conv2d_int8_im2col, golden_models.cpp:883-933) with
+ * ReLU + per-channel requant (:298-303, :378-411) followed by the 3x3 / stride 2 / pad 1 max-pool (maxpool2d_int8 :534-571,
+ * padding = -128), layer table resnet_inference.cpp:61-127.  Writes only the pooled tensor int8 [batch, c_out, H/4, W/4]
+ * with rows of `out_pitch` bytes (0 = dense).  The pool is taken on the INT32 accumulators, which is bit-identical because
+ * requant is monotone for the positive per-channel factors the exporters produce (the caller guarantees chan_scale > 0);
+ * epi->sat_count still counts every clipped convolution output.  Needs a plan prepared with
+ * accel_plan_conv_ws_prepare(ksize = 7); returns ACCEL_ILLEGAL_COMMAND when the geometry has no fused kernel (then run
+ * accel_conv_bsr_i8 and accel_maxpool_i8). */
+ACCEL_API int accel_conv_pool_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const accel_conv_geom* geom,
+                           const accel_epilogue* epi, int32_t pool, int32_t pool_stride, int32_t pool_pad, int8_t* out,
+                           int32_t out_pitch, accel_stream_t stream);
+
 /* --- weight-stationary re-layout for 3x3 stride-1 pad-1 convolutions (conv2d_int8_im2col, golden_models.cpp:883-933,
  * K order (c_in, kh, kw) of im2col_int8 :801-842).  Optional: when a plan has been prepared for (c_in, c_out) and the
  * tensors of an accel_conv_bsr_i8 call allow it (16-byte aligned rows, int8 output, width <= 62; ksize 3 with stride 1
- * or 2, and ksize 1 as the second plan of accel_conv_bsr_i8_dual), that call runs the
+ * or 2, ksize 1 as the second plan of accel_conv_bsr_i8_dual, ksize 7 with c_in <= 4 and c_out <= 64 for
+ * accel_conv_pool_bsr_i8), that call runs the
  * kernel of csrc/conv_ws.cuh: the stored blocks are scattered once into 128x32 K-major weight tiles per
  * (channel group, 32-channel chunk, tap) and the activation tile is fed to the tensor core straight from TMA.
  * conv_ws_bytes reports the workspace for that layout (0 = no such path for this geometry); conv_ws_prepare fills it

@@ -65,6 +65,7 @@ SYMBOLS = {
     "accel_conv_bsr_i8": (C.c_int, [_P, _P, C.POINTER(ConvGeom), C.POINTER(Epilogue), _P, C.POINTER(OutLayout), _P]),
     "accel_conv_bsr_i8_dual": (C.c_int, [_P, _P, _P, C.POINTER(ConvGeom), C.POINTER(Epilogue), _P, C.POINTER(Epilogue), _P,
                                          C.POINTER(OutLayout), _P]),
+    "accel_conv_pool_bsr_i8": (C.c_int, [_P, _P, C.POINTER(ConvGeom), C.POINTER(Epilogue), _I32, _I32, _I32, _P, _I32, _P]),
     "accel_bsr_gemm_generic": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _P, _I64, _P]),
     "accel_block_l1_i8": (C.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
     "accel_block_l2_f32": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32, _P, _P]),

@@ -18,6 +18,7 @@
 #include "bsr_tc.cuh"
 #include "bsr_tcp.cuh"
 #include "conv_ws.cuh"
+#include "stem_ws.cuh"
 #include "plan.h"
 #include "simple_kernels.cuh"
 
@@ -84,6 +85,9 @@ void set_kernel_attrs() {
   }
   if (g_attr_err == cudaSuccess)
     g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::conv_ws_kernel),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
+  if (g_attr_err == cudaSuccess)
+    g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::stem_ws_kernel),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
 }
 
@@ -283,12 +287,16 @@ struct accel_plan {
 namespace {
 
 bool ws_geometry_ok(const accel_plan* plan, int32_t c_in, int32_t c_out, int32_t ksize) {
+  if (ksize == 7)      // stem layout (stem_ws.cuh): K rows (c, kh) fit one 32-row chunk, one lane quadrant slice per image
+    return c_in > 0 && c_in * 7 <= accel::kWsCk && c_out > 0 && c_out <= 64 && c_out <= plan->p.nbr * accel::kBlock &&
+           (static_cast<int64_t>(c_in) * 49 + accel::kBlock - 1) / accel::kBlock <= plan->p.nbc;
   if ((ksize != 3 && ksize != 1) || c_in <= 0 || c_in % accel::kWsCk != 0 || c_in / accel::kWsCk > accel::kWsMaxChunks) return false;
   if (c_out <= 0 || c_out > plan->p.nbr * accel::kBlock || (c_out + accel::kWsCo - 1) / accel::kWsCo > accel::kWsMaxGroups)
     return false;
   return (static_cast<int64_t>(c_in) * ksize * ksize + accel::kBlock - 1) / accel::kBlock <= plan->p.nbc;
 }
 size_t ws_blob_bytes(int32_t c_in, int32_t c_out, int32_t taps) {
+  if (taps == 49) return accel::kStWBytes;
   return static_cast<size_t>((c_out + accel::kWsCo - 1) / accel::kWsCo) * (c_in / accel::kWsCk) * taps * accel::kWsTapBytes;
 }
 
@@ -473,7 +481,7 @@ int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   WsState& W = plan->ws;
   W.ready = false;
-  W.c_in = c_in; W.c_out = c_out; W.taps = taps; W.n_chunks = c_in / accel::kWsCk; W.n_groups = (c_out + accel::kWsCo - 1) / accel::kWsCo;
+  W.c_in = c_in; W.c_out = c_out; W.taps = taps; W.n_chunks = taps == 49 ? 1 : c_in / accel::kWsCk; W.n_groups = (c_out + accel::kWsCo - 1) / accel::kWsCo;
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   CU(cudaMemsetAsync(ws, 0, blob, st));
   std::memset(W.masks, 0, sizeof(W.masks));
@@ -482,6 +490,7 @@ int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32
   for (int32_t br = 0; br < plan->p.nbr; ++br)
     for (int32_t i = plan->row_ptr[br]; i < plan->row_ptr[br + 1]; ++i) {
       blk_row[i] = br;
+      if (taps == 49) continue;
       const int32_t bc = plan->col_idx[i];
       const int co_lo = br * accel::kBlock, co_hi = std::min(co_lo + accel::kBlock, c_out) - 1;
       if (co_hi < co_lo) continue;
@@ -498,7 +507,10 @@ int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32
     int32_t* d_col = d_row + nnz;
     CU(cudaMemcpyAsync(d_row, blk_row.data(), static_cast<size_t>(nnz) * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_col, plan->col_idx.data(), static_cast<size_t>(nnz) * 4, cudaMemcpyHostToDevice, st));
-    accel::ws_scatter_kernel<<<static_cast<unsigned>(nnz), 64, 0, st>>>(blocks_dev, d_row, d_col, nnz, c_in, c_out, W.n_chunks, taps, ws);
+    if (taps == 49)
+      accel::stem_scatter_kernel<<<static_cast<unsigned>(nnz), 64, 0, st>>>(blocks_dev, d_row, d_col, nnz, c_in, c_out, ws);
+    else
+      accel::ws_scatter_kernel<<<static_cast<unsigned>(nnz), 64, 0, st>>>(blocks_dev, d_row, d_col, nnz, c_in, c_out, W.n_chunks, taps, ws);
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(st));     // blk_row is pageable host memory
@@ -732,6 +744,50 @@ int accel_conv_bsr_i8_dual(const accel_plan* plan, const accel_plan* plan_ds, co
   accel_conv_geom g1 = *g;
   g1.ksize = 1; g1.pad = 0;
   return accel_conv_bsr_i8(plan_ds, input_nchw, &g1, epi_ds, out_ds, layout, stream);
+}
+
+int accel_conv_pool_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, const accel_conv_geom* g, const accel_epilogue* epi,
+                           int32_t pool, int32_t pool_stride, int32_t pool_pad, int8_t* out, int32_t out_pitch, accel_stream_t stream) {
+  if (!plan || !g || !epi || !out) return fail(ACCEL_INVALID_CONFIG, "null plan / geometry / epilogue / output");
+  if (!plan->p.uploaded) return fail(ACCEL_NOT_READY, "Weights not loaded");
+  const WsState& W = plan->ws;
+  // the fused kernel exists for the ResNet stem shape family only; anything else is ACCEL_ILLEGAL_COMMAND and the caller
+  // runs accel_conv_bsr_i8 + accel_maxpool_i8 (no scratch tensor is owned by this library)
+  const bool ok = !g_no_ws && W.ready && W.taps == 49 && g->ksize == 7 && g->stride == 2 && g->pad == 3 && pool == 3 &&
+                  pool_stride == 2 && pool_pad == 1 && g->c_in == W.c_in && epi->n_channels == W.c_out &&
+                  (epi->flags & ACCEL_OUT_I8) && !epi->chan_absmax && !epi->residual && !(epi->flags & ACCEL_RELU_OUT) &&
+                  epi->chan_scale && g->batch > 0 && g->w % 32 == 0 && g->w <= 224 && g->h % 4 == 0 &&
+                  g->c_in * 7 * (g->w / 32) <= 160;
+  if (!ok) return fail(ACCEL_ILLEGAL_COMMAND, "no fused convolution + max-pool kernel for this geometry");
+  const int64_t in_pitch = g->in_row_pitch > 0 ? g->in_row_pitch : g->w;
+  const int Hc = g->h / 2, Wc = g->w / 2, Hp = Hc / 2, Wp = Wc / 2;
+  if (out_pitch == 0) out_pitch = Wp;
+  if ((in_pitch & 15) || (reinterpret_cast<uintptr_t>(input_nchw) & 15) || (out_pitch & 3) || out_pitch < ((Wp + 3) & ~3) ||
+      (reinterpret_cast<uintptr_t>(out) & 3) || static_cast<int64_t>(g->batch) * W.c_out * Hp * out_pitch >= (1ll << 40))
+    return fail(ACCEL_ILLEGAL_COMMAND, "fused convolution + max-pool needs 16-byte aligned input rows and 4-byte aligned output rows");
+  std::call_once(g_attr_once, set_kernel_attrs);
+  if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(smem)");
+  accel::StemParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.C = g->c_in; p.H = g->h; p.W = g->w; p.B = g->batch;
+  p.Hc = Hc; p.Wc = Wc; p.Hp = Hp; p.Wp = Wp;
+  p.c_out = W.c_out; p.in_pitch = static_cast<int32_t>(in_pitch); p.out_pitch = out_pitch;
+  p.n_pairs = (g->batch + 1) / 2;
+  const int64_t n_items = static_cast<int64_t>(p.n_pairs) * Hp;
+  if (n_items > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "too many rows");
+  p.n_items = static_cast<int32_t>(n_items);
+  p.d_hp = accel::make_fastdiv(static_cast<uint32_t>(Hp));
+  p.x = input_nchw; p.wblob = W.blob; p.epi = *epi; p.out = out;
+  p.chan_stride = Hp * out_pitch;
+  p.image_stride = static_cast<int64_t>(W.c_out) * p.chan_stride;
+  p.dbg = g_dbg_flags;
+  const int ctas = n_items < sm_count() ? static_cast<int>(n_items) : sm_count();
+  const int smem = 1024 + accel::kStSmemBar + accel::kStWBytes + accel::kStSlots * accel::kStStageBytes;
+  accel::stem_ws_kernel<<<static_cast<unsigned>(ctas), accel::kStThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "stem_ws_kernel launch");
+  ++g_ws_launches;
+  return ACCEL_OK;
 }
 
 int accel_bsr_gemm_generic(const int8_t* act, int64_t M, int64_t K, int64_t lda, const int32_t* row_ptr,

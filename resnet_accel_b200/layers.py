@@ -195,14 +195,35 @@ class BsrNetwork:
                         self.fused_ds[cand.name] = sp.name
                         break
             prev = sp.name
-        self.n_launches = sum(1 for _ in specs) - len(self.fused_ds)
+        # the stem convolution and the max-pool behind it run as one kernel when the library has one for the geometry
+        # (csrc/stem_ws.cuh); the convolution's own output tensor is then never materialised
+        self.fused_pool: Dict[str, str] = {}
+        for i, sp in enumerate(specs[:-1]):
+            nx = specs[i + 1]
+            if (sp.kind == "conv" and (sp.k, sp.stride, sp.pad) == (7, 2, 3) and sp.relu and not sp.residual
+                    and nx.kind == "maxpool" and (nx.k, nx.stride, nx.pad) == (3, 2, 1) and not nx.src
+                    and sp.c_in * 7 <= 32 and sp.c_out <= 64 and sp.w % 32 == 0 and sp.w <= 224 and sp.h % 4 == 0
+                    and not any(o.src == sp.name or o.residual == sp.name for o in specs)
+                    and bool((self.layers[sp.name].sf > 0).all().item())):
+                self.fused_pool[sp.name] = nx.name
+                self.buffers.pop(sp.name, None)
+        self.n_launches = sum(1 for _ in specs) - len(self.fused_ds) - len(self.fused_pool)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         prev = "input"
         t: Dict[str, torch.Tensor] = {"input": x}
         t.update(self.buffers)
         for sp in self.specs:
+            if sp.name in self.fused_pool.values():
+                prev = sp.name                          # written by the stem convolution it is fused with
+                continue
             src = t[sp.src] if sp.src else t[prev]
+            if sp.name in self.fused_pool:
+                L = self.layers[sp.name]
+                ops.conv_pool(L.plan, src, sp.c_out, chan_scale=L.sf, bias=L.bias, relu=True,
+                              out=self.buffers[self.fused_pool[sp.name]], sat_count=self.sat)
+                prev = sp.name
+                continue
             out = self.buffers[sp.name]
             if sp.kind == "conv" and sp.name in self.fused_ds.values():
                 pass                                   # written by the stride-2 convolution it is fused with

@@ -267,6 +267,43 @@ def conv_dual(plan: BsrPlan, plan_ds: BsrPlan, x: torch.Tensor, c_out: int, *, c
     return out, out_ds
 
 
+def conv_pool(plan: BsrPlan, x: torch.Tensor, c_out: int, *, chan_scale, bias=None, relu: bool = True, ksize: int = 7,
+              stride: int = 2, pad: int = 3, pool: int = 3, pool_stride: int = 2, pool_pad: int = 1,
+              out: Optional[torch.Tensor] = None, sat_count: Optional[torch.Tensor] = None,
+              scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Convolution + ReLU/requant + max-pool (the ResNet stem).  One fused kernel when the library has one for the
+    geometry, else the convolution into ``scratch`` (allocated here when missing) followed by the pool."""
+    if x.dtype != torch.int8 or x.dim() != 4 or not x.is_cuda:
+        raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 4-D INT8 CUDA tensor (NCHW)")
+    in_pitch = _row_pitch(x)
+    if in_pitch is None:
+        x = x.contiguous()
+        in_pitch = x.shape[3]
+    B, Cin, H, W = x.shape
+    Hc, Wc = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    Hp, Wp = (Hc + 2 * pool_pad - pool) // pool_stride + 1, (Wc + 2 * pool_pad - pool) // pool_stride + 1
+    if out is None:
+        out = alloc_padded((B, c_out, Hp, Wp))
+    out_pitch = _row_pitch(out)
+    if out_pitch is None:
+        raise AcceleratorError(_lib.INVALID_CONFIG, "output must be NCHW, dense or with padded rows")
+    fused = ksize == 7 and stride == 2 and pad == 3 and (pool, pool_stride, pool_pad) == (3, 2, 1) and Cin * 7 <= 32 and c_out <= 64
+    if fused:
+        plan._prepare_conv_ws(Cin, c_out, 7)
+        e, keep = plan._epilogue("i8", c_out, chan_scale, bias, relu, None, None, sat_count, None)
+        g = ConvGeom(B, Cin, H, W, ksize, stride, pad, in_pitch)
+        rc = _lib.lib().accel_conv_pool_bsr_i8(plan._h, _ptr(x), C.byref(g), C.byref(e), pool, pool_stride, pool_pad, _ptr(out),
+                                               out_pitch, _stream())
+        if rc == 0:
+            return out
+        if rc != _lib.ILLEGAL_COMMAND:
+            check(rc)
+    if scratch is None:
+        scratch = alloc_padded((B, c_out, Hc, Wc))
+    plan.conv(x, ksize, stride, pad, c_out, "i8", chan_scale=chan_scale, bias=bias, relu=relu, out=scratch, sat_count=sat_count)
+    return maxpool_i8(scratch, pool, pool_stride, pool_pad, out=out)
+
+
 def _is_cuda(a) -> bool:
     return isinstance(a, torch.Tensor) and a.is_cuda
 

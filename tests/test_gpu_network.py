@@ -53,9 +53,20 @@ def test_network_layers_match_oracle_port():
     torch.cuda.synchronize()
     t = {"input": x}
     prev = "input"
+    from oracle import bsr_oracle as O
     for sp in specs:
         src = t[sp.src] if sp.src else t[prev]
+        if sp.name in net.fused_pool:       # stem convolution fused with its max-pool: its own output is never materialised
+            lay = net.layers[sp.name]
+            bsr = {k: lay.bsr[k].cpu().numpy() for k in ("indptr", "indices", "data")}
+            t[sp.name], _ = c_oracle.conv_bsr_layer(src, bsr["indptr"], bsr["indices"], bsr["data"], sp.c_out, sp.k, sp.stride,
+                                                    sp.pad, bias=lay.bias.cpu().numpy(), relu=sp.relu, sf=lay.sf.cpu().numpy())
+            prev = sp.name
+            continue
         got = net.buffers[sp.name].cpu().numpy()
+        if sp.kind == "maxpool" and prev in net.fused_pool:
+            want = np.stack([O.maxpool2d_int8(src[b], sp.k, sp.stride, sp.pad) for b in range(src.shape[0])])
+            assert np.array_equal(got, want), sp.name
         if sp.kind == "conv":
             lay = net.layers[sp.name]
             bsr = {k: lay.bsr[k].cpu().numpy() for k in ("indptr", "indices", "data")}
