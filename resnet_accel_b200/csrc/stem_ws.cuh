@@ -8,8 +8,11 @@
 //     (s = -1, 0, 1) and O[x + s] for kw = 4 + 2s (s = -2 .. 1) - a stride-1 problem with seven column shifts.
 //   * K = (c, kh): 21 of 32 rows of a chunk; two chunks per tile (E and O), [32 k-rows][128 pixels] with the 128-byte
 //     swizzle = one MN-major atom row per k.  Pixels 112..127 are zero (never written).
-//   * Column shifts through the accumulator address as in conv_ws.cuh: even shifts (0, -2) -> Z at +0 / +2, odd shifts
-//     (-1, +1) -> U at +2 / +0 with U = Z + 126, Y[x] = Z[x] + U[x + 1]: seven MMAs (M = 64, N = 128, K = 32) per tile.
+//   * Column shifts through the accumulator address, which must be an even column: the loaders (a register path anyway)
+//     stage every chunk twice, as it is and shifted right by one pixel (E1[j] = E[j-1], O1[j] = O[j-1]), so that the
+//     seven taps all land in ONE accumulator at offsets 0 / 2 / 4: seven MMAs (M = 64, N = 128, K = 32) per tile and
+//     one TMEM read per output (TMEM reads, 64 B/clk/SM, are what bounds these epilogues: a second accumulator for the
+//     odd shifts, as conv_ws.cuh uses, doubles them).
 //   * <= 64 output channels: two IMAGES share an accumulator set (lanes 0-15 / 16-31 of every lane quadrant).
 //   * The pool is taken on the INT32 accumulators: requant (and ReLU) are monotone in the accumulator for a positive
 //     per-channel factor, so max-then-requant equals requant-then-max bit for bit, and only one value in four is
@@ -24,15 +27,15 @@ namespace accel {
 constexpr int kStEpiWarps = 8;
 constexpr int kStWarpIssue = kStEpiWarps;            // 8
 constexpr int kStWarpLoad = kStWarpIssue + 1;        // 9..14: loaders (LDG -> byte de-interleave -> STS)
-constexpr int kStLoadWarps = 6;
+constexpr int kStLoadWarps = 3;
 constexpr int kStLoadThreads = kStLoadWarps * 32;
-constexpr int kStThreads = (kStWarpLoad + kStLoadWarps) * 32;   // 480
-constexpr int kStStageBytes = 8192;                  // E chunk (4 KB) + O chunk (4 KB)
+constexpr int kStThreads = (kStWarpLoad + kStLoadWarps) * 32;   // 384: 168 registers per thread
+constexpr int kStStageBytes = 16384;                 // E, O, E1, O1 chunks of 4 KB
 constexpr int kStSlots = 8;
 constexpr int kStWBytes = 7 * kWsTapBytes;           // one 64(128) x 32 tile per kw
 constexpr int kStSmemBar = 1024;
 constexpr int kStN = 128;
-constexpr uint32_t kStUOff = kStN - 2;
+constexpr uint32_t kStY0 = 2;                        // accumulator column of conv pixel 0
 
 struct StemParams {
   int32_t C, H, W, B;            // input
@@ -115,8 +118,15 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
     const int bias = (ch_ok && p.epi.bias) ? p.epi.bias[co] : 0;
     const int relu_lo = (p.epi.flags & ACCEL_RELU) ? 0 : INT_MIN;
     const bool sat_on = p.epi.sat_count != nullptr;
-    int lo_c = INT_MIN, hi_c = INT_MAX;
-    if (sat_on && ch_ok) ws_sat_bounds(sf, lo_c, hi_c);
+    // clipped  <=>  max(a + bias, relu_lo) outside [lo_c, hi_c]  <=>  a > hi_a or a < lo_a  (a = raw accumulator)
+    int lo_a = INT_MIN, hi_a = INT_MAX;
+    if (sat_on && ch_ok) {
+      int lo_c, hi_c;
+      ws_sat_bounds(sf, lo_c, hi_c);
+      const long long h = static_cast<long long>(hi_c) - bias, l = static_cast<long long>(lo_c) - bias;
+      hi_a = hi_c < relu_lo ? INT_MIN : static_cast<int>(min(max(h, static_cast<long long>(INT_MIN)), static_cast<long long>(INT_MAX)));
+      lo_a = relu_lo >= lo_c ? INT_MIN : static_cast<int>(min(max(l, static_cast<long long>(INT_MIN)), static_cast<long long>(INT_MAX)));
+    }
     const int col0 = half ? 64 : 0;                 // first conv column this thread loads (64 columns) and counts
     const int xp_lo = half ? 32 : 0, xp_hi = half ? p.Wp : min(32, p.Wp);       // pooled columns this thread produces
     const bool warp_has_ch = q * 16 < p.c_out;
@@ -140,35 +150,43 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
         ++nrow;
         if (warp_has_ch && !(p.dbg & 1)) {
           const bool count = sat_on && dy >= 0 && img_ok && ch_ok;
-          // eight steps of 8 columns, double buffered: the TMEM loads of step k + 1 are in flight while step k is folded
-          // into the running maxima (a tcgen05.ld round trip costs ~1000 cycles when it is waited for on its own)
-          uint32_t za[8], ua[8], zb[8], ub[8];
-          uint32_t zl = 0u, ul = 0u;
-          if (half) { zl = tmem_ld1(acc + col0 - 1); ul = tmem_ld1(acc + kStUOff + col0); }
-          tmem_ld8(acc + col0, za);
-          tmem_ld8(acc + kStUOff + 1 + col0, ua);
-#define STEM_FOLD(Z, U, J0)                                                                         \
-  _Pragma("unroll") for (int e = 0; e < 8; ++e) {                                                   \
-    const int a = static_cast<int>(Z[e] + U[e]);                                                    \
-    vm[(J0) + e] = max(vm[(J0) + e], a);                                                            \
-    if (count) {                                                                                    \
-      const int t = max(a + bias, relu_lo);                                                         \
-      sat += (col0 + (J0) + e < p.Wc && (t > hi_c || t < lo_c)) ? 1u : 0u;                          \
+          // four steps of 16 columns folded into the running maxima.  Clipping is counted the way conv_ws.cuh does it: the
+          // chunk's accumulator range against per-channel thresholds, an exact recount only when it trips.
+          if (half) {
+            const uint32_t zl = tmem_ld1(acc + kStY0 + col0 - 1);
+            tmem_ld_wait();
+            vleft = max(vleft, static_cast<int>(zl));
+          }
+#define STEM_FOLD(Z, J0)                                                                            \
+  {                                                                                                 \
+    int amax = INT_MIN, amin = INT_MAX;                                                             \
+    _Pragma("unroll") for (int e = 0; e < 16; ++e) {                                                \
+      const int a = static_cast<int>(Z[e]);                                                         \
+      vm[(J0) + e] = max(vm[(J0) + e], a);                                                          \
+      amax = max(amax, a);                                                                          \
+      amin = min(amin, a);                                                                          \
+    }                                                                                               \
+    if (count && (amax > hi_a || amin < lo_a)) {                                                    \
+      _Pragma("unroll") for (int e = 0; e < 16; ++e) {                                              \
+        const int a = static_cast<int>(Z[e]);                                                       \
+        sat += (col0 + (J0) + e < p.Wc && (a > hi_a || a < lo_a)) ? 1u : 0u;                        \
+      }                                                                                             \
     }                                                                                               \
   }
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
+          {
+            uint32_t za[16], zb[16];                 // the TMEM load of step k + 1 is in flight while step k is folded
+            tmem_ld16(acc + kStY0 + col0, za);
             tmem_ld_wait();
-            tmem_ld8(acc + col0 + 8 * (i + 1), zb);
-            tmem_ld8(acc + kStUOff + 1 + col0 + 8 * (i + 1), ub);
-            if (i == 0 && half) vleft = max(vleft, static_cast<int>(zl + ul));
-            STEM_FOLD(za, ua, 8 * i)
+            tmem_ld16(acc + kStY0 + col0 + 16, zb);
+            STEM_FOLD(za, 0)
             tmem_ld_wait();
-            if (i + 2 < 8) {
-              tmem_ld8(acc + col0 + 8 * (i + 2), za);
-              tmem_ld8(acc + kStUOff + 1 + col0 + 8 * (i + 2), ua);
-            }
-            STEM_FOLD(zb, ub, 8 * (i + 1))
+            tmem_ld16(acc + kStY0 + col0 + 32, za);
+            STEM_FOLD(zb, 16)
+            tmem_ld_wait();
+            tmem_ld16(acc + kStY0 + col0 + 48, zb);
+            STEM_FOLD(za, 32)
+            tmem_ld_wait();
+            STEM_FOLD(zb, 48)
           }
 #undef STEM_FOLD
         }
@@ -231,19 +249,19 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
             mbar_wait(&a_full[as], aph);
             tc_fence_after();
             const uint32_t e_lo = b_lo0 | (((a_addr + as * kStStageBytes) >> 4) & 0x3FFFu);
-            const uint32_t o_lo = e_lo + (4096u >> 4);
-            const uint64_t be = (static_cast<uint64_t>(b_hi) << 32) | e_lo, bo = (static_cast<uint64_t>(b_hi) << 32) | o_lo;
+            const uint64_t be = (static_cast<uint64_t>(b_hi) << 32) | e_lo, bo = (static_cast<uint64_t>(b_hi) << 32) | (e_lo + 256u);
+            const uint64_t be1 = (static_cast<uint64_t>(b_hi) << 32) | (e_lo + 512u), bo1 = (static_cast<uint64_t>(b_hi) << 32) | (e_lo + 768u);
             auto wt = [&](int kw) { return (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + kw * (kWsTapBytes >> 4)); };
             if (!(p.dbg & 2)) {
-            // E chunk: kw = 3 (shift 0) initialises Z, kw = 1 (shift -1) initialises U + 2, kw = 5 (shift +1) adds into U
-            mma_i8_ss(z, wt(3), be, idesc, 0u);
-            mma_i8_ss(z + kStUOff + 2, wt(1), be, idesc, 0u);
-            mma_i8_ss(z + kStUOff, wt(5), be, idesc, 1u);
-            // O chunk: kw = 4 (0) -> Z, kw = 0 (-2) -> Z + 2, kw = 2 (-1) -> U + 2, kw = 6 (+1) -> U
-            mma_i8_ss(z, wt(4), bo, idesc, 1u);
-            mma_i8_ss(z + 2, wt(0), bo, idesc, 1u);
-            mma_i8_ss(z + kStUOff + 2, wt(2), bo, idesc, 1u);
-            mma_i8_ss(z + kStUOff, wt(6), bo, idesc, 1u);
+              // conv pixel x lives in column 2 + x.  Unshifted chunks: shift 0 -> +2, shift -2 -> +4.  Chunks shifted right by
+              // one pixel: shift -1 -> +2, shift +1 -> +0.  The first MMA overwrites [2, 130); columns 0, 1, 130, 131 are never read.
+              mma_i8_ss(z + 2, wt(3), be, idesc, 0u);      // E,  kw 3, shift  0
+              mma_i8_ss(z + 2, wt(1), be1, idesc, 1u);     // E1, kw 1, shift -1
+              mma_i8_ss(z + 0, wt(5), be1, idesc, 1u);     // E1, kw 5, shift +1
+              mma_i8_ss(z + 2, wt(4), bo, idesc, 1u);      // O,  kw 4, shift  0
+              mma_i8_ss(z + 4, wt(0), bo, idesc, 1u);      // O,  kw 0, shift -2
+              mma_i8_ss(z + 2, wt(2), bo1, idesc, 1u);     // O1, kw 2, shift -1
+              mma_i8_ss(z + 0, wt(6), bo1, idesc, 1u);     // O1, kw 6, shift +1
             }
             mma_commit(&a_empty[as]);
             if (++as == kStSlots) { as = 0; aph ^= 1u; }
@@ -256,14 +274,14 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
     tc_fence_before();
   } else {
     // =================================================================== loaders: 32 input bytes -> 16 even + 16 odd
-    // Stage s (one conv row of one image) belongs to loader warp s % 6: six stages are in flight, and every lane has
+    // Stage s (one conv row of one image) belongs to loader warp s % 3: three stages are in flight, and every lane has
     // its (up to) five 32-byte units of a stage outstanding at once.
     const int lw = warp - kStWarpLoad;
     const int upr = p.W >> 5;                        // 32-byte units per input row (W % 32 == 0)
     const int n_units = p.C * 7 * upr;
     constexpr int kUnits = 5;                        // ceil(160 / 32): C * 7 * (W / 32) <= 160
-    uint32_t soff[kUnits];
-    int32_t goff[kUnits], ukh[kUnits];
+    uint32_t soff[kUnits], stail[kUnits];
+    int32_t goff[kUnits], ukh[kUnits], ufirst[kUnits];     // ufirst: 1 = first unit of its row, 2 = last, 0 = inner (3 = both)
 #pragma unroll
     for (int k = 0; k < kUnits; ++k) {
       const int un = lane + 32 * k;
@@ -271,8 +289,10 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
       const int rowid = has ? un / upr : 0, u = has ? un - rowid * upr : 0;
       const int c = rowid / 7, kh = rowid - c * 7;
       soff[k] = static_cast<uint32_t>(rowid) * 128u + ((static_cast<uint32_t>(u) ^ (rowid & 7)) << 4);
+      stail[k] = static_cast<uint32_t>(rowid) * 128u + ((static_cast<uint32_t>(u + 1) ^ (rowid & 7)) << 4);
       goff[k] = (c * p.H + kh - 3) * p.in_pitch + 32 * u;       // + 2 * yc * pitch
       ukh[k] = has ? kh : -1000;
+      ufirst[k] = (u == 0 ? 1 : 0) | (u == upr - 1 ? 2 : 0);
     }
     uint32_t sidx = 0;                               // running stage number (identical in the issuer)
     for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -288,11 +308,16 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
           const int8_t* src = p.x + static_cast<int64_t>(2u * pr + sub) * p.C * p.H * p.in_pitch +
                               static_cast<int64_t>(2 * yc) * p.in_pitch;
           uint4 lo[kUnits], hi[kUnits];
+          uint32_t pv[kUnits];                        // the four input bytes left of the unit (its last two feed the shifted copies)
 #pragma unroll
           for (int k = 0; k < kUnits; ++k) {
             const int r = 2 * yc + ukh[k] - 3;
-            lo[k] = make_uint4(0u, 0u, 0u, 0u); hi[k] = lo[k];
-            if (r >= 0 && r < p.H && !(p.dbg & 4)) { lo[k] = ldg128(src + goff[k]); hi[k] = ldg128(src + goff[k] + 16); }
+            lo[k] = make_uint4(0u, 0u, 0u, 0u); hi[k] = lo[k]; pv[k] = 0u;
+            if (r >= 0 && r < p.H && !(p.dbg & 4)) {
+              lo[k] = ldg128(src + goff[k]);
+              hi[k] = ldg128(src + goff[k] + 16);
+              if (!(ufirst[k] & 1)) pv[k] = *reinterpret_cast<const uint32_t*>(src + goff[k] - 4);
+            }
           }
           mbar_wait(&a_empty[as], aph ^ 1u);
           uint8_t* dst = smem + kStSmemBar + kStWBytes + as * kStStageBytes;
@@ -303,8 +328,19 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
                                         __byte_perm(hi[k].x, hi[k].y, 0x6420), __byte_perm(hi[k].z, hi[k].w, 0x6420));
             const uint4 od = make_uint4(__byte_perm(lo[k].x, lo[k].y, 0x7531), __byte_perm(lo[k].z, lo[k].w, 0x7531),
                                         __byte_perm(hi[k].x, hi[k].y, 0x7531), __byte_perm(hi[k].z, hi[k].w, 0x7531));
+            // shifted right by one pixel: byte 0 comes from the unit on the left (zero at the image edge)
+            const uint4 ev1 = make_uint4(__byte_perm(pv[k], ev.x, 0x6542), __funnelshift_l(ev.x, ev.y, 8), __funnelshift_l(ev.y, ev.z, 8),
+                                         __funnelshift_l(ev.z, ev.w, 8));
+            const uint4 od1 = make_uint4(__byte_perm(pv[k], od.x, 0x6543), __funnelshift_l(od.x, od.y, 8), __funnelshift_l(od.y, od.z, 8),
+                                         __funnelshift_l(od.z, od.w, 8));
             *reinterpret_cast<uint4*>(dst + soff[k]) = ev;
             *reinterpret_cast<uint4*>(dst + soff[k] + 4096) = od;
+            *reinterpret_cast<uint4*>(dst + soff[k] + 8192) = ev1;
+            *reinterpret_cast<uint4*>(dst + soff[k] + 12288) = od1;
+            if (ufirst[k] & 2) {                       // last unit of the row: pixel 16 * upr of the shifted copies
+              *reinterpret_cast<uint4*>(dst + stail[k] + 8192) = make_uint4(ev.w >> 24, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(dst + stail[k] + 12288) = make_uint4(od.w >> 24, 0u, 0u, 0u);
+            }
           }
           fence_proxy_async_smem();                  // generic-proxy stores -> visible to tcgen05.mma
           mbar_arrive(&a_full[as]);
