@@ -34,10 +34,10 @@ constexpr int kWsWarpIssue = kWsEpiWarps;          // 8: MMA issuer (+ TMEM allo
 constexpr int kWsWarpWeights = kWsWarpIssue + 1;   // 9: weight tiles by bulk copy (its own warp: it must never hold back
                                                    //    the activation loaders, or the two rings deadlock)
 constexpr int kWsWarpLoad = kWsWarpWeights + 1;    // 10, 11: activation loaders (LDGSTS)
-constexpr int kWsLoadWarps = 6;
+constexpr int kWsLoadWarps = 2;
 constexpr int kWsLoadThreads = kWsLoadWarps * 32;  // 64
 constexpr int kWsThreads = (kWsWarpLoad + kWsLoadWarps) * 32;   // 384
-constexpr int kWsLoadOps = 3;                      // 16-byte copies per loader thread and stage (<= 512 per stage)
+constexpr int kWsLoadOps = 8;                      // 16-byte copies per loader thread and stage (<= 512 per stage)
 constexpr int kWsCo = 128;                         // output channels per group (TMEM lanes)
 constexpr int kWsCk = 32;                          // input channels per chunk (one MMA K)
 constexpr int kWsTapBytes = kWsCo * kWsCk;         // 4096
