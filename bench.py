@@ -13,8 +13,8 @@ by GPU (weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
              between timed steps, CUDA-event time, max over ranks.
   e2e        same metric through the public API with HOST buffers: pinned-host -> device copy of
              the int8 images and device -> host read of the INT32 logits inside the timed region.
-  roofline   the tensor-core convolution / FC launches of one step (conv_ws_kernel for the 3x3 layers, bsr_tcp_kernel /
-             bsr_tc_kernel for the stem and the FC): algorithmic bytes / event-timed duration vs the measured HBM
+  roofline   the tensor-core convolution / FC launches of one step (conv_ws_kernel for the 3x3 layers, stem_ws_kernel for
+             conv1 + max-pool, bsr_tcp_kernel for the FC): algorithmic bytes / event-timed duration vs the measured HBM
              peak (MEASURED_PEAKS.json); `traffic` = DRAM bytes of the same launches from the committed ncu capture
              (profiles/r01_traffic.json, written by tools/ncu_launches.py).
   cpu_baseline  the reference's C++ golden path (oracle/_ref: conv2d_int8_im2col + relu_int32 +
@@ -323,9 +323,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": (traffic or {}).get("conv_fc_dram_bytes_per_step"),
                          "traffic_source": (traffic or {}).get("source"), "peak_source": src,
-                         "kernel": f"conv_ws_kernel (3x3 layers) + bsr_tcp_kernel / bsr_tc_kernel (stem, fc): "
-                                   f"{sum(1 for n in conv_names if n not in net.fused_ds.values())} launches per step, "
-                                   "algorithmic bytes and time summed over them",
+                         "kernel": f"conv_ws_kernel (3x3 layers, downsamples fused) + stem_ws_kernel (conv1 + max-pool) + "
+                                   f"bsr_tcp_kernel (fc): {sum(1 for n in conv_names if n not in net.fused_ds.values())} "
+                                   "launches per step; algorithmic bytes of the reference's layer sequence (unfused) over "
+                                   "the event-timed eager forward",
                          "useful_tops": ach_tops, "tensor_frac_of_2x_bf16_sustained": ach_tops / int8_peak_tops,
                          "kernel_ms_per_step": kms, "algorithmic_bytes_per_step": conv_bytes,
                          "useful_ops_per_step": conv_ops},
