@@ -45,7 +45,7 @@ constexpr int kWsChunkBytes = 9 * kWsTapBytes;     // 36864
 constexpr int kWsMaxChunks = 16;                   // Cin <= 512
 constexpr int kWsMaxGroups = 8;                    // Cout <= 1024
 constexpr int kWsMaxWSlots = 4;                    // resident: Cin <= 128; else a ring of this many chunk slots
-constexpr int kWsMaxASlots = 8;
+constexpr int kWsMaxASlots = 16;
 constexpr int kWsAccCols = 256;                    // per accumulator set: Z1 [0, N), U [N-2, 2N)
 constexpr int kWsSmemBar = 1024;                   // barriers + TMEM slot in front of the operand areas
 

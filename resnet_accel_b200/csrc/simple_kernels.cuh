@@ -415,34 +415,40 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_i8_x16_kernel(const int8_t* 
     }
   }
 }
-// one warp per plane: (sum + HW/2) / HW with C truncating division (golden_models.cpp:619)
+// eight lanes per plane (four planes per warp): (sum + HW/2) / HW with C truncating division (golden_models.cpp:619)
 __global__ void avgpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out, int64_t n_planes,
                                   int32_t H, int32_t W, int32_t in_pitch) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  const int64_t grp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 3;
+  const int64_t ngrp = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 3;
   const int hw = H * W;
   // rows that are 4-byte aligned words: one 32-bit load per 4 columns, packed byte sums by dp4a
   const bool words = (in_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0;
   const int wpr = (W + 3) >> 2;                        // words per row
-  for (int64_t pl = warp0; pl < n_planes; pl += nwarps) {
+  const int64_t n_iter = (n_planes + ngrp - 1) / ngrp;
+  for (int64_t itn = 0; itn < n_iter; ++itn) {         // uniform trip count: the shuffles below need the whole warp
+    const int64_t pl = grp0 + itn * ngrp;
     int s = 0;
-    if (words) {
-      for (int i = lane; i < H * wpr; i += 32) {
-        const int r = i / wpr, wi = i - r * wpr;
-        uint32_t v = *reinterpret_cast<const uint32_t*>(x + (pl * H + r) * in_pitch + 4 * wi);
-        const int nv = W - 4 * wi;
-        if (nv < 4) v &= (1u << (8 * nv)) - 1u;
-        s = __dp4a(static_cast<int>(v), 0x01010101, s);
-      }
-    } else {
-      for (int i = lane; i < hw; i += 32) {
-        const int r = i / W;
-        s += x[(pl * H + r) * in_pitch + (i - r * W)];
+    if (pl < n_planes) {
+      if (words) {
+        for (int i = sub; i < H * wpr; i += 8) {
+          const int r = i / wpr, wi = i - r * wpr;
+          uint32_t v = *reinterpret_cast<const uint32_t*>(x + (pl * H + r) * in_pitch + 4 * wi);
+          const int nv = W - 4 * wi;
+          if (nv < 4) v &= (1u << (8 * nv)) - 1u;
+          s = __dp4a(static_cast<int>(v), 0x01010101, s);
+        }
+      } else {
+        for (int i = sub; i < hw; i += 8) {
+          const int r = i / W;
+          s += x[(pl * H + r) * in_pitch + (i - r * W)];
+        }
       }
     }
-    s = __reduce_add_sync(0xffffffffu, s);
-    if (lane == 0) out[pl] = static_cast<int8_t>(min(127, max(-128, (s + hw / 2) / hw)));
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (sub == 0 && pl < n_planes) out[pl] = static_cast<int8_t>(min(127, max(-128, (s + hw / 2) / hw)));
   }
 }
 

@@ -168,7 +168,7 @@ class BsrNetwork:
                 if sp.kind in ("conv", "fc"):
                     syn = synthetic_conv_weights(sp, sparsity_pct, idx, bias_range)
                     self.layers[sp.name] = BsrLayer(sp, syn["w2"], bias=syn["bias"],
-                                                    group_rows=(8 if sp.kind == "fc" else 0))
+                                                    group_rows=(int(__import__('os').environ.get('ACCEL_FC_GROUP_ROWS', 8)) if sp.kind == "fc" else 0))
                     idx += 1
         self.buffers: Dict[str, torch.Tensor] = {}
         self.sat = torch.zeros(1, dtype=torch.int64, device="cuda")

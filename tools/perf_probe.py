@@ -39,17 +39,27 @@ def main():
         torch.cuda.synchronize()
         work = net.work()
         tot = 0.0
+        xin = ops.alloc_padded(tuple(x.shape))
+        xin.copy_(x)
         for sp, wl in zip(net.specs, work["layers"]):
-            sub = L.BsrNetwork.__new__(L.BsrNetwork)
-            sub.__dict__.update(net.__dict__)
-            sub.specs = [sp]
-            src = x if sp.name == "conv1" else net.buffers[sp.src or net.specs[net.specs.index(sp) - 1].name]
+            if sp.name in net.fused_pool.values() or sp.name in net.fused_ds.values():
+                continue                      # timed with the layer it is fused into
+            prev_name = net.specs[net.specs.index(sp) - 1].name if net.specs.index(sp) else None
+            src = xin if sp.name == "conv1" else net.buffers[sp.src or prev_name]
 
             def run(sp=sp, src=src):
                 t = {"input": src}
                 t.update(net.buffers)
                 Lr = net.layers.get(sp.name)
+                if sp.name in net.fused_pool:
+                    ops.conv_pool(Lr.plan, src, sp.c_out, chan_scale=Lr.sf, relu=True, out=net.buffers[net.fused_pool[sp.name]])
+                    return
                 out = net.buffers[sp.name]
+                if sp.name in net.fused_ds:
+                    D = net.layers[net.fused_ds[sp.name]]
+                    ops.conv_dual(Lr.plan, D.plan, src, sp.c_out, chan_scale=Lr.sf, chan_scale_ds=D.sf, relu=True, relu_ds=False,
+                                  out=out, out_ds=net.buffers[net.fused_ds[sp.name]])
+                    return
                 if sp.kind == "conv":
                     if sp.residual:
                         Lr.plan.conv(src, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=Lr.sf, residual=t[sp.residual],
@@ -67,7 +77,8 @@ def main():
             tops = wl["ops"] / ms / 1e9
             gbs = wl["bytes"] / ms / 1e6
             mma = net.layers[sp.name].plan.num_mma if sp.name in net.layers else 0
-            print(f"{sp.name:22s} {ms:8.3f} ms  {tops:8.1f} TOPS(useful)  {gbs:8.1f} GB/s  mma/tile={mma}")
+            tag = sp.name + ("+pool" if sp.name in net.fused_pool else "+ds" if sp.name in net.fused_ds else "")
+            print(f"{tag:22s} {ms:8.3f} ms  {tops:8.1f} TOPS(useful)  {gbs:8.1f} GB/s  mma/tile={mma}")
         print(f"sum of layers {tot:.3f} ms -> {batch/tot*1e3:.0f} img/s")
         ms = timeit(lambda: net.forward(x), 5, 2)
         print(f"eager forward {ms:.3f} ms -> {batch/ms*1e3:.0f} img/s")

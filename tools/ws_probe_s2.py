@@ -36,3 +36,15 @@ for st in (2, 3, 4):
     e1.record()
     torch.cuda.synchronize()
     print(f"layer{st}.0 conv1+downsample {e0.elapsed_time(e1) / 20 * 1000:8.1f} us  (dbg={os.environ.get('ACCEL_DBG_FLAGS', '0')})")
+    if os.environ.get("ALONE"):
+        def run2():
+            lay.plan.conv(x, 3, 2, 1, sp.c_out, "i8", chan_scale=lay.sf, relu=True, out=o1, sat_count=cnt)
+        for _ in range(3):
+            run2()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            run2()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"layer{st}.0 conv1 alone (stride 2) {e0.elapsed_time(e1) / 20 * 1000:8.1f} us")
