@@ -60,6 +60,7 @@ long long* g_timeline = nullptr;   // accel_debug_set_timeline
 int g_dbg_flags = 0;
 bool g_no_persist = std::getenv("ACCEL_NO_PERSIST") != nullptr;   // developer switch: one-shot kernel everywhere
 long long g_ws_launches = 0;         // accel_debug_counter(0)
+bool g_ws_s2_streamed = std::getenv("ACCEL_WS_S2_STREAMED") != nullptr;   // developer switch: allow stride 2 with streamed weights
 bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
@@ -315,6 +316,9 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   if (!(epi->flags & ACCEL_OUT_I8) || epi->chan_absmax) return kWsNotApplicable;
   const int stride = g->stride;
   if (stride == 2 && ((g->h | g->w) & 1 || epi->residual)) return kWsNotApplicable;
+  // stride 2 with streamed weights (Cin > 128) measures slower than the gather kernels (layer4.0 of ResNet-18: 168 us
+  // fused against 67 + 62 us): the 64-pixel tiles re-stream every weight chunk twice per image.  Not taken until fixed.
+  if (stride == 2 && W.n_chunks > accel::kWsMaxWSlots && !g_ws_s2_streamed) return kWsNotApplicable;
   if (plan_ds) {
     const WsState& D = plan_ds->ws;
     if (stride != 2 || !D.ready || D.taps != 1 || D.c_in != W.c_in || D.c_out != W.c_out || !epi_ds || !out_ds) return kWsNotApplicable;

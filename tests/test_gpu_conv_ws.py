@@ -103,7 +103,7 @@ def test_conv_ws_dense_layout_and_fallback():
     assert np.array_equal(got, ref)
 
 
-def _s2_case(B, Cin, H, W, Cout, density, seed, with_ds=True):
+def _s2_case(B, Cin, H, W, Cout, density, seed, with_ds=True, expect_ws=True):
     import torch
     from resnet_accel_b200 import _lib, ops
     from resnet_accel_b200.ops import BsrPlan
@@ -140,7 +140,7 @@ def _s2_case(B, Cin, H, W, Cout, density, seed, with_ds=True):
     else:
         plan3.conv(xd, 3, 2, 1, Cout, "i8", chan_scale=sf3, bias=bias3, relu=True, out=out3, sat_count=cnt)
     torch.cuda.synchronize()
-    assert _lib.lib().accel_debug_counter(0) == before + 1, "the weight-stationary kernel did not run"
+    assert _lib.lib().accel_debug_counter(0) == before + (1 if expect_ws else 0), "unexpected kernel choice"
     ref3, sat3 = c_oracle.conv_bsr_layer(x, bsr3["indptr"], bsr3["indices"], bsr3["data"], Cout, 3, 2, 1, bias=bias3, relu=True, sf=sf3)
     assert np.array_equal(out3.cpu().numpy(), ref3)
     sat = sat3
@@ -163,7 +163,8 @@ def _s2_case(B, Cin, H, W, Cout, density, seed, with_ds=True):
     (2, 64, 12, 60, 70, 0.1),        # wide rows, very sparse
 ])
 def test_conv_ws_stride2_with_downsample(B, Cin, H, W, Cout, density):
-    _s2_case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W)
+    # Cin > 128 (streamed weights) is routed to the gather kernels for stride 2: same call, same results
+    _s2_case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W, expect_ws=Cin <= 128)
 
 
 def test_conv_ws_stride2_alone():
