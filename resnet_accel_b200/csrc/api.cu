@@ -111,15 +111,17 @@ int check_epilogue(const accel_epilogue* epi, const accel_out_layout* lay, const
 //   q0 = s * rcp;  e = fma(-q0, s_out, s);  q = fma(e, rcp, q0)      with rcp = RN(1 / s_out)
 // when that reproduces the reference's int8 result for EVERY (main, residual) int8 pair - decided here,
 // once per scale triple, by exhaustive comparison with the true quotient.
-bool residual_fast_divide_ok(float s_main, float s_res, float s_out) {
+// Returns 0: IEEE divide needed, 1: the 3-instruction sequence is exact, 2: even the single multiply  q = s * rcp  gives the
+// reference's int8 for every pair (the weight-stationary kernel then drops the two FMAs as well).
+int residual_divide_mode(float s_main, float s_res, float s_out) {
   static std::mutex mu;
-  static std::map<std::array<uint32_t, 3>, bool> cache;
+  static std::map<std::array<uint32_t, 3>, int> cache;
   std::array<uint32_t, 3> key;
   std::memcpy(&key[0], &s_main, 4); std::memcpy(&key[1], &s_res, 4); std::memcpy(&key[2], &s_out, 4);
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
-  bool ok = std::isfinite(s_out) && s_out != 0.f;
+  bool ok = std::isfinite(s_out) && s_out != 0.f, ok_mul = true;
   const float rcp = 1.0f / s_out;
   ok = ok && std::isfinite(rcp);
   auto sat8 = [](float f) {
@@ -133,15 +135,19 @@ bool residual_fast_divide_ok(float s_main, float s_res, float s_out) {
       volatile float sum = am + rr;
       const float s = sum;
       const float truth = s / s_out;
-      const float q0 = s * rcp;
+      volatile float q0v = s * rcp;
+      const float q0 = q0v;
       const float e = std::fmaf(-q0, s_out, s);
       const float q = std::fmaf(e, rcp, q0);
       if (!std::isfinite(truth) || !std::isfinite(q) || sat8(q) != sat8(truth)) { ok = false; break; }
+      if (sat8(q0) != sat8(truth)) ok_mul = false;
     }
   }
-  cache[key] = ok;
-  return ok;
+  const int mode = !ok ? 0 : (ok_mul ? 2 : 1);
+  cache[key] = mode;
+  return mode;
 }
+bool residual_fast_divide_ok(float s_main, float s_res, float s_out) { return residual_divide_mode(s_main, s_res, s_out) >= 1; }
 
 // ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda needed)
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -390,7 +396,7 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   p.x = input; p.in_pitch = static_cast<int32_t>(in_pitch);
   p.epi = *epi;
   if (epi->residual) {
-    p.res_fast = residual_fast_divide_ok(epi->res_scale_main, epi->res_scale_res, epi->res_scale_out) ? 1 : 0;
+    p.res_fast = residual_divide_mode(epi->res_scale_main, epi->res_scale_res, epi->res_scale_out);
     p.res_rcp = 1.0f / epi->res_scale_out;
   }
   p.out = static_cast<int8_t*>(out);

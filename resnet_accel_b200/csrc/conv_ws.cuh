@@ -62,7 +62,7 @@ struct WsParams {
   FastDiv d_tpi;
   const uint8_t* wblob;        // [group][chunk][tap][4096]
   accel_epilogue epi;
-  int32_t res_fast;
+  int32_t res_fast;            // residual divide: 0 IEEE, 1 exact 3-instruction sequence, 2 single multiply (verified on the host)
   float res_rcp;
   int8_t* out;
   int32_t out_pitch;           // bytes between output rows
@@ -188,7 +188,9 @@ __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)
         const float r = __fmul_rn(rf, p.epi.res_scale_res);
         const float sm = __fadd_rn(a, r);
         float d;
-        if constexpr (RESMODE == 1) {      // exact for every (int8, int8) pair: verified on the host
+        if constexpr (RESMODE == 3) {      // the multiply alone already rounds to the reference's int8 for every pair
+          d = __fmul_rn(sm, p.res_rcp);
+        } else if constexpr (RESMODE == 1) {      // exact for every (int8, int8) pair: verified on the host
           const float q0 = __fmul_rn(sm, p.res_rcp);
           const float er = __fmaf_rn(-q0, p.epi.res_scale_out, sm);
           d = __fmaf_rn(er, p.res_rcp, q0);
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     kc.out_lo = (p.epi.flags & ACCEL_RELU_OUT) ? 0 : -128;
     kc.lo_c = INT_MIN; kc.hi_c = INT_MAX;
     if (sat_on && ch_ok) ws_sat_bounds(sf, kc.lo_c, kc.hi_c);
-    const int resmode = !p.epi.residual ? 0 : (p.res_fast ? 1 : 2);
+    const int resmode = !p.epi.residual ? 0 : (p.res_fast == 2 ? 3 : (p.res_fast == 1 ? 1 : 2));
     const int variant = resmode * 2 + (sat_on ? 1 : 0);
     WsEpiRole er;
     er.item0 = item0; er.item_step = item_step; er.n_items = n_items; er.n_tiles = n_tiles; er.dual = dual; er.sub = sub;
@@ -486,7 +488,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       case 2: sat = ws_epi_loop<1, false>(p, er, kc, lane); break;
       case 3: sat = ws_epi_loop<1, true>(p, er, kc, lane); break;
       case 4: sat = ws_epi_loop<2, false>(p, er, kc, lane); break;
-      default: sat = ws_epi_loop<2, true>(p, er, kc, lane); break;
+      case 5: sat = ws_epi_loop<2, true>(p, er, kc, lane); break;
+      case 6: sat = ws_epi_loop<3, false>(p, er, kc, lane); break;
+      default: sat = ws_epi_loop<3, true>(p, er, kc, lane); break;
     }
     if (sat_on) {
       const uint32_t wsum = __reduce_add_sync(0xffffffffu, sat);
