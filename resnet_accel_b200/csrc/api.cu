@@ -61,6 +61,7 @@ int g_dbg_flags = 0;
 bool g_no_persist = std::getenv("ACCEL_NO_PERSIST") != nullptr;   // developer switch: one-shot kernel everywhere
 long long g_ws_launches = 0;         // accel_debug_counter(0)
 bool g_ws_s2_streamed = std::getenv("ACCEL_WS_S2_STREAMED") != nullptr;   // developer switch: allow stride 2 with streamed weights
+bool g_no_twin = std::getenv("ACCEL_NO_TWIN") != nullptr;          // developer switch: one image per tile even for 7-pixel rows
 bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
@@ -85,7 +86,10 @@ void set_kernel_attrs() {
       g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPersist);
   }
   if (g_attr_err == cudaSuccess)
-    g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::conv_ws_kernel),
+    g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::conv_ws_kernel<false>),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
+  if (g_attr_err == cudaSuccess)
+    g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::conv_ws_kernel<true>),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
   if (g_attr_err == cudaSuccess)
     g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::stem_ws_kernel),
@@ -368,12 +372,18 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   }
   p.R = best_r; p.N = p.R * P;
   p.stride = stride; p.Ho = Ho; p.Wo = Wo;
+
   p.rows_in = stride == 2 ? 2 * p.R + 1 : p.R + 2;
   p.has_ds = plan_ds ? 1 : 0;
   p.w_chunk_bytes = accel::kWsChunkBytes + (plan_ds ? accel::kWsTapBytes : 0);
   p.n_chunks = W.n_chunks; p.n_groups = W.n_groups; p.c_out = W.c_out;
   p.tiles_per_image = (Ho + p.R - 1) / p.R;
-  const int64_t n_tiles = static_cast<int64_t>(g->batch) * p.tiles_per_image;
+  // 16-pixel rows with <= 7 valid pixels (layer4 of ResNet-18): two images side by side in every staged row
+  p.twin = (stride == 1 && P == 16 && Wd <= 7 && W.c_out > 64 && g->batch >= 2 && !g_no_twin &&
+            static_cast<int64_t>(g->c_in) * H * in_pitch < (1ll << 30)) ? 1 : 0;
+  p.u_alias = p.twin ? 0 : 1;      // twin tiles end in a valid pixel of the second image: U cannot alias Z1's tail (N <= 112)
+  p.u_off = p.u_alias ? p.N - 2 : p.N;
+  const int64_t n_tiles = static_cast<int64_t>(p.twin ? (g->batch + 1) / 2 : g->batch) * p.tiles_per_image;
   if (n_tiles > INT_MAX) return kWsNotApplicable;
   p.n_tiles = static_cast<int32_t>(n_tiles);
   p.w_resident = W.n_chunks <= accel::kWsMaxWSlots ? 1 : 0;
@@ -418,7 +428,8 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   if (per_group > n_items) per_group = n_items;
   if (per_group < 1) return kWsNotApplicable;
   const int smem = fixed + p.a_slots * p.a_stage_bytes;
-  accel::conv_ws_kernel<<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);
+  if (p.twin) accel::conv_ws_kernel<true><<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);
+  else accel::conv_ws_kernel<false><<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_ws_kernel launch");
   ++g_ws_launches;

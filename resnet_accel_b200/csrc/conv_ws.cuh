@@ -57,6 +57,10 @@ struct WsParams {
   int32_t w_slots, w_resident, a_slots, a_stage_bytes, a_box_bytes;
   const int8_t* x;             // input tensor, rows of in_pitch bytes
   int32_t in_pitch;
+  int32_t u_off, u_alias;      // U = Z1 + u_off.  N = 128 (or stride 2): u_off = N - 2, U's first two columns alias Z1's last two
+                               // (padding pixels, exact zeros).  Smaller N: u_off = N, nothing aliases.
+  int32_t twin;                // W <= 7 (16-pixel rows): a staged row holds row y of TWO images, [A0..A6 0 B0..B6 0]: the zero
+                               // column between them is the padding of both, and a tile carries two images
   int32_t dual;                // c_out <= 64: items are pairs of pixel tiles, two interleaved M = 64 accumulators
   uint32_t b_layout, b_lbo, b_sbo, row_stride;
   FastDiv d_tpi;
@@ -227,7 +231,7 @@ struct WsChunk {           // one 16-pixel chunk of this thread's channel
 };
 __device__ __forceinline__ void ws_chunk_load(const WsParams& p, uint32_t acc, const WsChunk& c, uint32_t (&z)[16], uint32_t (&u)[16]) {
   tmem_ld16(acc + c.p0, z);
-  tmem_ld16(acc + (p.N - 2) + 1 + c.p0, u);
+  tmem_ld16(acc + p.u_off + 1 + c.p0, u);
 }
 struct WsEpiConst {        // per-thread (= per-channel) constants of the epilogue
   int bias, relu_lo, out_lo, lo_c, hi_c;
@@ -309,6 +313,16 @@ __device__ __forceinline__ void ws_epi_tile(const WsParams& p, uint32_t acc, con
   tmem_ld_wait();
 }
 
+__device__ __forceinline__ void stg64(void* p, const uint2& v) {
+  asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+// Twin tiles (WsParams::twin): every 16-pixel chunk is one row of two images, 8 bytes each.  Unpipelined: these layers
+// are 7x7 images, the epilogue is a small part of them.
+__device__ __forceinline__ uint2 ldg64(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
 // ---- stride-2 epilogue: 16 full-resolution pixels -> the 8 even ones -> 8 output bytes
 template <bool SAT>
 __device__ __forceinline__ uint2 ws_epi8_even(const uint32_t (&z)[16], const uint32_t* u, const WsEpiConst& k, int n_valid, bool lane_ok,
@@ -322,9 +336,6 @@ __device__ __forceinline__ uint2 ws_epi8_even(const uint32_t (&z)[16], const uin
     q[e] = e < n_valid ? max(static_cast<int>(cvt_sat_s8(f)), k.out_lo) : 0;
   }
   return make_uint2(pack4_s8(q[0], q[1], q[2], q[3]), pack4_s8(q[4], q[5], q[6], q[7]));
-}
-__device__ __forceinline__ void stg64(void* p, const uint2& v) {
-  asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
 // The epilogue role of one warp for the whole launch (instantiated per variant: the variant is chosen once, outside the loop).
@@ -360,6 +371,59 @@ __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRo
   return sat;
 }
 
+template <int RESMODE, bool SAT>
+__device__ __forceinline__ uint32_t ws_epi_loop_twin(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, int lane) {
+  uint32_t sat = 0, n = 0;
+  const uint64_t keep64 = p.W >= 8 ? ~0ull : ((1ull << (8 * p.W)) - 1ull);
+  const uint32_t keep_lo = static_cast<uint32_t>(keep64), keep_hi = static_cast<uint32_t>(keep64 >> 32);
+  for (uint32_t it = r.item0; it < r.n_items; it += r.item_step, ++n) {
+    const uint32_t pr = fdiv(it, p.d_tpi);
+    const int y0 = static_cast<int>(it - pr * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
+    const uint32_t img_a = 2u * pr;
+    const bool ok_a = r.ch_ok, ok_b = r.ch_ok && img_a + 1u < static_cast<uint32_t>(p.B);
+    const uint32_t ab = n & 1u;
+    const uint32_t acc = r.tmem_acc + ab * kWsAccCols;
+    const int64_t obase = static_cast<int64_t>(img_a) * p.image_stride + static_cast<int64_t>(r.co) * p.chan_stride;
+    mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
+    tc_fence_after();
+    if (r.warp_has_ch && !(p.dbg & 1)) {
+      for (int k = 0; k < kWsMaxMyChunks; ++k) {
+        const int i = 2 * (r.half + 2 * (k >> 1)) + (k & 1);         // chunk = staged row i of the tile
+        if (i >= r.n_c16) break;
+        if (y0 + i >= p.H) continue;
+        const int64_t off_a = obase + static_cast<int64_t>(y0 + i) * p.out_pitch, off_b = off_a + p.image_stride;
+        uint32_t z[16], u[16];
+        tmem_ld16(acc + 16 * i, z);
+        tmem_ld16(acc + p.u_off + 1 + 16 * i, u);
+        uint4 rb = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (RESMODE != 0) {
+          if (ok_a) { const uint2 t = ldg64(p.epi.residual + off_a); rb.x = t.x; rb.y = t.y; }
+          if (ok_b) { const uint2 t = ldg64(p.epi.residual + off_b); rb.z = t.x; rb.w = t.y; }
+        }
+        tmem_ld_wait();
+        int amin = INT_MAX, amax = INT_MIN;
+        const uint4 o = ws_epi16<RESMODE, SAT>(p, z, u, kc.bias, kc.sf, kc.relu_lo, kc.out_lo, rb, amin, amax);
+        if constexpr (SAT) {
+          if (r.ch_ok && (amax > kc.hi_c || amin < kc.lo_c)) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int a = max(static_cast<int>(z[e] + u[e]) + kc.bias, kc.relu_lo);
+              const float f = __fmul_rn(__int2float_rn(a), kc.sf);
+              sat += ((e & 7) < p.W && (e < 8 ? ok_a : ok_b) && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
+            }
+          }
+        }
+        if (ok_a) stg64(p.out + off_a, make_uint2(o.x & keep_lo, o.y & keep_hi));
+        if (ok_b) stg64(p.out + off_b, make_uint2(o.z & keep_lo, o.w & keep_hi));
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&r.acc_empty[ab]);
+  }
+  return sat;
+}
+
 template <bool SAT>
 __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, const WsEpiConst& kc2,
                                                    int lane) {
@@ -381,7 +445,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEp
         if (y0 + row >= p.Ho || x0 >= p.x_store_end) continue;                // warp-uniform
         uint32_t z[16], u[16], v[16];
         tmem_ld16(acc + p0, z);
-        tmem_ld16(acc + (p.N - 2) + 1 + p0, u);
+        tmem_ld16(acc + p.u_off + 1 + p0, u);
         if (p.has_ds) tmem_ld16(acc + kWsVCol + p0, v);
         tmem_ld_wait();
         const int n_valid = max(0, min(8, p.Wo - x0));
@@ -401,6 +465,9 @@ __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEp
   return sat;
 }
 
+// TWIN: the twin-tile variant (WsParams::twin) is its own instantiation, so that its extra code paths (8-byte copies, the
+// twin epilogues, the unaliased U) cost the other layers neither registers nor instruction-cache space.
+template <bool TWIN>
 __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_constant__ WsLaunch L) {
   extern __shared__ uint8_t smem_dyn[];
   const WsParams& p = L.p;
@@ -481,7 +548,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
         kc2.out_lo = (p.epi2.flags & ACCEL_RELU_OUT) ? 0 : -128;
       }
       sat = sat_on ? ws_epi_loop_s2<true>(p, er, kc, kc2, lane) : ws_epi_loop_s2<false>(p, er, kc, kc2, lane);
-    } else
+    } else if constexpr (TWIN) {
+      switch (variant) {
+        case 0: sat = ws_epi_loop_twin<0, false>(p, er, kc, lane); break;
+        case 1: sat = ws_epi_loop_twin<0, true>(p, er, kc, lane); break;
+        case 2: sat = ws_epi_loop_twin<1, false>(p, er, kc, lane); break;
+        case 3: sat = ws_epi_loop_twin<1, true>(p, er, kc, lane); break;
+        case 4: sat = ws_epi_loop_twin<2, false>(p, er, kc, lane); break;
+        case 5: sat = ws_epi_loop_twin<2, true>(p, er, kc, lane); break;
+        case 6: sat = ws_epi_loop_twin<3, false>(p, er, kc, lane); break;
+        default: sat = ws_epi_loop_twin<3, true>(p, er, kc, lane); break;
+      }
+    } else {
     switch (variant) {
       case 0: sat = ws_epi_loop<0, false>(p, er, kc, lane); break;
       case 1: sat = ws_epi_loop<0, true>(p, er, kc, lane); break;
@@ -491,6 +569,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       case 5: sat = ws_epi_loop<2, true>(p, er, kc, lane); break;
       case 6: sat = ws_epi_loop<3, false>(p, er, kc, lane); break;
       default: sat = ws_epi_loop<3, true>(p, er, kc, lane); break;
+    }
     }
     if (sat_on) {
       const uint32_t wsum = __reduce_add_sync(0xffffffffu, sat);
@@ -506,7 +585,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       const uint32_t b_lo0 = static_cast<uint32_t>(bdesc0);
       const uint32_t a_lo0 = static_cast<uint32_t>(adesc0);
       const uint32_t row16 = p.row_stride >> 4;
-      const uint32_t u_off = static_cast<uint32_t>(p.N - 2);
+      const uint32_t u_off = static_cast<uint32_t>(p.u_off);
+      // the first U-type MMA of a tile overwrites: with aliasing it must be the shifted one (kw = 0 at U + 2, so that the
+      // aliased columns keep Z1's zeros), without aliasing the unshifted one (kw = 2 at U + 0, which covers U's first columns)
+      constexpr bool alias = !TWIN;
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0;
       for (uint32_t it = item0; it < n_items; it += item_step, ++n) {
         const uint32_t ab = n & 1u;
@@ -539,12 +621,21 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
                 mma_i8_ss(z1, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 1) * (kWsTapBytes >> 4)), bd, idesc, z_on);
                 z_on = 1u;
               }
-              if (mask & (1u << (kh * 3 + 0))) {
-                mma_i8_ss(z1 + u_off + 2, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 0) * (kWsTapBytes >> 4)), bd, idesc, u_on);
-                u_on = 1u;
+              if (alias) {       // kw = 0 (U + 2) first: it overwrites, the aliased columns keep Z1's zeros
+                if (mask & (1u << (kh * 3 + 0))) {
+                  mma_i8_ss(z1 + u_off + 2, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 0) * (kWsTapBytes >> 4)), bd, idesc, u_on);
+                  u_on = 1u;
+                }
+                if (mask & (1u << (kh * 3 + 2)))
+                  mma_i8_ss(z1 + u_off, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 2) * (kWsTapBytes >> 4)), bd, idesc, 1u);
+              } else {           // kw = 2 (U + 0) first: it covers U's first columns
+                if (mask & (1u << (kh * 3 + 2))) {
+                  mma_i8_ss(z1 + u_off, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 2) * (kWsTapBytes >> 4)), bd, idesc, u_on);
+                  u_on = 1u;
+                }
+                if (mask & (1u << (kh * 3 + 0)))
+                  mma_i8_ss(z1 + u_off + 2, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 0) * (kWsTapBytes >> 4)), bd, idesc, 1u);
               }
-              if (mask & (1u << (kh * 3 + 2)))
-                mma_i8_ss(z1 + u_off, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 2) * (kWsTapBytes >> 4)), bd, idesc, 1u);
               if (kh == 1 && p.has_ds && (p.masks2[g * kWsMaxChunks + j] & 1u) && !(p.dbg & 2)) {   // fused 1x1 / stride 2
                 mma_i8_ss(z1 + kWsVCol, (static_cast<uint64_t>(a_hi) << 32) | (wl + 9 * (kWsTapBytes >> 4)), bd, idesc, v_on);
                 v_on = 1u;
@@ -571,20 +662,25 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     // several times faster and zero-fill the padding just the same.
     const int lt = static_cast<int>(threadIdx.x) - kWsWarpLoad * 32;           // 0..191
     const int x16s = p.P >> 4, rows = p.rows_in;
-    const int n_ops = kWsCk * rows * x16s;
-    uint32_t soff[kWsLoadOps];
-    int32_t goff[kWsLoadOps], yrow[kWsLoadOps], nbytes[kWsLoadOps];
+    const int n_ops = kWsCk * rows * (p.twin ? 2 : x16s);
+    constexpr int kOps = TWIN ? kWsLoadOps + 1 : kWsLoadOps;      // twin tiles: 576 eight-byte copies per stage
+    uint32_t soff[kOps];
+    int32_t goff[kOps], yrow[kOps], nbytes[kOps];
 #pragma unroll
-    for (int k = 0; k < kWsLoadOps; ++k) {
+    for (int k = 0; k < kOps; ++k) {
       const int o = lt + kWsLoadThreads * k;
-      const int xq = o % x16s, y = (o / x16s) % rows, c = o / (x16s * rows);
-      uint32_t so = static_cast<uint32_t>(y) * p.row_stride + static_cast<uint32_t>(c * p.P + xq * 16);
+      // twin: xq = which image of the pair (8 bytes each inside the 16-byte row), else the 16-byte column of the row
+      const int xq = TWIN ? (o & 1) : o % x16s, y = TWIN ? (o >> 1) % rows : (o / x16s) % rows,
+                c = TWIN ? (o >> 1) / rows : o / (x16s * rows);
+      uint32_t so = static_cast<uint32_t>(y) * p.row_stride + static_cast<uint32_t>(c * p.P + xq * (TWIN ? 8 : 16));
       if (p.b_layout == 4u) so ^= ((so >> 7) & 3u) << 4;           // 64-byte swizzle
       else if (p.b_layout == 6u) so ^= ((so >> 7) & 1u) << 4;      // 32-byte swizzle
       soff[k] = so;
-      goff[k] = (c * p.H + y) * p.in_pitch + xq * 16;       // + (y0 - 1) * pitch >= 0 whenever the row is inside the image
+      goff[k] = TWIN ? (c * p.H + y) * p.in_pitch + xq * (p.C * p.H * p.in_pitch)
+                       : (c * p.H + y) * p.in_pitch + xq * 16;       // + (y0 - 1) * pitch >= 0 whenever the row is inside the image
       yrow[k] = y;
-      nbytes[k] = o < n_ops ? max(0, min(16, p.W - xq * 16)) : -1;
+      nbytes[k] = o < n_ops ? (TWIN ? min(8, p.W) : max(0, min(16, p.W - xq * 16))) : -1;
+      if (TWIN) yrow[k] |= xq << 16;                                // image B of the pair may not exist (odd batch)
     }
     uint32_t as = 0, aph = 0;
     const int64_t chunk_stride = static_cast<int64_t>(kWsCk) * p.H * p.in_pitch;
@@ -592,16 +688,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
       for (uint32_t sub = 0; sub < n_sub; ++sub) {
         const uint32_t tt = dual ? 2u * it + sub : it;
-        const uint32_t img = fdiv(tt, p.d_tpi);
-        const int y0 = static_cast<int>(tt - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
+        const uint32_t ti = fdiv(tt, p.d_tpi);                      // image (twin: image pair) of the tile
+        const uint32_t img = TWIN ? 2u * ti : ti;
+        const int y0 = static_cast<int>(tt - ti * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
+        const bool have_b = img + 1u < static_cast<uint32_t>(p.B);
         // per tile: which of this thread's copies read an input row inside the image (the others zero-fill: 0 bytes
         // from offset 0), so that the per-stage loop is one LDGSTS and one address add per copy
-        uint32_t go[kWsLoadOps];
-        int nb[kWsLoadOps];
+        uint32_t go[kOps];
+        int nb[kOps];
 #pragma unroll
-        for (int k = 0; k < kWsLoadOps; ++k) {
-          const int yy = p.stride * y0 - 1 + yrow[k];
-          const bool ok = yy >= 0 && yy < p.H && nbytes[k] > 0;
+        for (int k = 0; k < kOps; ++k) {
+          const int yy = p.stride * y0 - 1 + (yrow[k] & 0xffff);
+          const bool ok = yy >= 0 && yy < p.H && nbytes[k] > 0 && ((yrow[k] >> 16) == 0 || have_b);
           nb[k] = ok ? nbytes[k] : min(nbytes[k], 0);
           go[k] = ok ? static_cast<uint32_t>(goff[k] + (p.stride * y0 - 1) * p.in_pitch) : 0u;
         }
@@ -610,8 +708,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
           mbar_wait(&a_empty[as], aph ^ 1u);
           const uint32_t dst0 = a_addr + as * static_cast<uint32_t>(p.a_stage_bytes);
 #pragma unroll
-          for (int k = 0; k < kWsLoadOps; ++k)
-            if (nb[k] >= 0) cp_async16_zfill_s(dst0 + soff[k], src0 + go[k], nb[k]);
+          for (int k = 0; k < kOps; ++k)
+            if (nb[k] >= 0) {
+              if constexpr (TWIN) cp_async8_zfill_s(dst0 + soff[k], src0 + go[k], nb[k]);
+              else cp_async16_zfill_s(dst0 + soff[k], src0 + go[k], nb[k]);
+            }
           src0 += chunk_stride;
           // arrives once this thread's copies have landed; like CUTLASS's sm100 cp.async mainloop, the consumer's
           // mbarrier wait is the only synchronisation between these copies and tcgen05.mma (a fence.proxy.async

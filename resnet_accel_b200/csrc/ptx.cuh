@@ -109,6 +109,9 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
 __device__ __forceinline__ void cp_async16_zfill_s(uint32_t smem_dst, const void* gmem_src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async8_zfill_s(uint32_t smem_dst, const void* gmem_src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async4_zfill_s(uint32_t smem_dst, const void* gmem_src, int src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }

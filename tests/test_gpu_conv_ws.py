@@ -67,6 +67,8 @@ def _case(B, Cin, H, W, Cout, density, seed, residual=True, relu=False, relu_out
     (2, 64, 30, 62, 70, 0.2),        # widest supported row (62 + 2 padding pixels)
     (2, 64, 12, 12, 30, 0.0),        # no stored blocks at all
     (2, 160, 11, 14, 129, 0.05),     # very sparse: some (chunk, tap) weight tiles are empty and skipped
+    (4, 64, 7, 7, 128, 0.3),         # 7-pixel rows, > 64 channels: two images per staged row ("twin" tiles), weights resident
+    (3, 288, 6, 5, 130, 0.4),        # twin tiles, odd batch (the last pair is half empty), streamed weights, two groups
 ])
 def test_conv_ws_vs_oracle(B, Cin, H, W, Cout, density):
     _case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W + Cout)
