@@ -69,6 +69,31 @@ constexpr int kSmemTwoCtas = 113 * 1024;    // per CTA when two CTAs share an SM
 constexpr int kSmemOneCta = 200 * 1024;
 constexpr int kSmemPersist = 220 * 1024;    // the persistent kernel owns its SM
 constexpr int kSmemWs = 227 * 1024;         // conv_ws_kernel: everything an SM has
+// conv_ws_kernel<mode, residual mode, saturation counting>: one instantiation per epilogue variant (stride 2 has no residual)
+using WsKernelFn = void (*)(accel::WsLaunch);
+template <int MODE, int RES>
+WsKernelFn ws_kernel_pick(bool sat) {
+  return sat ? static_cast<WsKernelFn>(accel::conv_ws_kernel<MODE, RES, true>) : static_cast<WsKernelFn>(accel::conv_ws_kernel<MODE, RES, false>);
+}
+WsKernelFn ws_kernel_ptr(int mode, int resmode, bool sat) {
+  if (mode == accel::kWsModeS2) return resmode == 0 ? ws_kernel_pick<accel::kWsModeS2, 0>(sat) : nullptr;
+  if (mode == accel::kWsModeTwin) {
+    switch (resmode) {
+      case 0: return ws_kernel_pick<accel::kWsModeTwin, 0>(sat);
+      case 1: return ws_kernel_pick<accel::kWsModeTwin, 1>(sat);
+      case 2: return ws_kernel_pick<accel::kWsModeTwin, 2>(sat);
+      default: return ws_kernel_pick<accel::kWsModeTwin, 3>(sat);
+    }
+  }
+  switch (resmode) {
+    case 0: return ws_kernel_pick<accel::kWsModeS1, 0>(sat);
+    case 1: return ws_kernel_pick<accel::kWsModeS1, 1>(sat);
+    case 2: return ws_kernel_pick<accel::kWsModeS1, 2>(sat);
+    default: return ws_kernel_pick<accel::kWsModeS1, 3>(sat);
+  }
+}
+const void* ws_kernel_fn(int mode, int resmode, bool sat) { return reinterpret_cast<const void*>(ws_kernel_ptr(mode, resmode, sat)); }
+
 void set_kernel_attrs() {
   const void* fns[] = {reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeGemm>),
                        reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeConv3>),
@@ -85,12 +110,11 @@ void set_kernel_attrs() {
     if (g_attr_err == cudaSuccess)
       g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPersist);
   }
-  if (g_attr_err == cudaSuccess)
-    g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::conv_ws_kernel<false>),
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
-  if (g_attr_err == cudaSuccess)
-    g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::conv_ws_kernel<true>),
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
+  for (int m = 0; m < 3; ++m)
+    for (int r = 0; r < 4; ++r)
+      for (int t = 0; t < 2; ++t)
+        if (const void* f = ws_kernel_fn(m, r, t != 0))
+          if (g_attr_err == cudaSuccess) g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
   if (g_attr_err == cudaSuccess)
     g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::stem_ws_kernel),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
@@ -428,8 +452,11 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   if (per_group > n_items) per_group = n_items;
   if (per_group < 1) return kWsNotApplicable;
   const int smem = fixed + p.a_slots * p.a_stage_bytes;
-  if (p.twin) accel::conv_ws_kernel<true><<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);
-  else accel::conv_ws_kernel<false><<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);
+  const int resmode = !epi->residual ? 0 : (p.res_fast == 2 ? 3 : (p.res_fast == 1 ? 1 : 2));
+  const int mode = stride == 2 ? accel::kWsModeS2 : (p.twin ? accel::kWsModeTwin : accel::kWsModeS1);
+  WsKernelFn kfn = ws_kernel_ptr(mode, resmode, epi->sat_count != nullptr);
+  if (!kfn) return kWsNotApplicable;
+  kfn<<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_ws_kernel launch");
   ++g_ws_launches;

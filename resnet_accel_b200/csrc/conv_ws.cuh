@@ -465,10 +465,13 @@ __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEp
   return sat;
 }
 
-// TWIN: the twin-tile variant (WsParams::twin) is its own instantiation, so that its extra code paths (8-byte copies, the
-// twin epilogues, the unaliased U) cost the other layers neither registers nor instruction-cache space.
-template <bool TWIN>
+// One instantiation per (tile mode, residual mode, saturation counting): every launch runs exactly one epilogue variant, so
+// the others cost it neither registers nor instruction-cache space (measured: the twin paths inside one big kernel slowed
+// the layer1 convolutions from 63 to 84 us).  MODE 0 = stride 1, 1 = stride 2 (+ fused 1x1), 2 = twin tiles.
+constexpr int kWsModeS1 = 0, kWsModeS2 = 1, kWsModeTwin = 2;
+template <int MODE, int RESMODE, bool SAT>
 __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_constant__ WsLaunch L) {
+  constexpr bool TWIN = MODE == kWsModeTwin;
   extern __shared__ uint8_t smem_dyn[];
   const WsParams& p = L.p;
   // operand areas need 1024-byte alignment (swizzle atoms): align the dynamic window by hand
@@ -522,15 +525,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     const bool ch_ok = co < p.c_out;
     const float sf = ch_ok ? p.epi.chan_scale[co] : 0.f;
     const int bias = (ch_ok && p.epi.bias) ? p.epi.bias[co] : 0;
-    const bool sat_on = p.epi.sat_count != nullptr;
+    constexpr bool sat_on = SAT;
     WsEpiConst kc;
     kc.bias = bias; kc.sf = sf;
     kc.relu_lo = (p.epi.flags & ACCEL_RELU) ? 0 : INT_MIN;
     kc.out_lo = (p.epi.flags & ACCEL_RELU_OUT) ? 0 : -128;
     kc.lo_c = INT_MIN; kc.hi_c = INT_MAX;
     if (sat_on && ch_ok) ws_sat_bounds(sf, kc.lo_c, kc.hi_c);
-    const int resmode = !p.epi.residual ? 0 : (p.res_fast == 2 ? 3 : (p.res_fast == 1 ? 1 : 2));
-    const int variant = resmode * 2 + (sat_on ? 1 : 0);
     WsEpiRole er;
     er.item0 = item0; er.item_step = item_step; er.n_items = n_items; er.n_tiles = n_tiles; er.dual = dual; er.sub = sub;
     er.tmem_acc = tmem_base + lane_base;
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     er.warp_has_ch = dual ? (q * 16 < p.c_out) : (static_cast<int>(g) * kWsCo + q * 32 < p.c_out);
     er.acc_full = acc_full; er.acc_empty = acc_empty;
     uint32_t sat;
-    if (p.stride == 2) {
+    if constexpr (MODE == kWsModeS2) {
       WsEpiConst kc2 = kc;
       if (p.has_ds) {
         kc2.sf = ch_ok ? p.epi2.chan_scale[co] : 0.f;
@@ -547,29 +548,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
         kc2.relu_lo = (p.epi2.flags & ACCEL_RELU) ? 0 : INT_MIN;
         kc2.out_lo = (p.epi2.flags & ACCEL_RELU_OUT) ? 0 : -128;
       }
-      sat = sat_on ? ws_epi_loop_s2<true>(p, er, kc, kc2, lane) : ws_epi_loop_s2<false>(p, er, kc, kc2, lane);
+      sat = ws_epi_loop_s2<SAT>(p, er, kc, kc2, lane);
     } else if constexpr (TWIN) {
-      switch (variant) {
-        case 0: sat = ws_epi_loop_twin<0, false>(p, er, kc, lane); break;
-        case 1: sat = ws_epi_loop_twin<0, true>(p, er, kc, lane); break;
-        case 2: sat = ws_epi_loop_twin<1, false>(p, er, kc, lane); break;
-        case 3: sat = ws_epi_loop_twin<1, true>(p, er, kc, lane); break;
-        case 4: sat = ws_epi_loop_twin<2, false>(p, er, kc, lane); break;
-        case 5: sat = ws_epi_loop_twin<2, true>(p, er, kc, lane); break;
-        case 6: sat = ws_epi_loop_twin<3, false>(p, er, kc, lane); break;
-        default: sat = ws_epi_loop_twin<3, true>(p, er, kc, lane); break;
-      }
+      sat = ws_epi_loop_twin<RESMODE, SAT>(p, er, kc, lane);
     } else {
-    switch (variant) {
-      case 0: sat = ws_epi_loop<0, false>(p, er, kc, lane); break;
-      case 1: sat = ws_epi_loop<0, true>(p, er, kc, lane); break;
-      case 2: sat = ws_epi_loop<1, false>(p, er, kc, lane); break;
-      case 3: sat = ws_epi_loop<1, true>(p, er, kc, lane); break;
-      case 4: sat = ws_epi_loop<2, false>(p, er, kc, lane); break;
-      case 5: sat = ws_epi_loop<2, true>(p, er, kc, lane); break;
-      case 6: sat = ws_epi_loop<3, false>(p, er, kc, lane); break;
-      default: sat = ws_epi_loop<3, true>(p, er, kc, lane); break;
-    }
+      sat = ws_epi_loop<RESMODE, SAT>(p, er, kc, lane);
     }
     if (sat_on) {
       const uint32_t wsum = __reduce_add_sync(0xffffffffu, sat);
