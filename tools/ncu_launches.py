@@ -42,7 +42,7 @@ for r in rd:
 tot = sum(d["gpu__time_duration.sum"] for d in per.values()) or 1.0
 if not a.forwards:
     a.forwards = int(sum(d["launches"] for n, d in per.items() if "avgpool_i8_kernel" in n)) or 1
-ours = re.compile(r"conv_ws_kernel|bsr_tcp_kernel|bsr_tc_kernel")
+ours = re.compile(r"conv_ws_kernel|stem_ws_kernel|bsr_tcp_kernel|bsr_tc_kernel")
 os.makedirs("profiles", exist_ok=True)
 with open(f"profiles/{a.tag}_launches.md", "w") as f:
     f.write(f"# ncu launch list ({a.tag}): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
@@ -56,7 +56,7 @@ with open(f"profiles/{a.tag}_launches.md", "w") as f:
 conv_bytes = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for n, d in per.items() if ours.search(n))
 conv_us = sum(d["gpu__time_duration.sum"] for n, d in per.items() if ours.search(n))
 out = {"conv_fc_dram_bytes_per_step": conv_bytes / a.forwards, "conv_fc_us_per_step_under_ncu": conv_us / a.forwards,
-       "source": f"profiles/{a.tag}_launches.csv: sum of dram__bytes_read + dram__bytes_write over the conv_ws / bsr_tcp / bsr_tc "
+       "source": f"profiles/{a.tag}_launches.csv: sum of dram__bytes_read + dram__bytes_write over the conv_ws / stem_ws / bsr_tcp / bsr_tc "
                  f"launches, divided by the {a.forwards} forward passes of the capture"}
 with open(f"profiles/{a.tag}_traffic.json", "w") as f:
     json.dump(out, f, indent=1)
