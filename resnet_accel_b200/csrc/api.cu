@@ -82,14 +82,16 @@ WsKernelFn ws_kernel_ptr(int mode, int resmode, bool sat) {
       case 0: return ws_kernel_pick<accel::kWsModeTwin, 0>(sat);
       case 1: return ws_kernel_pick<accel::kWsModeTwin, 1>(sat);
       case 2: return ws_kernel_pick<accel::kWsModeTwin, 2>(sat);
-      default: return ws_kernel_pick<accel::kWsModeTwin, 3>(sat);
+      case 3: return ws_kernel_pick<accel::kWsModeTwin, 3>(sat);
+      default: return ws_kernel_pick<accel::kWsModeTwin, 4>(sat);
     }
   }
   switch (resmode) {
     case 0: return ws_kernel_pick<accel::kWsModeS1, 0>(sat);
     case 1: return ws_kernel_pick<accel::kWsModeS1, 1>(sat);
     case 2: return ws_kernel_pick<accel::kWsModeS1, 2>(sat);
-    default: return ws_kernel_pick<accel::kWsModeS1, 3>(sat);
+    case 3: return ws_kernel_pick<accel::kWsModeS1, 3>(sat);
+    default: return ws_kernel_pick<accel::kWsModeS1, 4>(sat);
   }
 }
 const void* ws_kernel_fn(int mode, int resmode, bool sat) { return reinterpret_cast<const void*>(ws_kernel_ptr(mode, resmode, sat)); }
@@ -111,7 +113,7 @@ void set_kernel_attrs() {
       g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPersist);
   }
   for (int m = 0; m < 3; ++m)
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 5; ++r)
       for (int t = 0; t < 2; ++t)
         if (const void* f = ws_kernel_fn(m, r, t != 0))
           if (g_attr_err == cudaSuccess) g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
@@ -140,7 +142,8 @@ int check_epilogue(const accel_epilogue* epi, const accel_out_layout* lay, const
 // when that reproduces the reference's int8 result for EVERY (main, residual) int8 pair - decided here,
 // once per scale triple, by exhaustive comparison with the true quotient.
 // Returns 0: IEEE divide needed, 1: the 3-instruction sequence is exact, 2: even the single multiply  q = s * rcp  gives the
-// reference's int8 for every pair (the weight-stationary kernel then drops the two FMAs as well).
+// reference's int8 for every pair (the weight-stationary kernel then drops the two FMAs as well), 3: the whole float
+// sequence equals the saturating INTEGER sum main + residual for every pair (matched scales, the usual identity add).
 int residual_divide_mode(float s_main, float s_res, float s_out) {
   static std::mutex mu;
   static std::map<std::array<uint32_t, 3>, int> cache;
@@ -149,7 +152,7 @@ int residual_divide_mode(float s_main, float s_res, float s_out) {
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
-  bool ok = std::isfinite(s_out) && s_out != 0.f, ok_mul = true;
+  bool ok = std::isfinite(s_out) && s_out != 0.f, ok_mul = true, ok_add = true;
   const float rcp = 1.0f / s_out;
   ok = ok && std::isfinite(rcp);
   auto sat8 = [](float f) {
@@ -169,9 +172,11 @@ int residual_divide_mode(float s_main, float s_res, float s_out) {
       const float q = std::fmaf(e, rcp, q0);
       if (!std::isfinite(truth) || !std::isfinite(q) || sat8(q) != sat8(truth)) { ok = false; break; }
       if (sat8(q0) != sat8(truth)) ok_mul = false;
+      const int isum = a + r;
+      if (sat8(truth) != (isum > 127 ? 127 : (isum < -128 ? -128 : isum))) ok_add = false;
     }
   }
-  const int mode = !ok ? 0 : (ok_mul ? 2 : 1);
+  const int mode = !ok ? 0 : (ok_add ? 3 : (ok_mul ? 2 : 1));
   cache[key] = mode;
   return mode;
 }
@@ -452,7 +457,7 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   if (per_group > n_items) per_group = n_items;
   if (per_group < 1) return kWsNotApplicable;
   const int smem = fixed + p.a_slots * p.a_stage_bytes;
-  const int resmode = !epi->residual ? 0 : (p.res_fast == 2 ? 3 : (p.res_fast == 1 ? 1 : 2));
+  const int resmode = !epi->residual ? 0 : (p.res_fast == 3 ? 4 : (p.res_fast == 2 ? 3 : (p.res_fast == 1 ? 1 : 2)));
   const int mode = stride == 2 ? accel::kWsModeS2 : (p.twin ? accel::kWsModeTwin : accel::kWsModeS1);
   WsKernelFn kfn = ws_kernel_ptr(mode, resmode, epi->sat_count != nullptr);
   if (!kfn) return kWsNotApplicable;

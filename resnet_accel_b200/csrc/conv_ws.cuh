@@ -66,7 +66,7 @@ struct WsParams {
   FastDiv d_tpi;
   const uint8_t* wblob;        // [group][chunk][tap][4096]
   accel_epilogue epi;
-  int32_t res_fast;            // residual divide: 0 IEEE, 1 exact 3-instruction sequence, 2 single multiply (verified on the host)
+  int32_t res_fast;            // residual: 0 IEEE divide, 1 exact 3-instruction sequence, 2 single multiply, 3 integer add (verified on the host)
   float res_rcp;
   int8_t* out;
   int32_t out_pitch;           // bytes between output rows
@@ -185,7 +185,12 @@ __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)
       }
       const float f = __fmul_rn(__int2float_rn(acc), sf);
       int r8 = cvt_sat_s8(f);
-      if constexpr (RESMODE != 0) {
+      if constexpr (RESMODE == 4) {
+        // matched scales: the host checked that the reference's float sequence equals the saturating integer sum for all
+        // 65 536 (main, residual) pairs
+        const int rv = static_cast<int>(static_cast<int8_t>((rw[w] >> (8 * b)) & 0xffu));
+        r8 = min(max(r8 + rv, -128), 127);
+      } else if constexpr (RESMODE != 0) {
         const float rf = b == 0 ? i2f_s8_byte<0>(rw[w]) : b == 1 ? i2f_s8_byte<1>(rw[w]) : b == 2 ? i2f_s8_byte<2>(rw[w])
                                                                                                      : i2f_s8_byte<3>(rw[w]);
         const float a = __fmul_rn(__int2float_rn(r8), p.epi.res_scale_main);
