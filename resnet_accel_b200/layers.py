@@ -291,3 +291,94 @@ class BsrNetwork:
             bytes_total += b
             per_layer.append({"name": sp.name, "ops": o, "bytes": b})
         return {"ops": ops_total, "bytes": bytes_total, "layers": per_layer}
+
+
+class ResNetInference:
+    """Python twin of the reference's ``ResNetInference`` engine (hw/sim/cpp/include/resnet_inference.hpp:180-271; its
+    ``load_model`` / ``run_inference`` are TODO stubs there) on top of :class:`BsrNetwork`.
+
+    ``load_model(weights_dir)`` reads the directory layout the header documents - ``<layer>_weight_int8.npy`` (OIHW or
+    [out, in] int8), ``<layer>_weight_scales.npy`` (float32 per output channel) and optionally ``<layer>_bias_int32.npy`` -
+    packs every layer into 14x14 BSR on the GPU (all-zero blocks are dropped, as ``build_bsr_14x14_int8_direct`` does) and
+    uploads the plans.  ``run_inference`` takes int8 NCHW images that are already quantised with ``s_in``."""
+
+    def __init__(self, batch: int = 1, image: int = 224, num_classes: int = 1000, s_in: float = S_ACT_IN,
+                 s_out: float = S_ACT_OUT):
+        self.batch, self.image, self.num_classes = batch, image, num_classes
+        self.s_in, self.s_out = s_in, s_out
+        self.specs = resnet18_specs(image, num_classes)
+        self.net: Optional[BsrNetwork] = None
+
+    def load_model(self, weights_dir: str) -> None:
+        import os
+        layers: Dict[str, BsrLayer] = {}
+        for sp in self.specs:
+            if sp.kind not in ("conv", "fc"):
+                continue
+            w = np.load(os.path.join(weights_dir, f"{sp.name}_weight_int8.npy"))
+            if w.dtype != np.int8 or w.shape[0] != sp.c_out or w.size != sp.c_out * sp.K:
+                raise ValueError(f"{sp.name}: expected int8 weights of shape [{sp.c_out}, {sp.K}] (or OIHW)")
+            scales = np.load(os.path.join(weights_dir, f"{sp.name}_weight_scales.npy")).astype(np.float32).reshape(-1)
+            bias_path = os.path.join(weights_dir, f"{sp.name}_bias_int32.npy")
+            bias = np.load(bias_path).astype(np.int32) if os.path.exists(bias_path) else None
+            bsr = exporters.build_bsr_14x14_int8_direct(torch.from_numpy(w.reshape(sp.c_out, -1)).cuda(), device=True)
+            layers[sp.name] = BsrLayer(sp, bsr=bsr, w_scales=scales, bias=bias, s_in=self.s_in, s_out=self.s_out,
+                                       group_rows=(8 if sp.kind == "fc" else 0))
+        self.net = BsrNetwork(self.specs, 0.0, self.batch, layers=layers)
+
+    def _require(self) -> BsrNetwork:
+        if self.net is None:
+            raise RuntimeError("Weights not loaded")          # AcceleratorError::NOT_READY in the C++ twin
+        return self.net
+
+    def run_inference(self, images: torch.Tensor) -> torch.Tensor:
+        """int8 [batch, 3, H, W] -> INT32 logits [batch, num_classes] (the FC accumulators, as the reference keeps them)."""
+        net = self._require()
+        x = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+        x = x.to("cuda", non_blocking=True)
+        if net.graph is None:
+            net.capture(x)
+        return net.replay(x).clone()
+
+    def get_top_k(self, logits: torch.Tensor, k: int = 5):
+        w = torch.from_numpy(self._require().layers["fc"].w_scales).to(logits.device)
+        real = logits.to(torch.float32) * (self.s_out * w)[: logits.shape[1]]       # de-quantise per channel before ranking
+        prob = torch.softmax(real, dim=1)
+        p, i = prob.topk(k, dim=1)
+        return i.cpu().numpy(), p.cpu().numpy()
+
+    def benchmark(self, num_runs: int = 100) -> Dict:
+        net = self._require()
+        x = torch.randint(-128, 128, (self.batch, 3, self.image, self.image), dtype=torch.int8, device="cuda")
+        if net.graph is None:
+            net.capture(x)
+        for _ in range(3):
+            net.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(num_runs):
+            net.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / num_runs
+        return {"ms_per_batch": ms, "images_per_s": self.batch / ms * 1e3, "batch": self.batch}
+
+    def get_layer_sparsity(self) -> List[Tuple[str, float]]:
+        out = []
+        for sp in self.specs:
+            if sp.name in self._require().layers:
+                lay = self.net.layers[sp.name]
+                total = lay.plan.n_block_rows * lay.plan.n_block_cols
+                out.append((sp.name, 1.0 - lay.plan.num_blocks / max(total, 1)))
+        return out
+
+    def get_model_sparsity(self) -> float:
+        net = self._require()
+        kept = sum(l.plan.num_blocks for l in net.layers.values())
+        total = sum(l.plan.n_block_rows * l.plan.n_block_cols for l in net.layers.values())
+        return 1.0 - kept / max(total, 1)
+
+    def print_model_summary(self) -> None:
+        for name, s in self.get_layer_sparsity():
+            print(f"{name:24s} block sparsity {100 * s:5.1f} %")
+        print(f"{'model':24s} block sparsity {100 * self.get_model_sparsity():5.1f} %")

@@ -83,3 +83,31 @@ def test_network_layers_match_oracle_port():
             assert np.array_equal(got, want), sp.name
         t[sp.name] = got            # continue from the device result so that one mismatch does not cascade
         prev = sp.name
+
+
+def test_resnet_inference_engine_roundtrip(tmp_path):
+    """ResNetInference.load_model on the directory layout of resnet_inference.hpp reproduces the network it was saved from."""
+    import torch
+    from oracle import bsr_oracle as O
+    from resnet_accel_b200 import layers as L
+    B = 2
+    specs = L.resnet18_specs(image=64, num_classes=50)
+    ref = L.BsrNetwork(specs, 70.0, B)
+    for name, lay in ref.layers.items():
+        dense = O.bsr_to_dense(lay.bsr["indptr"].cpu().numpy(), lay.bsr["indices"].cpu().numpy(), lay.bsr["data"].cpu().numpy(),
+                               lay.bsr["num_block_cols"])
+        sp = lay.spec
+        np.save(tmp_path / f"{name}_weight_int8.npy", dense[:sp.c_out, :sp.K].astype(np.int8).reshape(sp.c_out, sp.c_in, sp.k, sp.k))
+        np.save(tmp_path / f"{name}_weight_scales.npy", lay.w_scales)
+    eng = L.ResNetInference(batch=B, image=64, num_classes=50)
+    with pytest.raises(RuntimeError):
+        eng.run_inference(torch.zeros((B, 3, 64, 64), dtype=torch.int8))
+    eng.load_model(str(tmp_path))
+    x = torch.randint(-128, 128, (B, 3, 64, 64), dtype=torch.int8, device="cuda")
+    want = ref.forward(x).cpu().numpy().copy()
+    got = eng.run_inference(x).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert 0.6 < eng.get_model_sparsity() < 0.8
+    idx, prob = eng.get_top_k(torch.from_numpy(got).cuda(), k=3)
+    assert idx.shape == (B, 3) and np.all(prob[:, 0] >= prob[:, 1])
+    assert eng.benchmark(3)["images_per_s"] > 0
