@@ -288,6 +288,11 @@ def conv_pool(plan: BsrPlan, x: torch.Tensor, c_out: int, *, chan_scale, bias=No
     if out_pitch is None:
         raise AcceleratorError(_lib.INVALID_CONFIG, "output must be NCHW, dense or with padded rows")
     fused = ksize == 7 and stride == 2 and pad == 3 and (pool, pool_stride, pool_pad) == (3, 2, 1) and Cin * 7 <= 32 and c_out <= 64
+    if fused and not getattr(plan, "_pool_fusable", False):
+        # the pool is taken on the INT32 accumulators: bit-identical only for positive requant factors (checked once per plan)
+        sf_t = chan_scale if isinstance(chan_scale, torch.Tensor) else torch.as_tensor(np.asarray(chan_scale))
+        fused = bool((sf_t[:c_out] > 0).all().item())
+        plan._pool_fusable = fused
     if fused:
         plan._prepare_conv_ws(Cin, c_out, 7)
         e, keep = plan._epilogue("i8", c_out, chan_scale, bias, relu, None, None, sat_count, None)
