@@ -69,6 +69,10 @@ def _case(B, Cin, H, W, Cout, density, seed, residual=True, relu=False, relu_out
     (2, 160, 11, 14, 129, 0.05),     # very sparse: some (chunk, tap) weight tiles are empty and skipped
     (4, 64, 7, 7, 128, 0.3),         # 7-pixel rows, > 64 channels: two images per staged row ("twin" tiles), weights resident
     (3, 288, 6, 5, 130, 0.4),        # twin tiles, odd batch (the last pair is half empty), streamed weights, two groups
+    (1, 32, 1, 1, 16, 1.0),          # a single pixel
+    (1, 64, 2, 3, 65, 0.5),          # batch 1, 65 channels (one channel over the paired-tile limit)
+    (7, 64, 7, 7, 65, 0.5),          # twin tiles, odd batch, resident weights
+    (1, 512, 7, 7, 70, 0.3),         # batch 1 with 7-pixel rows: no second image to pair with
 ])
 def test_conv_ws_vs_oracle(B, Cin, H, W, Cout, density):
     _case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W + Cout)

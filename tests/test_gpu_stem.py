@@ -48,6 +48,8 @@ def _stem_case(B, Cin, H, W, Cout, density, seed, expect_fused=True, bias_on=Tru
     (2, 1, 40, 64, 14, 1.0),          # one input channel, dense
     (2, 4, 36, 128, 64, 0.4),         # four input channels
     (2, 3, 16, 32, 30, 0.0),          # no stored blocks
+    (1, 3, 4, 32, 8, 1.0),            # batch 1, the smallest image the kernel takes (one pooled row)
+    (5, 2, 100, 224, 64, 0.5),        # full-width rows, two channels, odd batch
 ])
 def test_stem_fused_vs_oracle(B, Cin, H, W, Cout, density):
     _stem_case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W + Cout)
