@@ -61,6 +61,7 @@ int g_dbg_flags = 0;
 bool g_no_persist = std::getenv("ACCEL_NO_PERSIST") != nullptr;   // developer switch: one-shot kernel everywhere
 long long g_ws_launches = 0;         // accel_debug_counter(0)
 bool g_ws_s2_streamed = std::getenv("ACCEL_WS_S2_STREAMED") != nullptr;   // developer switch: allow stride 2 with streamed weights
+bool g_no_pdl = std::getenv("ACCEL_NO_PDL") != nullptr;            // developer switch: plain stream-ordered launches
 bool g_no_twin = std::getenv("ACCEL_NO_TWIN") != nullptr;          // developer switch: one image per tile even for 7-pixel rows
 bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
 std::once_flag g_attr_once;
@@ -70,6 +71,20 @@ constexpr int kSmemOneCta = 200 * 1024;
 constexpr int kSmemPersist = 220 * 1024;    // the persistent kernel owns its SM
 constexpr int kSmemWs = 227 * 1024;         // conv_ws_kernel: everything an SM has
 // conv_ws_kernel<mode, residual mode, saturation counting>: one instantiation per epilogue variant (stride 2 has no residual)
+// Launch with programmatic stream serialization: the grid may begin (prologue, TMEM allocation, resident weight load)
+// while the previous kernel on the stream drains; the kernels order their dependent reads and all their writes behind
+// griddepcontrol.wait themselves.  Captured into CUDA graphs as a programmatic dependency edge.
+template <typename Params>
+cudaError_t launch_overlapped(void (*kfn)(Params), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const Params& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kfn, arg);
+}
+
 using WsKernelFn = void (*)(accel::WsLaunch);
 template <int MODE, int RES>
 WsKernelFn ws_kernel_pick(bool sat) {
@@ -461,8 +476,8 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   const int mode = stride == 2 ? accel::kWsModeS2 : (p.twin ? accel::kWsModeTwin : accel::kWsModeS1);
   WsKernelFn kfn = ws_kernel_ptr(mode, resmode, epi->sat_count != nullptr);
   if (!kfn) return kWsNotApplicable;
-  kfn<<<static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st>>>(L);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_overlapped(kfn, static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st, L);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_ws_kernel launch");
   ++g_ws_launches;
   return ACCEL_OK;
@@ -836,8 +851,9 @@ int accel_conv_pool_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, con
   p.dbg = g_dbg_flags;
   const int ctas = n_items < sm_count() ? static_cast<int>(n_items) : sm_count();
   const int smem = 1024 + accel::kStSmemBar + accel::kStWBytes + accel::kStSlots * accel::kStStageBytes;
-  accel::stem_ws_kernel<<<static_cast<unsigned>(ctas), accel::kStThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_overlapped(accel::stem_ws_kernel, static_cast<unsigned>(ctas), accel::kStThreads, smem,
+                                    static_cast<cudaStream_t>(stream), p);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "stem_ws_kernel launch");
   ++g_ws_launches;
   return ACCEL_OK;

@@ -505,6 +505,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
   const uint32_t dual = static_cast<uint32_t>(p.dual);
   const uint32_t n_items = dual ? (n_tiles + 1u) >> 1 : n_tiles;
 
+  // The next kernel on the stream may take over SMs as CTAs of this grid retire (its prologue and resident weight
+  // load then overlap our tail); everything here that reads what the previous kernel wrote sits behind griddep_wait().
+  griddep_launch();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWsMaxASlots; ++s) { mbar_init(&a_full[s], kWsLoadThreads); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kWsMaxChunks; ++s) mbar_init(&w_full[s], 1);
@@ -523,6 +526,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
 
   if (warp < kWsEpiWarps) {
     // =================================================================== epilogue: thread = output channel
+    griddep_wait();          // residuals, the output buffer (still being read) and the counters belong to earlier kernels
     const int q = warp & 3, half = warp >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sub = dual ? static_cast<uint32_t>(lane >> 4) : 0u;          // which tile of the pair
@@ -648,6 +652,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     // names.  TMA tensor tiles deliver exactly this layout too, but their rows are 16-64 bytes and the TMA unit retires
     // about one row per 4 cycles (measured: 685 cycles per 8 KB stage); 16-byte LDGSTS copies issued by two warps are
     // several times faster and zero-fill the padding just the same.
+    griddep_wait();          // the activations are the previous kernel's output
     const int lt = static_cast<int>(threadIdx.x) - kWsWarpLoad * 32;           // 0..191
     const int x16s = p.P >> 4, rows = p.rows_in;
     const int n_ops = kWsCk * rows * (p.twin ? 2 : x16s);

@@ -25,6 +25,13 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while its
+// predecessor on the stream is still draining.  griddep_launch() lets the successor of THIS grid be scheduled as CTAs
+// here finish; griddep_wait() returns once the predecessor grid has completed and its writes are visible.  Both are
+// no-ops for a plain launch.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

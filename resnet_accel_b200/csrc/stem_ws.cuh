@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const uint32_t n_items = static_cast<uint32_t>(p.n_items);
 
+  griddep_launch();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStSlots; ++s) { mbar_init(&a_full[s], 32); mbar_init(&a_empty[s], 1); }
     mbar_init(w_full, 1);
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
 
   if (warp < kStEpiWarps) {
     // =================================================================== epilogue: thread = (image of the pair, channel)
+    griddep_wait();
     const int q = warp & 3, half = warp >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int sub = lane >> 4;
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
     // =================================================================== loaders: 32 input bytes -> 16 even + 16 odd
     // Stage s (one conv row of one image) belongs to loader warp s % 3: three stages are in flight, and every lane has
     // its (up to) five 32-byte units of a stage outstanding at once.
+    griddep_wait();
     const int lw = warp - kStWarpLoad;
     const int upr = p.W >> 5;                        // 32-byte units per input row (W % 32 == 0)
     const int n_units = p.C * 7 * upr;

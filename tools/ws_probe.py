@@ -34,9 +34,20 @@ for name in os.environ.get("LAYER", "layer1.0.conv1,layer1.0.conv2,layer2.1.conv
         run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graph = None
+    if os.environ.get("GRAPH"):                  # 20 launches replayed from one CUDA graph
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                run()
+        graph.replay()
+        torch.cuda.synchronize()
     e0.record()
-    for _ in range(20):
-        run()
+    if graph is not None:
+        graph.replay()
+    else:
+        for _ in range(20):
+            run()
     e1.record()
     torch.cuda.synchronize()
     print(f"{name:20s} {e0.elapsed_time(e1) / 20 * 1000:8.1f} us  (dbg={os.environ.get('ACCEL_DBG_FLAGS', '0')})")
