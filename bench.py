@@ -303,6 +303,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     kms /= reps
     conv_bytes = sum(l["bytes"] for l in work["layers"] if l["name"] in conv_names)
     conv_ops = sum(l["ops"] for l in work["layers"] if l["name"] in conv_names)
+    dense_ops = sum(l["dense_ops"] for l in work["layers"] if l["name"] in conv_names)
 
     if rank == 0:
         hbm_peak, int8_peak_tops, src = measured_peaks()
@@ -328,6 +329,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                    "launches per step; algorithmic bytes of the reference's layer sequence (unfused) over "
                                    "the event-timed eager forward",
                          "useful_tops": ach_tops, "tensor_frac_of_2x_bf16_sustained": ach_tops / int8_peak_tops,
+                         # the weight-stationary kernels contract every 32-channel chunk that holds a stored block:
+                         # the work the tensor pipe does is the dense layer's, of which `useful` is the stored share
+                         "dense_equiv_tops": dense_ops / (kms / 1e3) / 1e12,
+                         "dense_equiv_tensor_frac": dense_ops / (kms / 1e3) / 1e12 / int8_peak_tops,
                          "kernel_ms_per_step": kms, "algorithmic_bytes_per_step": conv_bytes,
                          "useful_ops_per_step": conv_ops},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel()) * world,

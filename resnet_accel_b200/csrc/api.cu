@@ -60,7 +60,7 @@ long long* g_timeline = nullptr;   // accel_debug_set_timeline
 int g_dbg_flags = 0;
 bool g_no_persist = std::getenv("ACCEL_NO_PERSIST") != nullptr;   // developer switch: one-shot kernel everywhere
 long long g_ws_launches = 0;         // accel_debug_counter(0)
-bool g_ws_s2_streamed = std::getenv("ACCEL_WS_S2_STREAMED") != nullptr;   // developer switch: allow stride 2 with streamed weights
+bool g_ws_s2_narrow = std::getenv("ACCEL_WS_S2_NARROW") != nullptr;   // developer switch: 64-pixel stride-2 tiles even with streamed weights
 bool g_no_pdl = std::getenv("ACCEL_NO_PDL") != nullptr;            // developer switch: plain stream-ordered launches
 bool g_no_twin = std::getenv("ACCEL_NO_TWIN") != nullptr;          // developer switch: one image per tile even for 7-pixel rows
 bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
@@ -370,9 +370,10 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   if (!(epi->flags & ACCEL_OUT_I8) || epi->chan_absmax) return kWsNotApplicable;
   const int stride = g->stride;
   if (stride == 2 && ((g->h | g->w) & 1 || epi->residual)) return kWsNotApplicable;
-  // stride 2 with streamed weights (Cin > 128) measures slower than the gather kernels (layer4.0 of ResNet-18: 168 us
-  // fused against 67 + 62 us): the 64-pixel tiles re-stream every weight chunk twice per image.  Not taken until fixed.
-  if (stride == 2 && W.n_chunks > accel::kWsMaxWSlots && !g_ws_s2_streamed) return kWsNotApplicable;
+  // stride 2 with streamed weights (Cin > 128): every tile re-reads the filter from L2, so the tile is made as large as
+  // TMEM allows (below).  ACCEL_WS_S2_NARROW keeps the 64-pixel tiles (layer4.0 of ResNet-18: 168 us fused, against
+  // 125 us on the gather kernels).
+  const bool s2_wide = stride == 2 && W.n_chunks > accel::kWsMaxWSlots && !g_ws_s2_narrow;
   if (plan_ds) {
     const WsState& D = plan_ds->ws;
     if (stride != 2 || !D.ready || D.taps != 1 || D.c_in != W.c_in || D.c_out != W.c_out || !epi_ds || !out_ds) return kWsNotApplicable;
@@ -410,8 +411,10 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   std::memset(&p, 0, sizeof(p));
   p.C = g->c_in; p.H = H; p.W = Wd; p.B = g->batch; p.P = P;
   int best_r = 1, best_cost = INT_MAX;
-  for (int r = 1; r <= (stride == 2 ? 64 : 128) / P; ++r) {       // stride 2: N <= 64 (three accumulators per set)
+  for (int r = 1; r <= (stride == 2 && !s2_wide ? 64 : 128) / P; ++r) {       // stride 2: N <= 64 (three accumulators per set)
     const int cost = (Ho + r - 1) / r * r;
+    const int copies = accel::kWsCk * (stride == 2 ? 2 * r + 1 : r + 2) * (P >> 4);      // 16-byte loader copies per stage
+    if (copies > accel::kWsLoadThreads * accel::kWsLoadOps) break;
     if (cost <= best_cost) { best_cost = cost; best_r = r; }
   }
   p.R = best_r; p.N = p.R * P;
@@ -419,6 +422,8 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
 
   p.rows_in = stride == 2 ? 2 * p.R + 1 : p.R + 2;
   p.has_ds = plan_ds ? 1 : 0;
+  p.acc_single = (s2_wide && plan_ds) ? 1 : 0;
+  p.v_col = p.acc_single ? 256 : 128;
   p.w_chunk_bytes = accel::kWsChunkBytes + (plan_ds ? accel::kWsTapBytes : 0);
   p.n_chunks = W.n_chunks; p.n_groups = W.n_groups; p.c_out = W.c_out;
   p.tiles_per_image = (Ho + p.R - 1) / p.R;

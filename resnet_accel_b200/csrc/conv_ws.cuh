@@ -79,13 +79,15 @@ struct WsParams {
   // the ResNet downsample).  Rows: the loader stages 2R+1 input rows and the B window of tap kh takes every second one.
   // Columns: computed at full resolution, the epilogue keeps the even ones.  The 1x1 convolution is one more tap on the
   // kh = 1 window, accumulated into V (columns [128, 128 + N), N <= 64) and written through its own epilogue.
-  int32_t stride, rows_in, Ho, Wo, w_chunk_bytes, has_ds;
+  // Streamed weights (more than kWsMaxWSlots chunks) make every tile re-read the whole filter from L2, so there the tile
+  // is as large as it can be (N <= 128, a whole 14 x 14 image): with the fused 1x1 the three accumulators then take
+  // one 512-column set (acc_single: Z1/U in [0, 256), V at 256; the epilogue no longer overlaps the next tile's MMAs).
+  int32_t stride, rows_in, Ho, Wo, w_chunk_bytes, has_ds, acc_single, v_col;
   const uint8_t* wblob2;       // [group][chunk][4096]
   accel_epilogue epi2;
   int8_t* out2;
   uint16_t masks2[kWsMaxGroups * kWsMaxChunks];
 };
-constexpr uint32_t kWsVCol = 128;
 struct WsLaunch {
   alignas(64) CUtensorMap tmap;
   WsParams p;
@@ -436,10 +438,10 @@ __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEp
   for (uint32_t it = r.item0; it < r.n_items; it += r.item_step, ++n) {
     const uint32_t img = fdiv(it, p.d_tpi);
     const int y0 = static_cast<int>(it - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
-    const uint32_t ab = n & 1u;
+    const uint32_t ab = p.acc_single ? 0u : (n & 1u);
     const uint32_t acc = r.tmem_acc + ab * kWsAccCols;
     const int64_t obase = static_cast<int64_t>(img) * p.image_stride + static_cast<int64_t>(r.co) * p.chan_stride;
-    mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
+    mbar_wait(&r.acc_full[ab], p.acc_single ? (n & 1u) : ((n >> 1) & 1u));
     tc_fence_after();
     if (r.warp_has_ch && !(p.dbg & 1)) {
       for (int k = 0; k < kWsMaxMyChunks; ++k) {
@@ -451,7 +453,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEp
         uint32_t z[16], u[16], v[16];
         tmem_ld16(acc + p0, z);
         tmem_ld16(acc + p.u_off + 1 + p0, u);
-        if (p.has_ds) tmem_ld16(acc + kWsVCol + p0, v);
+        if (p.has_ds) tmem_ld16(acc + static_cast<uint32_t>(p.v_col) + p0, v);
         tmem_ld_wait();
         const int n_valid = max(0, min(8, p.Wo - x0));
         const int64_t off = obase + static_cast<int64_t>(y0 + row) * p.out_pitch + x0;
@@ -583,8 +585,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       constexpr bool alias = !TWIN;
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0;
       for (uint32_t it = item0; it < n_items; it += item_step, ++n) {
-        const uint32_t ab = n & 1u;
-        mbar_wait(&acc_empty[ab], ((n >> 1) & 1u) ^ 1u);
+        const bool one_set = MODE == kWsModeS2 && p.acc_single;
+        const uint32_t ab = one_set ? 0u : (n & 1u);
+        mbar_wait(&acc_empty[ab], (one_set ? (n & 1u) : ((n >> 1) & 1u)) ^ 1u);
         tc_fence_after();
         const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
         for (uint32_t sub = 0; sub < n_sub; ++sub) {
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
                   mma_i8_ss(z1 + u_off + 2, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 0) * (kWsTapBytes >> 4)), bd, idesc, 1u);
               }
               if (kh == 1 && p.has_ds && (p.masks2[g * kWsMaxChunks + j] & 1u) && !(p.dbg & 2)) {   // fused 1x1 / stride 2
-                mma_i8_ss(z1 + kWsVCol, (static_cast<uint64_t>(a_hi) << 32) | (wl + 9 * (kWsTapBytes >> 4)), bd, idesc, v_on);
+                mma_i8_ss(z1 + static_cast<uint32_t>(p.v_col), (static_cast<uint64_t>(a_hi) << 32) | (wl + 9 * (kWsTapBytes >> 4)), bd, idesc, v_on);
                 v_on = 1u;
               }
             }

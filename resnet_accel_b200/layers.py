@@ -289,7 +289,8 @@ class BsrNetwork:
                 b = in_bytes + B * sp.c_out * (sp.h_out * sp.w_out if sp.kind == "maxpool" else 1)
             ops_total += o
             bytes_total += b
-            per_layer.append({"name": sp.name, "ops": o, "bytes": b})
+            dense = 2 * B * sp.h_out * sp.w_out * sp.c_out * sp.c_in * sp.k * sp.k if sp.kind in ("conv", "fc") else 0
+            per_layer.append({"name": sp.name, "ops": o, "dense_ops": dense, "bytes": b})
         return {"ops": ops_total, "bytes": bytes_total, "layers": per_layer}
 
 

@@ -164,15 +164,19 @@ def _s2_case(B, Cin, H, W, Cout, density, seed, with_ds=True, expect_ws=True):
 @pytest.mark.parametrize("B,Cin,H,W,Cout,density", [
     (2, 64, 56, 56, 128, 0.3),       # layer2.0: conv1 + downsample, one output row per tile
     (3, 128, 28, 28, 256, 0.3),      # layer3.0: two output rows per tile, two channel groups
-    (5, 256, 14, 14, 512, 0.3),      # layer4.0: four rows per tile (7 rows: ragged), streamed weights
+    (5, 256, 14, 14, 512, 0.3),      # layer4.0: streamed weights, a whole image per tile, one 512-column accumulator set
     (2, 32, 10, 20, 40, 0.6),        # small / odd channel count
     (2, 64, 12, 60, 70, 0.1),        # wide rows, very sparse
+    (3, 160, 16, 16, 130, 0.4),      # streamed weights, 8 output rows (the loaders cap the tile at 7), two groups
+    (2, 192, 20, 28, 64, 0.3),       # streamed weights, 32-pixel rows (three output rows per tile)
+    (1, 160, 6, 40, 48, 0.5),        # streamed weights, 64-pixel rows (one output row per tile)
 ])
 def test_conv_ws_stride2_with_downsample(B, Cin, H, W, Cout, density):
-    # Cin > 128 (streamed weights) is routed to the gather kernels for stride 2: same call, same results
-    _s2_case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W, expect_ws=Cin <= 128)
+    _s2_case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W)
 
 
 def test_conv_ws_stride2_alone():
     _s2_case(2, 64, 28, 28, 96, 0.4, seed=5, with_ds=False)
     _s2_case(9, 128, 28, 28, 128, 0.3, seed=6, with_ds=False)
+    _s2_case(3, 256, 14, 14, 200, 0.3, seed=7, with_ds=False)     # streamed weights: whole-image tiles, two accumulator sets
+    _s2_case(2, 160, 12, 24, 64, 0.5, seed=8, with_ds=False)
