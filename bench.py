@@ -70,8 +70,33 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml_rows, self._stop, self._thr = [], threading.Event(), None
+
+    def _nvml_loop(self):
+        """NVML from a thread, every ~2 ms: the timed regions last tens of milliseconds, shorter than nvidia-smi's period."""
+        try:
+            import pynvml as N
+            import torch
+            N.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            names = (("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap))
+            while not self._stop.is_set():
+                sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.nvml_rows.append((sm, mx, [n for n, b in names if bits & b]))
+                time.sleep(0.002)
+        except Exception:
+            pass
 
     def start(self):
+        self._thr = threading.Thread(target=self._nvml_loop, daemon=True)
+        self._thr.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -86,7 +111,12 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1.0)
         sm, mx, reasons = [], 0.0, set()
+        for v, m, rs in self.nvml_rows:
+            sm.append(v); mx = max(mx, m); reasons.update(rs)
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
