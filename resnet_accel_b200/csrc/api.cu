@@ -1043,6 +1043,12 @@ int accel_avgpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, 
   if (n_planes <= 0) return ACCEL_OK;
   if (in_pitch == 0) in_pitch = w;
   if (in_pitch < w) return fail(ACCEL_INVALID_CONFIG, "row pitch smaller than the row");
+  if (w <= 16 && (in_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && n_planes < (1ll << 28)) {
+    accel::avgpool_i8_rows16_kernel<<<static_cast<unsigned>((n_planes * 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, out, static_cast<uint32_t>(n_planes), h, w, in_pitch);
+    CU(cudaGetLastError());
+    return ACCEL_OK;
+  }
   accel::avgpool_i8_kernel<<<grid_for(n_planes * 8, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, n_planes,
                                                                                                         h, w, in_pitch);
   CU(cudaGetLastError());

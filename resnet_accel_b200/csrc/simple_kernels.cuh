@@ -452,4 +452,36 @@ __global__ void avgpool_i8_kernel(const int8_t* __restrict__ x, int8_t* __restri
   }
 }
 
+// Rows of at most 16 pixels in 16-byte aligned, 16-byte-multiple pitches (the padded activation tensors): eight lanes per
+// plane, lane `sub` sums rows sub, sub + 8, ... with one 16-byte load each - a warp reads four whole planes, contiguous
+// when the pitch is 16.  Same rounding as above.
+__global__ void __launch_bounds__(256) avgpool_i8_rows16_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ out,
+                                                                uint32_t n_planes, int32_t H, int32_t W, int32_t in_pitch) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t pl = t >> 3;
+  const int sub = static_cast<int>(t & 7u);
+  const int hw = H * W;
+  uint32_t m[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int nv = W - 4 * i;
+    m[i] = nv >= 4 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : (1u << (8 * nv)) - 1u);
+  }
+  int s = 0;
+  if (pl < n_planes) {
+    const int8_t* base = x + static_cast<size_t>(pl) * H * in_pitch;
+    for (int r = sub; r < H; r += 8) {
+      const uint4 v = ldg_nc_128(base + static_cast<size_t>(r) * in_pitch);
+      s = __dp4a(static_cast<int>(v.x & m[0]), 0x01010101, s);
+      s = __dp4a(static_cast<int>(v.y & m[1]), 0x01010101, s);
+      s = __dp4a(static_cast<int>(v.z & m[2]), 0x01010101, s);
+      s = __dp4a(static_cast<int>(v.w & m[3]), 0x01010101, s);
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (sub == 0 && pl < n_planes) out[pl] = static_cast<int8_t>(min(127, max(-128, (s + hw / 2) / hw)));
+}
+
 }  // namespace accel

@@ -122,3 +122,21 @@ def test_pools_padded_rows():
     assert np.array_equal(out.cpu().numpy(), want)
     got = ops.avgpool_i8(xd).cpu().numpy()
     assert np.array_equal(got, np.stack([O.avgpool_global_int8(x[b]) for b in range(3)]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(5, 37, 7, 7), (2, 9, 14, 14), (3, 4, 19, 16), (1, 3, 1, 1), (2, 6, 9, 3)])
+def test_avgpool_padded_16_byte_rows(shape):
+    """Global average pool over tensors whose rows are padded to 16 bytes (the layer4 output of the network): the padding
+    bytes hold junk here and must not count."""
+    import torch
+    from resnet_accel_b200 import ops
+    rng = np.random.default_rng(sum(shape))
+    x = rng.integers(-128, 128, shape, dtype=np.int8)
+    xd = ops.alloc_padded(shape)
+    base = xd._base if xd._base is not None else xd
+    base.copy_(torch.randint(-128, 128, base.shape, dtype=torch.int8, device="cuda"))
+    xd.copy_(torch.from_numpy(x).cuda())
+    got = ops.avgpool_i8(xd).cpu().numpy()
+    assert np.array_equal(got, np.stack([O.avgpool_global_int8(x[b]) for b in range(shape[0])]))
+
