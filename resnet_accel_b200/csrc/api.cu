@@ -422,8 +422,6 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
 
   p.rows_in = stride == 2 ? 2 * p.R + 1 : p.R + 2;
   p.has_ds = plan_ds ? 1 : 0;
-  static const int l2_prefetch = std::getenv("ACCEL_WS_L2_PREFETCH") ? std::atoi(std::getenv("ACCEL_WS_L2_PREFETCH")) : 0;
-  p.l2_prefetch = l2_prefetch;
   p.acc_single = (s2_wide && plan_ds) ? 1 : 0;
   p.v_col = p.acc_single ? 256 : 128;
   p.w_chunk_bytes = accel::kWsChunkBytes + (plan_ds ? accel::kWsTapBytes : 0);
@@ -444,8 +442,6 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   const int fixed = 1024 /* alignment slack */ + accel::kWsSmemBar + p.w_slots * p.w_chunk_bytes;
   int a_slots = (kSmemWs - fixed) / p.a_stage_bytes;
   if (a_slots > accel::kWsMaxASlots) a_slots = accel::kWsMaxASlots;
-  static const int a_cap = std::getenv("ACCEL_WS_A_SLOTS") ? std::atoi(std::getenv("ACCEL_WS_A_SLOTS")) : 0;
-  if (a_cap > 0 && a_slots > a_cap) a_slots = a_cap;
   if (a_slots < 3) return kWsNotApplicable;
   p.a_slots = a_slots;
   p.row_stride = static_cast<uint32_t>(accel::kWsCk * P);          // bytes between staged image rows

@@ -83,7 +83,6 @@ struct WsParams {
   // is as large as it can be (N <= 128, a whole 14 x 14 image): with the fused 1x1 the three accumulators then take
   // one 512-column set (acc_single: Z1/U in [0, 256), V at 256; the epilogue no longer overlaps the next tile's MMAs).
   int32_t stride, rows_in, Ho, Wo, w_chunk_bytes, has_ds, acc_single, v_col;
-  int32_t l2_prefetch;         // items ahead of the loaders whose input rows are requested into L2 (0 = off)
   const uint8_t* wblob2;       // [group][chunk][4096]
   accel_epilogue epi2;
   int8_t* out2;
@@ -138,6 +137,10 @@ __device__ __forceinline__ void stg128(void* p, const uint4& v) {
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ uint32_t pack4_s8(int a, int b, int c, int d) {
+  return __byte_perm(__byte_perm(static_cast<uint32_t>(a), static_cast<uint32_t>(b), 0x0040),
+                     __byte_perm(static_cast<uint32_t>(c), static_cast<uint32_t>(d), 0x0040), 0x5410);
+}
 template <int B>
 __device__ __forceinline__ float i2f_s8_byte(uint32_t w) {     // float(int8 at byte B of w): one I2F with a byte selector
   float f;
@@ -166,29 +169,14 @@ __device__ __forceinline__ void ws_sat_bounds(float sf, int& lo, int& hi) {
 
 // 16 pixels of one output channel: accumulators -> int8, optional residual add
 // (golden_models.cpp:465-490), optional ReLU on the int8 value.  SAT: track the accumulator range of the chunk.
-// cvt.rni.sat.s8.f32 leaves the int8 in the low byte of the register; the byte permutes below take that byte as it is
-// (an int8_t return value would cost two more permutes per value to sign-extend).
-__device__ __forceinline__ uint32_t cvt_sat_s8_raw(float f) {
-  uint32_t v;
-  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(v) : "f"(f));
-  return v;
-}
-__device__ __forceinline__ uint32_t pack4_b0(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {      // byte 0 of each
-  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
-}
-// relu_int8 on four packed int8 when relu_mask is all ones (0: leave them): clear the bytes whose sign bit is set
-__device__ __forceinline__ uint32_t relu4_s8(uint32_t x, uint32_t relu_mask) {
-  return x & ~(__byte_perm(x, 0u, 0xba98) & relu_mask);
-}
 template <int RESMODE, bool SAT>
 __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)[16], const uint32_t (&u)[16], int bias, float sf,
                                           int relu_lo, int out_lo, const uint4& rbytes, int& amin, int& amax) {
   uint32_t packed[4];
   const uint32_t rw[4] = {rbytes.x, rbytes.y, rbytes.z, rbytes.w};
-  const uint32_t relu_mask = out_lo == 0 ? 0xFFFFFFFFu : 0u;        // out_lo is 0 (relu_int8) or -128 (none)
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    uint32_t q[4];
+    int q[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int e = 4 * w + b;
@@ -198,11 +186,16 @@ __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)
         amin = min(amin, acc);
       }
       const float f = __fmul_rn(__int2float_rn(acc), sf);
-      q[b] = cvt_sat_s8_raw(f);
-      if constexpr (RESMODE != 0 && RESMODE != 4) {
+      int r8 = cvt_sat_s8(f);
+      if constexpr (RESMODE == 4) {
+        // matched scales: the host checked that the reference's float sequence equals the saturating integer sum for all
+        // 65 536 (main, residual) pairs
+        const int rv = static_cast<int>(static_cast<int8_t>((rw[w] >> (8 * b)) & 0xffu));
+        r8 = min(max(r8 + rv, -128), 127);
+      } else if constexpr (RESMODE != 0) {
         const float rf = b == 0 ? i2f_s8_byte<0>(rw[w]) : b == 1 ? i2f_s8_byte<1>(rw[w]) : b == 2 ? i2f_s8_byte<2>(rw[w])
                                                                                                      : i2f_s8_byte<3>(rw[w]);
-        const float a = __fmul_rn(i2f_s8_byte<0>(q[b]), p.epi.res_scale_main);
+        const float a = __fmul_rn(__int2float_rn(r8), p.epi.res_scale_main);
         const float r = __fmul_rn(rf, p.epi.res_scale_res);
         const float sm = __fadd_rn(a, r);
         float d;
@@ -215,14 +208,11 @@ __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)
         } else {
           d = __fdiv_rn(sm, p.epi.res_scale_out);
         }
-        q[b] = cvt_sat_s8_raw(d);
+        r8 = cvt_sat_s8(d);
       }
+      q[b] = max(r8, out_lo);
     }
-    uint32_t pk = pack4_b0(q[0], q[1], q[2], q[3]);
-    // matched scales: the host checked that the reference's float sequence equals the saturating integer sum for all
-    // 65 536 (main, residual) pairs - four of them per packed saturating add
-    if constexpr (RESMODE == 4) pk = __vaddss4(pk, rw[w]);
-    packed[w] = relu4_s8(pk, relu_mask);
+    packed[w] = pack4_s8(q[0], q[1], q[2], q[3]);
   }
   return make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
@@ -344,20 +334,15 @@ __device__ __forceinline__ uint2 ldg64(const void* p) {
 template <bool SAT>
 __device__ __forceinline__ uint2 ws_epi8_even(const uint32_t (&z)[16], const uint32_t* u, const WsEpiConst& k, int n_valid, bool lane_ok,
                                               uint32_t& sat) {
-  uint32_t q[8];
+  int q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int acc = max(static_cast<int>(z[2 * e] + (u ? u[2 * e] : 0u)) + k.bias, k.relu_lo);
     const float f = __fmul_rn(__int2float_rn(acc), k.sf);
     if constexpr (SAT) sat += (lane_ok && e < n_valid && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
-    q[e] = cvt_sat_s8_raw(f);
+    q[e] = e < n_valid ? max(static_cast<int>(cvt_sat_s8(f)), k.out_lo) : 0;
   }
-  // bytes past the row end are stored as zeros (the row padding stays zero)
-  const uint32_t relu_mask = k.out_lo == 0 ? 0xFFFFFFFFu : 0u;
-  const uint32_t keep_lo = n_valid >= 4 ? 0xFFFFFFFFu : (n_valid <= 0 ? 0u : (1u << (8 * n_valid)) - 1u);
-  const uint32_t keep_hi = n_valid >= 8 ? 0xFFFFFFFFu : (n_valid <= 4 ? 0u : (1u << (8 * (n_valid - 4))) - 1u);
-  return make_uint2(relu4_s8(pack4_b0(q[0], q[1], q[2], q[3]), relu_mask) & keep_lo,
-                    relu4_s8(pack4_b0(q[4], q[5], q[6], q[7]), relu_mask) & keep_hi);
+  return make_uint2(pack4_s8(q[0], q[1], q[2], q[3]), pack4_s8(q[4], q[5], q[6], q[7]));
 }
 
 // The epilogue role of one warp for the whole launch (instantiated per variant: the variant is chosen once, outside the loop).
@@ -715,20 +700,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
           go[k] = ok ? static_cast<uint32_t>(goff[k] + (p.stride * y0 - 1) * p.in_pitch) : 0u;
         }
         const int8_t* src0 = p.x + static_cast<int64_t>(img) * p.C * p.H * p.in_pitch;
-        if constexpr (!TWIN) {
-          // The LDGSTS path sustains only so many bytes in flight per SM: ask L2 for the rows of a later item of this
-          // CTA now (one contiguous run of rows per channel, a channel per loader thread), so that its copies hit L2.
-          const uint32_t itp = it + static_cast<uint32_t>(p.l2_prefetch) * item_step;
-          const uint32_t ttp = dual ? 2u * itp + sub : itp;
-          if (p.l2_prefetch && itp < n_items && ttp < n_tiles) {
-            const uint32_t tip = fdiv(ttp, p.d_tpi);
-            const int y0p = static_cast<int>(ttp - tip * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
-            const int ya = max(p.stride * y0p - 1, 0), yb = min(p.stride * y0p - 1 + p.rows_in, p.H);
-            const uint32_t bytes = static_cast<uint32_t>((yb - ya) * p.in_pitch);
-            const int8_t* base = p.x + (static_cast<int64_t>(tip) * p.C * p.H + ya) * p.in_pitch;
-            for (int c = lt; c < p.C; c += kWsLoadThreads) prefetch_l2_bulk(base + static_cast<int64_t>(c) * p.H * p.in_pitch, bytes);
-          }
-        }
         for (uint32_t j = 0; j < n_chunks; ++j) {
           mbar_wait(&a_empty[as], aph ^ 1u);
           const uint32_t dst0 = a_addr + as * static_cast<uint32_t>(p.a_stage_bytes);
