@@ -16,8 +16,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaccel_b200.so")
 SOURCES = ["api.cu", "plan.cpp"]
-DEPS = ["api.cu", "plan.cpp", "plan.h", "ptx.cuh", "bsr_tc.cuh", "bsr_tcp.cuh", "simple_kernels.cuh",
-        os.path.join("..", "..", "include", "accel_b200.h")]
+# every file under csrc/ (a header left out of this list once made edits to it silently not rebuild) + the public header
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h"))) + [
+    os.path.join("..", "..", "include", "accel_b200.h")]
 
 
 def _nvcc() -> str:

@@ -83,6 +83,7 @@ struct WsParams {
   // is as large as it can be (N <= 128, a whole 14 x 14 image): with the fused 1x1 the three accumulators then take
   // one 512-column set (acc_single: Z1/U in [0, 256), V at 256; the epilogue no longer overlaps the next tile's MMAs).
   int32_t stride, rows_in, Ho, Wo, w_chunk_bytes, has_ds, acc_single, v_col;
+  int32_t l2_prefetch;
   const uint8_t* wblob2;       // [group][chunk][4096]
   accel_epilogue epi2;
   int8_t* out2;
@@ -137,10 +138,6 @@ __device__ __forceinline__ void stg128(void* p, const uint4& v) {
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ __forceinline__ uint32_t pack4_s8(int a, int b, int c, int d) {
-  return __byte_perm(__byte_perm(static_cast<uint32_t>(a), static_cast<uint32_t>(b), 0x0040),
-                     __byte_perm(static_cast<uint32_t>(c), static_cast<uint32_t>(d), 0x0040), 0x5410);
-}
 template <int B>
 __device__ __forceinline__ float i2f_s8_byte(uint32_t w) {     // float(int8 at byte B of w): one I2F with a byte selector
   float f;
@@ -169,14 +166,31 @@ __device__ __forceinline__ void ws_sat_bounds(float sf, int& lo, int& hi) {
 
 // 16 pixels of one output channel: accumulators -> int8, optional residual add
 // (golden_models.cpp:465-490), optional ReLU on the int8 value.  SAT: track the accumulator range of the chunk.
+// cvt.rni.sat.s8.f32 leaves the int8 in the low byte of the register; the byte permutes below take that byte as it is
+// (an int8_t return value would cost two more permutes per value to sign-extend).
+__device__ __forceinline__ uint32_t cvt_sat_s8_raw(float f) {
+  uint32_t v;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(v) : "f"(f));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack4_b0(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {      // byte 0 of each
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+// relu_int8 on four packed int8 when relu_mask is all ones (0: leave them): clear the bytes whose sign bit is set
+__device__ __forceinline__ uint32_t relu4_s8(uint32_t x, uint32_t relu_mask) {
+  uint32_t sign;      // 0xFF in every byte whose sign bit is set (prmt's sign-replicate selectors; __byte_perm keeps only 3 selector bits)
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(sign) : "r"(x));
+  return x & ~(sign & relu_mask);
+}
 template <int RESMODE, bool SAT>
 __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)[16], const uint32_t (&u)[16], int bias, float sf,
                                           int relu_lo, int out_lo, const uint4& rbytes, int& amin, int& amax) {
   uint32_t packed[4];
   const uint32_t rw[4] = {rbytes.x, rbytes.y, rbytes.z, rbytes.w};
+  const uint32_t relu_mask = out_lo == 0 ? 0xFFFFFFFFu : 0u;        // out_lo is 0 (relu_int8) or -128 (none)
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    int q[4];
+    uint32_t q[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int e = 4 * w + b;
@@ -186,16 +200,11 @@ __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)
         amin = min(amin, acc);
       }
       const float f = __fmul_rn(__int2float_rn(acc), sf);
-      int r8 = cvt_sat_s8(f);
-      if constexpr (RESMODE == 4) {
-        // matched scales: the host checked that the reference's float sequence equals the saturating integer sum for all
-        // 65 536 (main, residual) pairs
-        const int rv = static_cast<int>(static_cast<int8_t>((rw[w] >> (8 * b)) & 0xffu));
-        r8 = min(max(r8 + rv, -128), 127);
-      } else if constexpr (RESMODE != 0) {
+      q[b] = cvt_sat_s8_raw(f);
+      if constexpr (RESMODE != 0 && RESMODE != 4) {
         const float rf = b == 0 ? i2f_s8_byte<0>(rw[w]) : b == 1 ? i2f_s8_byte<1>(rw[w]) : b == 2 ? i2f_s8_byte<2>(rw[w])
                                                                                                      : i2f_s8_byte<3>(rw[w]);
-        const float a = __fmul_rn(__int2float_rn(r8), p.epi.res_scale_main);
+        const float a = __fmul_rn(i2f_s8_byte<0>(q[b]), p.epi.res_scale_main);
         const float r = __fmul_rn(rf, p.epi.res_scale_res);
         const float sm = __fadd_rn(a, r);
         float d;
@@ -208,11 +217,14 @@ __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)
         } else {
           d = __fdiv_rn(sm, p.epi.res_scale_out);
         }
-        r8 = cvt_sat_s8(d);
+        q[b] = cvt_sat_s8_raw(d);
       }
-      q[b] = max(r8, out_lo);
     }
-    packed[w] = pack4_s8(q[0], q[1], q[2], q[3]);
+    uint32_t pk = pack4_b0(q[0], q[1], q[2], q[3]);
+    // matched scales: the host checked that the reference's float sequence equals the saturating integer sum for all
+    // 65 536 (main, residual) pairs - four of them per packed saturating add
+    if constexpr (RESMODE == 4) pk = __vaddss4(pk, rw[w]);
+    packed[w] = relu4_s8(pk, relu_mask);
   }
   return make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
@@ -334,15 +346,20 @@ __device__ __forceinline__ uint2 ldg64(const void* p) {
 template <bool SAT>
 __device__ __forceinline__ uint2 ws_epi8_even(const uint32_t (&z)[16], const uint32_t* u, const WsEpiConst& k, int n_valid, bool lane_ok,
                                               uint32_t& sat) {
-  int q[8];
+  uint32_t q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int acc = max(static_cast<int>(z[2 * e] + (u ? u[2 * e] : 0u)) + k.bias, k.relu_lo);
     const float f = __fmul_rn(__int2float_rn(acc), k.sf);
     if constexpr (SAT) sat += (lane_ok && e < n_valid && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
-    q[e] = e < n_valid ? max(static_cast<int>(cvt_sat_s8(f)), k.out_lo) : 0;
+    q[e] = cvt_sat_s8_raw(f);
   }
-  return make_uint2(pack4_s8(q[0], q[1], q[2], q[3]), pack4_s8(q[4], q[5], q[6], q[7]));
+  // bytes past the row end are stored as zeros (the row padding stays zero)
+  const uint32_t relu_mask = k.out_lo == 0 ? 0xFFFFFFFFu : 0u;
+  const uint32_t keep_lo = n_valid >= 4 ? 0xFFFFFFFFu : (n_valid <= 0 ? 0u : (1u << (8 * n_valid)) - 1u);
+  const uint32_t keep_hi = n_valid >= 8 ? 0xFFFFFFFFu : (n_valid <= 4 ? 0u : (1u << (8 * (n_valid - 4))) - 1u);
+  return make_uint2(relu4_s8(pack4_b0(q[0], q[1], q[2], q[3]), relu_mask) & keep_lo,
+                    relu4_s8(pack4_b0(q[4], q[5], q[6], q[7]), relu_mask) & keep_hi);
 }
 
 // The epilogue role of one warp for the whole launch (instantiated per variant: the variant is chosen once, outside the loop).

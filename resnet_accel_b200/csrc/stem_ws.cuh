@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
                        static_cast<int64_t>(yp) * p.out_pitch;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {               // 4 pooled outputs per group
-          int qv[4];
+          uint32_t qv[4];
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const int xp = xp_lo + 4 * g + b;
@@ -212,9 +212,9 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
             m = max(m, j > 0 ? vm[j > 0 ? j - 1 : 0] : vleft);     // column -1 is padding: vleft stays INT_MIN in the lower half
             if (2 * xp + 1 < p.Wc) m = max(m, vm[j + 1]);
             const int a = max(m + bias, relu_lo);
-            qv[b] = xp < xp_hi ? static_cast<int>(cvt_sat_s8(__fmul_rn(__int2float_rn(a), sf))) : 0;
+            qv[b] = xp < xp_hi ? cvt_sat_s8_raw(__fmul_rn(__int2float_rn(a), sf)) : 0u;
           }
-          if (xp_lo + 4 * g < xp_hi) *reinterpret_cast<uint32_t*>(orow + xp_lo + 4 * g) = pack4_s8(qv[0], qv[1], qv[2], qv[3]);
+          if (xp_lo + 4 * g < xp_hi) *reinterpret_cast<uint32_t*>(orow + xp_lo + 4 * g) = pack4_b0(qv[0], qv[1], qv[2], qv[3]);
         }
       }
     }
