@@ -83,7 +83,6 @@ struct WsParams {
   // is as large as it can be (N <= 128, a whole 14 x 14 image): with the fused 1x1 the three accumulators then take
   // one 512-column set (acc_single: Z1/U in [0, 256), V at 256; the epilogue no longer overlaps the next tile's MMAs).
   int32_t stride, rows_in, Ho, Wo, w_chunk_bytes, has_ds, acc_single, v_col;
-  int32_t l2_prefetch;
   const uint8_t* wblob2;       // [group][chunk][4096]
   accel_epilogue epi2;
   int8_t* out2;
