@@ -97,7 +97,8 @@ ACCEL_API int accel_device_check(void);
  * (kernel entry, prologue done, first activation stage acquired / published, main loop done by the producers,
  * accumulators complete, epilogue done, CTA exit).  The buffer must hold 8 int64 per CTA of the largest launch. */
 ACCEL_API void accel_debug_set_timeline(long long* dev_buffer);
-/* Developer aid: event counters of this process.  which = 0: launches of the weight-stationary convolution kernel. */
+/* Developer aid: event counters of this process.  which = 0: launches of the weight-stationary convolution kernels,
+ * 1: launches of the dense-equivalent GEMM kernel (gemm_ws_kernel). */
 ACCEL_API long long accel_debug_counter(int which);
 
 /* --- weight plan: replaces AccelDriver.load_sparse_weights (sw/host/accel.py:177-236) and
@@ -168,6 +169,21 @@ ACCEL_API int accel_conv_pool_bsr_i8(const accel_plan* plan, const int8_t* input
 ACCEL_API int accel_plan_conv_ws_bytes(const accel_plan* plan, int32_t c_in, int32_t c_out, int32_t ksize, size_t* bytes);
 ACCEL_API int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32_t c_in, int32_t c_out, int32_t ksize,
                                void* workspace_dev, size_t workspace_bytes, accel_stream_t stream);
+
+/* --- dense-equivalent layout for GEMMs (csrc/gemm_ws.cuh).  Optional: when a plan has been prepared and the tensors of an
+ * accel_bsr_gemm_i8 call allow it (16-byte aligned activation rows, a strided output layout), that call runs
+ * gemm_ws_kernel: the stored blocks are scattered once into a plain row-major int8 matrix [channels, K] (neither padded
+ * 14 -> 16), both operands reach the tensor core by TMA, CTA pairs share 256 x 256 tiles (tcgen05.mma.cta_group::2), and
+ * (channel tile, 128-k chunk) regions without any non-zero weight are skipped.  Same results as the gather kernel, bit for
+ * bit (gemm_bsr_int8_golden, sw/golden/golden_fc1_test.py:49-108).  gemm_ws_bytes reports the workspace (0 = no such
+ * layout for this plan); gemm_ws_prepare fills it (`workspace_dev` 256-byte aligned, owned by the caller until
+ * gemm_ws_release or plan destruction; synchronises `stream`).  live_chunks: number of (tile, chunk) regions the kernel
+ * visits per 256-row activation tile, for cta_group 1 or 2 (tooling). */
+ACCEL_API int accel_plan_gemm_ws_bytes(const accel_plan* plan, size_t* bytes);
+ACCEL_API int accel_plan_gemm_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, void* workspace_dev, size_t workspace_bytes,
+                               accel_stream_t stream);
+ACCEL_API void accel_plan_gemm_ws_release(accel_plan* plan);
+ACCEL_API int64_t accel_plan_gemm_ws_live_chunks(const accel_plan* plan, int32_t cta_group);
 
 /* --- reference-shaped CUDA-core kernels: any block size (4/8/14/16 fixtures), Convention B or A.
  * Same arithmetic as above, used for the generic-block path and as an on-device cross-check.

@@ -61,6 +61,10 @@ SYMBOLS = {
     "accel_plan_export_mma": (_I64, [_P, _P, _I64]),
     "accel_plan_conv_ws_bytes": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_SZ)]),
     "accel_plan_conv_ws_prepare": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _SZ, _P]),
+    "accel_plan_gemm_ws_bytes": (C.c_int, [_P, C.POINTER(_SZ)]),
+    "accel_plan_gemm_ws_prepare": (C.c_int, [_P, _P, _P, _SZ, _P]),
+    "accel_plan_gemm_ws_release": (None, [_P]),
+    "accel_plan_gemm_ws_live_chunks": (_I64, [_P, _I32]),
     "accel_bsr_gemm_i8": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(Epilogue), _P, C.POINTER(OutLayout), _P]),
     "accel_conv_bsr_i8": (C.c_int, [_P, _P, C.POINTER(ConvGeom), C.POINTER(Epilogue), _P, C.POINTER(OutLayout), _P]),
     "accel_conv_bsr_i8_dual": (C.c_int, [_P, _P, _P, C.POINTER(ConvGeom), C.POINTER(Epilogue), _P, C.POINTER(Epilogue), _P,

@@ -18,6 +18,7 @@
 #include "bsr_tc.cuh"
 #include "bsr_tcp.cuh"
 #include "conv_ws.cuh"
+#include "gemm_ws.cuh"
 #include "stem_ws.cuh"
 #include "plan.h"
 #include "simple_kernels.cuh"
@@ -57,13 +58,17 @@ int grid_for(int64_t work_items, int threads, int per_sm = 8) {
 }
 
 long long* g_timeline = nullptr;   // accel_debug_set_timeline
-int g_dbg_flags = 0;
+int g_dbg_flags = std::getenv("ACCEL_DBG_FLAGS") ? std::atoi(std::getenv("ACCEL_DBG_FLAGS")) : 0;   // developer aid (stage isolation)
 bool g_no_persist = std::getenv("ACCEL_NO_PERSIST") != nullptr;   // developer switch: one-shot kernel everywhere
 long long g_ws_launches = 0;         // accel_debug_counter(0)
 bool g_ws_s2_narrow = std::getenv("ACCEL_WS_S2_NARROW") != nullptr;   // developer switch: 64-pixel stride-2 tiles even with streamed weights
 bool g_no_pdl = std::getenv("ACCEL_NO_PDL") != nullptr;            // developer switch: plain stream-ordered launches
 bool g_no_twin = std::getenv("ACCEL_NO_TWIN") != nullptr;          // developer switch: one image per tile even for 7-pixel rows
 bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
+bool g_no_gemm_ws = std::getenv("ACCEL_NO_GEMM_WS") != nullptr;    // developer switch: GEMMs stay on the gather kernels
+int g_gemm_ws_cg = std::getenv("ACCEL_GEMM_WS_CG") ? std::atoi(std::getenv("ACCEL_GEMM_WS_CG")) : 2;   // 1: no CTA pairs
+int g_gemm_ws_stages = std::getenv("ACCEL_GEMM_WS_STAGES") ? std::atoi(std::getenv("ACCEL_GEMM_WS_STAGES")) : 0;
+long long g_gw_launches = 0;         // accel_debug_counter(1)
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
 constexpr int kSmemTwoCtas = 113 * 1024;    // per CTA when two CTAs share an SM (227 KB usable, 1 KB reserved each)
@@ -111,6 +116,13 @@ WsKernelFn ws_kernel_ptr(int mode, int resmode, bool sat) {
 }
 const void* ws_kernel_fn(int mode, int resmode, bool sat) { return reinterpret_cast<const void*>(ws_kernel_ptr(mode, resmode, sat)); }
 
+using GwKernelFn = void (*)(accel::GwLaunch);
+GwKernelFn gw_kernel_ptr(int cg, int outk) {
+  if (cg == 2) return outk == 0 ? accel::gemm_ws_kernel<2, 0> : (outk == 1 ? accel::gemm_ws_kernel<2, 1> : accel::gemm_ws_kernel<2, 2>);
+  return outk == 0 ? accel::gemm_ws_kernel<1, 0> : (outk == 1 ? accel::gemm_ws_kernel<1, 1> : accel::gemm_ws_kernel<1, 2>);
+}
+const void* gw_kernel_fn(int cg, int outk) { return reinterpret_cast<const void*>(gw_kernel_ptr(cg, outk)); }
+
 void set_kernel_attrs() {
   const void* fns[] = {reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeGemm>),
                        reinterpret_cast<const void*>(accel::bsr_tc_kernel<accel::kModeConv3>),
@@ -135,6 +147,10 @@ void set_kernel_attrs() {
   if (g_attr_err == cudaSuccess)
     g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::stem_ws_kernel),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
+  for (int cg = 1; cg <= 2; ++cg)
+    for (int k = 0; k < 3; ++k)
+      if (g_attr_err == cudaSuccess)
+        g_attr_err = cudaFuncSetAttribute(gw_kernel_fn(cg, k), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
 }
 
 int check_epilogue(const accel_epilogue* epi, const accel_out_layout* lay, const void* out, int32_t max_channels) {
@@ -214,7 +230,8 @@ EncodeTiledFn encode_tiled_fn() {
 }
 // int8 tensor, dims / box innermost first, strides in bytes for dims 1..rank-1 (multiples of 16)
 bool encode_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                 const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
+                 const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE,
+                 CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint64_t gd[4], gs[3];
@@ -222,7 +239,7 @@ bool encode_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* di
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs, bx, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -333,10 +350,22 @@ struct WsState {
   uint16_t masks[accel::kWsMaxGroups * accel::kWsMaxChunks] = {};
 };
 
+// dense-equivalent GEMM state of a plan (gemm_ws.cuh)
+struct GwState {
+  bool ready = false;
+  int64_t n_pad = 0, k_pad = 0;            // Wd is [n_pad, k_pad] int8 row-major (n_pad multiple of 256, k_pad of 128)
+  int32_t n128 = 0, n_chunks = 0;          // 128-channel tiles, 128-byte K chunks
+  const int8_t* wd = nullptr;
+  const uint16_t* klist[2] = {nullptr, nullptr};    // [CG - 1]: live-chunk lists per tile of 128 * CG channels
+  const uint16_t* kcount[2] = {nullptr, nullptr};
+  int64_t live_chunks[2] = {0, 0};         // sum of the list lengths (tooling)
+};
+
 struct accel_plan {
   accel::Plan p;
   std::vector<int32_t> row_ptr, col_idx;   // host copies of the BSR structure (for later re-layouts)
   WsState ws;
+  GwState gw;
 };
 
 namespace {
@@ -488,6 +517,73 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   return ACCEL_OK;
 }
 
+
+// Route a GEMM to gemm_ws_kernel when the plan carries the dense-equivalent layout and the tensors allow TMA
+// (16-byte aligned activation rows, a strided output layout without padded image rows); kWsNotApplicable otherwise.
+int try_gemm_ws(const accel_plan* plan, const int8_t* act, int64_t M, int64_t K, int64_t lda, const accel_epilogue* epi, void* out,
+                const accel_out_layout* lay, cudaStream_t st) {
+  const GwState& G = plan->gw;
+  if (g_no_gemm_ws || !G.ready || M <= 0 || K <= 0) return kWsNotApplicable;
+  if ((reinterpret_cast<uintptr_t>(act) & 15) || (lda & 15) || lay->row_len != 0 || epi->chan_absmax) return kWsNotApplicable;
+  if (epi->n_channels <= 0) return kWsNotApplicable;
+  const int cg = g_gemm_ws_cg == 1 ? 1 : 2;
+  std::call_once(g_attr_once, set_kernel_attrs);
+  if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(smem)");
+  static thread_local accel::GwLaunch L;
+  accel::GwParams& p = L.p;
+  std::memset(&p, 0, sizeof(p));
+  const uint64_t wdims[2] = {static_cast<uint64_t>(G.k_pad), static_cast<uint64_t>(G.n_pad)};
+  const uint64_t wstr[1] = {static_cast<uint64_t>(G.k_pad)};
+  const uint64_t xdims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+  const uint64_t xstr[1] = {static_cast<uint64_t>(lda)};
+  const uint32_t box[2] = {static_cast<uint32_t>(accel::kGwKc), 128u};
+  if (!encode_tmap(&L.tmap_w, G.wd, 2, wdims, wstr, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
+      !encode_tmap(&L.tmap_x, act, 2, xdims, xstr, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+    return kWsNotApplicable;
+  p.M = M;
+  // channel tiles: only those that hold channels the caller wants written
+  const int tile_ch = accel::kGwCh * cg;
+  int n_ct = (epi->n_channels + tile_ch - 1) / tile_ch;
+  const int n_ct_plan = cg == 2 ? G.n128 / 2 : G.n128;
+  if (n_ct > n_ct_plan) return kWsNotApplicable;       // n_channels <= nbr * 14 <= n_pad: cannot happen
+  p.n_ch_tiles = n_ct;
+  const int64_t n_rt = (M + accel::kGwRows - 1) / accel::kGwRows;
+  if (n_rt * n_ct >= (1ll << 31)) return kWsNotApplicable;
+  p.n_row_tiles = static_cast<int32_t>(n_rt);
+  const int stage_bytes = accel::kGwBoxBytes * (cg == 2 ? 2 : 3);
+  int stages = (kSmemWs - 1024 - accel::kGwSmemBar) / stage_bytes;
+  if (stages > accel::kGwMaxStages) stages = accel::kGwMaxStages;
+  if (g_gemm_ws_stages >= 2 && g_gemm_ws_stages < stages) stages = g_gemm_ws_stages;
+  p.n_stages = stages;
+  p.klist = G.klist[cg - 1]; p.kcount = G.kcount[cg - 1]; p.klist_stride = G.n_chunks;
+  p.k_chunks_x = static_cast<int32_t>((K + accel::kGwKc - 1) / accel::kGwKc);
+  p.epi = *epi;
+  if (epi->residual) {
+    p.res_fast = residual_fast_divide_ok(epi->res_scale_main, epi->res_scale_res, epi->res_scale_out) ? 1 : 0;
+    p.res_rcp = 1.0f / epi->res_scale_out;
+  }
+  p.out = out; p.lay = *lay;
+  p.single_image = lay->rows_per_image >= M ? 1 : 0;
+  p.d_rpi = accel::make_fastdiv(static_cast<uint32_t>(lay->rows_per_image < (1ll << 31) ? lay->rows_per_image : 1));
+  p.dbg = g_dbg_flags;
+  const int outk = (epi->flags & ACCEL_OUT_I32) ? 0 : ((epi->flags & ACCEL_OUT_I8) ? 1 : 2);
+  const int64_t tiles = n_rt * n_ct;
+  const int units_max = cg == 2 ? sm_count() / 2 : sm_count();
+  const int units = static_cast<int>(tiles < units_max ? tiles : units_max);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(units * cg)); cfg.blockDim = dim3(accel::kGwThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(1024 + accel::kGwSmemBar + stages * stage_bytes); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cg); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gw_kernel_ptr(cg, outk), L);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "gemm_ws_kernel launch");
+  ++g_gw_launches;
+  return ACCEL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -501,7 +597,7 @@ void accel_debug_set_timeline(long long* dev_buffer) {
   g_dbg_flags = f ? std::atoi(f) : 0;
 }
 
-long long accel_debug_counter(int which) { return which == 0 ? g_ws_launches : -1; }
+long long accel_debug_counter(int which) { return which == 0 ? g_ws_launches : (which == 1 ? g_gw_launches : -1); }
 
 int accel_device_check(void) {
   int dev = 0;
@@ -592,6 +688,93 @@ int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32
   return ACCEL_OK;
 }
 
+static size_t gw_align(size_t v) { return (v + 255) / 256 * 256; }
+
+int accel_plan_gemm_ws_bytes(const accel_plan* plan, size_t* bytes) {
+  if (!plan || !bytes) return fail(ACCEL_INVALID_CONFIG, "null argument");
+  const int64_t n_pad = (static_cast<int64_t>(plan->p.nbr) * accel::kBlock + 255) / 256 * 256;
+  const int64_t k_pad = (static_cast<int64_t>(plan->p.nbc) * accel::kBlock + 127) / 128 * 128;
+  *bytes = 0;
+  if (n_pad == 0 || k_pad == 0 || k_pad / 128 > 65535) return ACCEL_OK;      // nothing to multiply / chunk index overflows u16
+  const size_t n128 = static_cast<size_t>(n_pad / 128), nch = static_cast<size_t>(k_pad / 128);
+  *bytes = gw_align(static_cast<size_t>(n_pad) * k_pad) + gw_align(n128 * nch) /* flags */ +
+           gw_align(n128 * nch * 2) + gw_align(n128 * 2) + gw_align(n128 / 2 * nch * 2) + gw_align(n128) +
+           gw_align(static_cast<size_t>(plan->p.nnz) * 8);
+  return ACCEL_OK;
+}
+
+int accel_plan_gemm_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, void* workspace_dev, size_t workspace_bytes,
+                               accel_stream_t stream) {
+  if (!plan || !workspace_dev) return fail(ACCEL_INVALID_CONFIG, "null plan / workspace");
+  size_t need = 0;
+  accel_plan_gemm_ws_bytes(plan, &need);
+  if (need == 0) return fail(ACCEL_INVALID_CONFIG, "plan has no dense-equivalent GEMM layout");
+  if (workspace_bytes < need) return fail(ACCEL_MEMORY_ERROR, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace_dev) & 255) return fail(ACCEL_MEMORY_ERROR, "workspace not 256-byte aligned");
+  const int64_t nnz = plan->p.nnz;
+  if (nnz > 0 && !blocks_dev) return fail(ACCEL_INVALID_CONFIG, "null blocks");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GwState& G = plan->gw;
+  G.ready = false;
+  G.n_pad = (static_cast<int64_t>(plan->p.nbr) * accel::kBlock + 255) / 256 * 256;
+  G.k_pad = (static_cast<int64_t>(plan->p.nbc) * accel::kBlock + 127) / 128 * 128;
+  G.n128 = static_cast<int32_t>(G.n_pad / 128); G.n_chunks = static_cast<int32_t>(G.k_pad / 128);
+  const size_t n128 = static_cast<size_t>(G.n128), nch = static_cast<size_t>(G.n_chunks);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  int8_t* wd = reinterpret_cast<int8_t*>(ws);
+  uint8_t* flags = ws + gw_align(static_cast<size_t>(G.n_pad) * G.k_pad);
+  uint16_t* kl1 = reinterpret_cast<uint16_t*>(flags + gw_align(n128 * nch));
+  uint16_t* kc1 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(kl1) + gw_align(n128 * nch * 2));
+  uint16_t* kl2 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(kc1) + gw_align(n128 * 2));
+  uint16_t* kc2 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(kl2) + gw_align(n128 / 2 * nch * 2));
+  int32_t* d_row = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(kc2) + gw_align(n128));
+  CU(cudaMemsetAsync(wd, 0, static_cast<size_t>(G.n_pad) * G.k_pad, st));
+  std::vector<int32_t> blk_row(static_cast<size_t>(nnz));
+  for (int32_t br = 0; br < plan->p.nbr; ++br)
+    for (int32_t i = plan->row_ptr[br]; i < plan->row_ptr[br + 1]; ++i) blk_row[i] = br;
+  if (nnz > 0) {
+    int32_t* d_col = d_row + nnz;
+    CU(cudaMemcpyAsync(d_row, blk_row.data(), static_cast<size_t>(nnz) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_col, plan->col_idx.data(), static_cast<size_t>(nnz) * 4, cudaMemcpyHostToDevice, st));
+    accel::gw_scatter_kernel<<<static_cast<unsigned>(nnz), 64, 0, st>>>(blocks_dev, d_row, d_col, nnz, G.k_pad, wd);
+    CU(cudaGetLastError());
+  }
+  accel::gw_flags_kernel<<<dim3(static_cast<unsigned>(nch), static_cast<unsigned>(n128)), 128, 0, st>>>(wd, G.k_pad, G.n_chunks, flags);
+  CU(cudaGetLastError());
+  std::vector<uint8_t> hflags(n128 * nch);
+  CU(cudaMemcpyAsync(hflags.data(), flags, n128 * nch, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  // live-chunk lists: per 128-channel tile (CG = 1) and per 256-channel tile (CG = 2)
+  std::vector<uint16_t> l1(n128 * nch, 0), c1(n128, 0), l2(n128 / 2 * nch, 0), c2(n128 / 2, 0);
+  G.live_chunks[0] = G.live_chunks[1] = 0;
+  for (size_t t = 0; t < n128; ++t)
+    for (size_t j = 0; j < nch; ++j)
+      if (hflags[t * nch + j]) l1[t * nch + c1[t]++] = static_cast<uint16_t>(j);
+  for (size_t t = 0; t < n128 / 2; ++t)
+    for (size_t j = 0; j < nch; ++j)
+      if (hflags[2 * t * nch + j] | hflags[(2 * t + 1) * nch + j]) l2[t * nch + c2[t]++] = static_cast<uint16_t>(j);
+  for (size_t t = 0; t < n128; ++t) G.live_chunks[0] += c1[t];
+  for (size_t t = 0; t < n128 / 2; ++t) G.live_chunks[1] += c2[t];
+  CU(cudaMemcpyAsync(kl1, l1.data(), l1.size() * 2, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(kc1, c1.data(), c1.size() * 2, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(kl2, l2.data(), l2.size() * 2, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(kc2, c2.data(), c2.size() * 2, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));     // the host vectors are pageable
+  G.wd = wd;
+  G.klist[0] = kl1; G.kcount[0] = kc1; G.klist[1] = kl2; G.kcount[1] = kc2;
+  G.ready = true;
+  return ACCEL_OK;
+}
+
+void accel_plan_gemm_ws_release(accel_plan* plan) {
+  if (plan) plan->gw.ready = false;
+}
+
+int64_t accel_plan_gemm_ws_live_chunks(const accel_plan* plan, int32_t cta_group) {
+  if (!plan || !plan->gw.ready || cta_group < 1 || cta_group > 2) return -1;
+  return plan->gw.live_chunks[cta_group - 1];
+}
+
 int accel_plan_upload(accel_plan* plan, const int8_t* blocks_dev, void* workspace_dev, size_t workspace_bytes,
                       accel_stream_t stream) {
   if (!plan || !workspace_dev) return fail(ACCEL_INVALID_CONFIG, "null plan / workspace");
@@ -678,6 +861,8 @@ int accel_bsr_gemm_i8(const accel_plan* plan, const int8_t* act, int64_t M, int6
   if (K >= 131072) return fail(ACCEL_INVALID_CONFIG, "K >= 131072 could overflow the INT32 accumulator");
   int rc = check_epilogue(epi, layout, out, plan->p.nbr * accel::kBlock);
   if (rc) return rc;
+  rc = try_gemm_ws(plan, act, M, K, lda, epi, out, layout, static_cast<cudaStream_t>(stream));
+  if (rc != kWsNotApplicable) return rc;
   accel::TcParams prm;
   std::memset(&prm, 0, sizeof(prm));
   prm.x = act; prm.M = M; prm.K = static_cast<int32_t>(K); prm.lda = lda;

@@ -12,6 +12,8 @@ from . import _lib
 from ._lib import AcceleratorError, ConvGeom, Epilogue, OutLayout, check
 
 BLOCK = 14
+# GEMMs with at least this many activation rows build the dense-equivalent layout of csrc/gemm_ws.cuh on first use
+GEMM_WS_MIN_ROWS = int(__import__("os").environ.get("ACCEL_GEMM_WS_MIN_ROWS", "128"))
 
 
 def _require_cuda() -> torch.device:
@@ -105,6 +107,7 @@ class BsrPlan:
         self.row_ptr, self.col_idx = rp, ci
         self._blocks = blk                      # kept for later re-layouts (conv_ws)
         self._ws_conv = {}                      # (c_in, c_out, ksize) -> workspace tensor (None: no such path)
+        self._ws_gemm = None                    # dense-equivalent GEMM layout: None = not built yet, False = no such path
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -132,6 +135,22 @@ class BsrPlan:
         check(L.accel_plan_conv_ws_prepare(self._h, _ptr(self._blocks) if self.col_idx.size else None, key[0], key[1], key[2],
                                            ptr, int(nbytes.value), _stream()))
         self._ws_conv[key] = buf
+
+    def _prepare_gemm_ws(self) -> None:
+        """Dense-equivalent layout for GEMMs (csrc/gemm_ws.cuh), built once per plan on the first large GEMM."""
+        if self._ws_gemm is not None:
+            return
+        L = _lib.lib()
+        nbytes = C.c_size_t()
+        check(L.accel_plan_gemm_ws_bytes(self._h, C.byref(nbytes)))
+        if nbytes.value == 0:
+            self._ws_gemm = False
+            return
+        buf = torch.empty(int(nbytes.value) + 256, dtype=torch.uint8, device=self.device)
+        ptr = buf.data_ptr() + (-buf.data_ptr()) % 256
+        check(L.accel_plan_gemm_ws_prepare(self._h, _ptr(self._blocks) if self.col_idx.size else None, ptr, int(nbytes.value),
+                                           _stream()))
+        self._ws_gemm = buf
 
     @property
     def n_out_padded(self) -> int:
@@ -185,6 +204,8 @@ class BsrPlan:
                 raise AcceleratorError(_lib.INVALID_CONFIG, "residual must have the output's shape and row stride")
         e, keep = self._epilogue(out_kind, n_channels, chan_scale, bias, relu, residual, res_scales, sat_count,
                                  chan_absmax, relu_out)
+        if M >= GEMM_WS_MIN_ROWS and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0 and chan_absmax is None:
+            self._prepare_gemm_ws()
         lay = OutLayout(max(M, 1), 0, 1, out.stride(0) if M else n_channels, 0, 0)
         check(_lib.lib().accel_bsr_gemm_i8(self._h, _ptr(x), M, K, x.stride(0) if M else K, C.byref(e), _ptr(out),
                                            C.byref(lay), _stream()))
