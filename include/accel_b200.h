@@ -169,6 +169,8 @@ ACCEL_API int accel_conv_pool_bsr_i8(const accel_plan* plan, const int8_t* input
 ACCEL_API int accel_plan_conv_ws_bytes(const accel_plan* plan, int32_t c_in, int32_t c_out, int32_t ksize, size_t* bytes);
 ACCEL_API int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32_t c_in, int32_t c_out, int32_t ksize,
                                void* workspace_dev, size_t workspace_bytes, accel_stream_t stream);
+/* Forget the prepared layout (call before freeing or reusing its workspace): later convolutions take the gather kernels. */
+ACCEL_API void accel_plan_conv_ws_release(accel_plan* plan);
 
 /* --- dense-equivalent layout for GEMMs (csrc/gemm_ws.cuh).  Optional: when a plan has been prepared and the tensors of an
  * accel_bsr_gemm_i8 call allow it (16-byte aligned activation rows, a strided output layout), that call runs

@@ -61,6 +61,7 @@ SYMBOLS = {
     "accel_plan_export_mma": (_I64, [_P, _P, _I64]),
     "accel_plan_conv_ws_bytes": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_SZ)]),
     "accel_plan_conv_ws_prepare": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _SZ, _P]),
+    "accel_plan_conv_ws_release": (None, [_P]),
     "accel_plan_gemm_ws_bytes": (C.c_int, [_P, C.POINTER(_SZ)]),
     "accel_plan_gemm_ws_prepare": (C.c_int, [_P, _P, _P, _SZ, _P]),
     "accel_plan_gemm_ws_release": (None, [_P]),

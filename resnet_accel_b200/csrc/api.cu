@@ -39,15 +39,22 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
   } while (0)
 
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+// SM count of the CURRENT device (a process may drive several GPUs)
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 // grid for grid-stride kernels: a multiple of the SM count, capped by the work
 int grid_for(int64_t work_items, int threads, int per_sm = 8) {
@@ -69,8 +76,11 @@ bool g_no_gemm_ws = std::getenv("ACCEL_NO_GEMM_WS") != nullptr;    // developer 
 int g_gemm_ws_cg = std::getenv("ACCEL_GEMM_WS_CG") ? std::atoi(std::getenv("ACCEL_GEMM_WS_CG")) : 2;   // 1: no CTA pairs
 int g_gemm_ws_stages = std::getenv("ACCEL_GEMM_WS_STAGES") ? std::atoi(std::getenv("ACCEL_GEMM_WS_STAGES")) : 0;
 long long g_gw_launches = 0;         // accel_debug_counter(1)
-std::once_flag g_attr_once;
-cudaError_t g_attr_err = cudaSuccess;
+// cudaFuncSetAttribute is per device: one flag and one status per device ordinal
+std::once_flag g_attr_once_dev[kMaxDevices];
+cudaError_t g_attr_err_dev[kMaxDevices] = {};
+#define g_attr_once g_attr_once_dev[current_device()]
+#define g_attr_err g_attr_err_dev[current_device()]
 constexpr int kSmemTwoCtas = 113 * 1024;    // per CTA when two CTAs share an SM (227 KB usable, 1 KB reserved each)
 constexpr int kSmemOneCta = 200 * 1024;
 constexpr int kSmemPersist = 220 * 1024;    // the persistent kernel owns its SM
@@ -635,6 +645,10 @@ int accel_plan_conv_ws_bytes(const accel_plan* plan, int32_t c_in, int32_t c_out
   if (!ws_geometry_ok(plan, c_in, c_out, ksize)) return ACCEL_OK;          // 0 bytes: this geometry has no such path
   *bytes = ws_blob_bytes(c_in, c_out, ksize * ksize) + (static_cast<size_t>(plan->p.nnz) * 8 + 255) / 256 * 256;
   return ACCEL_OK;
+}
+
+void accel_plan_conv_ws_release(accel_plan* plan) {
+  if (plan) { plan->ws.ready = false; plan->ws.blob = nullptr; }
 }
 
 int accel_plan_conv_ws_prepare(accel_plan* plan, const int8_t* blocks_dev, int32_t c_in, int32_t c_out, int32_t ksize,

@@ -619,6 +619,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
               mbar_wait(&w_full[ws], wph);
             }
             mbar_wait(&a_full[as], aph);
+            // the stage was written by cp.async (generic proxy) and is read by tcgen05.mma (async proxy): one proxy fence per
+            // stage on the consumer side, by the single issuing thread, after the barrier has made the writes visible to it
+            fence_proxy_async_smem();
             tc_fence_after();
             const uint32_t mask = (p.dbg & 2) ? 0u : p.masks[g * kWsMaxChunks + j];
             const uint32_t wl = a_lo0 | (((w_addr + wslot * static_cast<uint32_t>(p.w_chunk_bytes)) >> 4) & 0x3FFFu);
@@ -726,9 +729,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
               else cp_async16_zfill_s(dst0 + soff[k], src0 + go[k], nb[k]);
             }
           src0 += chunk_stride;
-          // arrives once this thread's copies have landed; like CUTLASS's sm100 cp.async mainloop, the consumer's
-          // mbarrier wait is the only synchronisation between these copies and tcgen05.mma (a fence.proxy.async
-          // per stage measured ~1000 cycles on either side)
+          // arrives once this thread's copies have landed; the issuer orders them against tcgen05.mma with one
+          // fence.proxy.async per stage after its mbarrier wait (a fence in each of the 64 loader threads measured ~1000
+          // cycles per stage in round 1; the single consumer-side fence is what the PTX memory model asks for)
           cp_async_mbar_arrive(&a_full[as]);
           if (++as == static_cast<uint32_t>(p.a_slots)) { as = 0; aph ^= 1u; }
         }

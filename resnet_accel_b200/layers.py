@@ -143,7 +143,11 @@ class BsrLayer:
         ws = w_scales.cpu().numpy() if isinstance(w_scales, torch.Tensor) else np.asarray(w_scales, np.float32)
         self.w_scales = ws.astype(np.float32)
         self.s_in, self.s_out = float(s_in), float(s_out)
-        self.sf = torch.from_numpy(channel_scale_factors(s_in, self.w_scales, s_out)).cuda()
+        sf_host = channel_scale_factors(s_in, self.w_scales, s_out)
+        self.sf = torch.from_numpy(sf_host).cuda()
+        # requant is monotone in the accumulator only for positive factors: decided here, on the host, once - the fused
+        # conv + max-pool kernel pools on INT32 accumulators and must not be taken otherwise (no device sync on the forward path)
+        self.sf_positive = bool((sf_host[: spec.c_out] > 0).all())
         self.bias = None if bias is None else torch.as_tensor(bias, dtype=torch.int32).cuda()
 
     # algorithmic work of one call
@@ -154,22 +158,56 @@ class BsrLayer:
         return self.plan.num_blocks * 200 + 4 * (self.plan.n_block_rows + 1) + 4 * self.spec.c_out
 
 
+def input_scales(specs: List[ConvSpec], s_input: float, s_out: float) -> Dict[str, float]:
+    """Activation scale of the tensor every conv / fc layer READS when scales chain through the network: the network input
+    is quantised with ``s_input``, every convolution requantises to ``s_out``, pools keep the scale of their input."""
+    scale_of: Dict[str, float] = {"input": float(s_input)}
+    s_in: Dict[str, float] = {}
+    prev = "input"
+    for sp in specs:
+        src = sp.src or prev
+        if sp.kind in ("conv", "fc"):
+            s_in[sp.name] = scale_of[src]
+            scale_of[sp.name] = float(s_out)
+        else:
+            scale_of[sp.name] = scale_of[src]
+        prev = sp.name
+    return s_in
+
+
 class BsrNetwork:
     """A chain of BSR conv / pool / fc layers on one GPU.  ``forward`` enqueues every layer on the current
-    stream; ``capture`` records it once into a CUDA graph for replay (launch-latency-bound tails)."""
+    stream; ``capture`` records it once into a CUDA graph for replay (launch-latency-bound tails).
+
+    Activation scales: every tensor has ONE scale (``scale_of``).  A layer's requant factor is built from the scale of the
+    tensor it reads and its own output scale, the residual add uses (own output scale, scale of the identity tensor, own
+    output scale).  ``chain_scales=False`` is the synthetic recipe of SURVEY.md 8d, where every layer is DEFINED to read
+    activations at ``S_ACT_IN`` and to write at ``S_ACT_OUT`` regardless of its producer (a throughput / parity workload,
+    not a calibrated model); ``chain_scales=True`` makes each layer read at its producer's output scale, which is what a
+    real quantised model needs (``ResNetInference.load_model``)."""
 
     def __init__(self, specs: List[ConvSpec], sparsity_pct: float, batch: int, bias_range: int = 0,
-                 layers: Optional[Dict[str, BsrLayer]] = None):
+                 layers: Optional[Dict[str, BsrLayer]] = None, s_input: float = S_ACT_IN, s_out: float = S_ACT_OUT,
+                 chain_scales: bool = False, shard: Optional[Tuple[int, int]] = None):
         self.specs, self.batch, self.sparsity_pct = specs, batch, sparsity_pct
         self.layers: Dict[str, BsrLayer] = layers or {}
         if not self.layers:
+            chained = input_scales(specs, s_input, s_out)
             idx = 0
             for sp in specs:
                 if sp.kind in ("conv", "fc"):
                     syn = synthetic_conv_weights(sp, sparsity_pct, idx, bias_range)
                     self.layers[sp.name] = BsrLayer(sp, syn["w2"], bias=syn["bias"],
+                                                    s_in=(chained[sp.name] if chain_scales else s_input), s_out=s_out,
                                                     group_rows=(int(__import__('os').environ.get('ACCEL_FC_GROUP_ROWS', 8)) if sp.kind == "fc" else 0))
                     idx += 1
+        # one scale per tensor: conv outputs carry their layer's s_out, pools keep their input's scale
+        self.scale_of: Dict[str, float] = {"input": float(s_input)}
+        prev = "input"
+        for sp in specs:
+            src = sp.src or prev
+            self.scale_of[sp.name] = self.layers[sp.name].s_out if sp.kind in ("conv", "fc") else self.scale_of[src]
+            prev = sp.name
         self.buffers: Dict[str, torch.Tensor] = {}
         self.sat = torch.zeros(1, dtype=torch.int64, device="cuda")
         for sp in specs:
@@ -204,7 +242,7 @@ class BsrNetwork:
                     and nx.kind == "maxpool" and (nx.k, nx.stride, nx.pad) == (3, 2, 1) and not nx.src
                     and sp.c_in * 7 <= 32 and sp.c_out <= 64 and sp.w % 32 == 0 and sp.w <= 224 and sp.h % 4 == 0
                     and not any(o.src == sp.name or o.residual == sp.name for o in specs)
-                    and bool((self.layers[sp.name].sf > 0).all().item())):
+                    and self.layers[sp.name].sf_positive):
                 self.fused_pool[sp.name] = nx.name
                 self.buffers.pop(sp.name, None)
         self.n_launches = sum(1 for _ in specs) - len(self.fused_ds) - len(self.fused_pool)
@@ -221,7 +259,7 @@ class BsrNetwork:
             if sp.name in self.fused_pool:
                 L = self.layers[sp.name]
                 ops.conv_pool(L.plan, src, sp.c_out, chan_scale=L.sf, bias=L.bias, relu=True,
-                              out=self.buffers[self.fused_pool[sp.name]], sat_count=self.sat)
+                              out=self.buffers[self.fused_pool[sp.name]], sat_count=self.sat, fused_ok=L.sf_positive)
                 prev = sp.name
                 continue
             out = self.buffers[sp.name]
@@ -237,7 +275,7 @@ class BsrNetwork:
                 if sp.residual:
                     # conv -> requant -> + identity -> ReLU on the int8 sum
                     L.plan.conv(src, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=L.sf, bias=L.bias, relu=False,
-                                residual=t[sp.residual], res_scales=(L.s_out, S_ACT_OUT, S_ACT_OUT), out=out,
+                                residual=t[sp.residual], res_scales=(L.s_out, self.scale_of[sp.residual], L.s_out), out=out,
                                 sat_count=self.sat, relu_out=True)
                 else:
                     L.plan.conv(src, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=L.sf, bias=L.bias,
@@ -294,6 +332,56 @@ class BsrNetwork:
         return {"ops": ops_total, "bytes": bytes_total, "layers": per_layer}
 
 
+class ShardedFcNetwork:
+    """BASELINE config 5: a batch-sharded convolution trunk followed by a block-row-sharded FC.
+
+    Every rank runs the trunk (all layers up to the global average pool) on its own ``batch_per_rank`` images - no
+    collective.  The pooled int8 features are written by the pool kernel straight into the rank's rows of the
+    ``[world * batch_per_rank, C]`` feature matrix, one in-place all-gather makes it whole on every rank, and the FC runs with
+    its block-rows (output channels) split over the ranks: each rank multiplies ALL rows by its own weight slice, the GEMM
+    epilogue writes the channel slice into the shard-major logits buffer and a second in-place all-gather completes it
+    (``parallel.ShardedBsrLinear``).  ``logits()`` is then a view ``[world * batch_per_rank, num_classes]`` - identical on all
+    ranks and bit-equal to the single-GPU network on the concatenated batch."""
+
+    def __init__(self, specs: List[ConvSpec], sparsity_pct: float, batch_per_rank: int, group=None, bias_range: int = 0):
+        from . import parallel
+        if specs[-1].kind != "fc" or specs[-2].kind != "avgpool":
+            raise ValueError("expected a network that ends in avgpool + fc")
+        self.rank, self.world = parallel._rank_world(group)
+        self.group, self.batch = group, int(batch_per_rank)
+        fc_spec = specs[-1]
+        self.trunk = BsrNetwork(specs[:-1], sparsity_pct, batch_per_rank, bias_range=bias_range)
+        fc_idx = sum(1 for sp in specs[:-1] if sp.kind in ("conv", "fc"))          # same seed as the unsharded network
+        syn = synthetic_conv_weights(fc_spec, sparsity_pct, fc_idx, bias_range)
+        q, w_scales = exporters.quantize_symmetric_per_channel(syn["w2"], device=True)
+        self.fc_bsr = exporters.build_bsr_14x14_int8_direct(q, device=True)
+        host = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in self.fc_bsr.items()}
+        self.fc = parallel.ShardedBsrLinear(host, fc_spec.c_out, group=group)
+        self.fc_bias = None if syn["bias"] is None else torch.as_tensor(syn["bias"], dtype=torch.int32).cuda()
+        self.fc_spec = fc_spec
+        C = specs[-2].c_out
+        self.features = torch.zeros((self.world * self.batch, C), dtype=torch.int8, device="cuda")
+        # the pool kernel writes this rank's rows of the gathered feature matrix directly
+        self.trunk.buffers[specs[-2].name] = self.features[self.rank * self.batch:(self.rank + 1) * self.batch]
+        self._buf: Optional[torch.Tensor] = None
+
+    def trunk_forward(self, x: torch.Tensor) -> None:
+        self.trunk.forward(x)
+
+    def head_forward(self) -> torch.Tensor:
+        """Feature all-gather -> sharded FC -> logits all-gather, all on the current stream.  Returns the logits view."""
+        from . import parallel
+        mine = self.features[self.rank * self.batch:(self.rank + 1) * self.batch]
+        parallel.gather_rows(mine, self.features, self.group)
+        self._buf = self.fc.local_gemm(self.features, "i32", bias=self.fc_bias)
+        self.fc.gather(self._buf)
+        return self.fc.result(self._buf)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.trunk_forward(x)
+        return self.head_forward()
+
+
 class ResNetInference:
     """Python twin of the reference's ``ResNetInference`` engine (hw/sim/cpp/include/resnet_inference.hpp:180-271; its
     ``load_model`` / ``run_inference`` are TODO stubs there) on top of :class:`BsrNetwork`.
@@ -313,6 +401,7 @@ class ResNetInference:
     def load_model(self, weights_dir: str) -> None:
         import os
         layers: Dict[str, BsrLayer] = {}
+        s_in_of = input_scales(self.specs, self.s_in, self.s_out)      # each layer reads at its producer's output scale
         for sp in self.specs:
             if sp.kind not in ("conv", "fc"):
                 continue
@@ -323,9 +412,9 @@ class ResNetInference:
             bias_path = os.path.join(weights_dir, f"{sp.name}_bias_int32.npy")
             bias = np.load(bias_path).astype(np.int32) if os.path.exists(bias_path) else None
             bsr = exporters.build_bsr_14x14_int8_direct(torch.from_numpy(w.reshape(sp.c_out, -1)).cuda(), device=True)
-            layers[sp.name] = BsrLayer(sp, bsr=bsr, w_scales=scales, bias=bias, s_in=self.s_in, s_out=self.s_out,
+            layers[sp.name] = BsrLayer(sp, bsr=bsr, w_scales=scales, bias=bias, s_in=s_in_of[sp.name], s_out=self.s_out,
                                        group_rows=(8 if sp.kind == "fc" else 0))
-        self.net = BsrNetwork(self.specs, 0.0, self.batch, layers=layers)
+        self.net = BsrNetwork(self.specs, 0.0, self.batch, layers=layers, s_input=self.s_in, s_out=self.s_out)
 
     def _require(self) -> BsrNetwork:
         if self.net is None:
@@ -343,7 +432,8 @@ class ResNetInference:
 
     def get_top_k(self, logits: torch.Tensor, k: int = 5):
         w = torch.from_numpy(self._require().layers["fc"].w_scales).to(logits.device)
-        real = logits.to(torch.float32) * (self.s_out * w)[: logits.shape[1]]       # de-quantise per channel before ranking
+        s_fc_in = self._require().layers["fc"].s_in                                  # the pooled features' scale
+        real = logits.to(torch.float32) * (s_fc_in * w)[: logits.shape[1]]          # de-quantise per channel before ranking
         prob = torch.softmax(real, dim=1)
         p, i = prob.topk(k, dim=1)
         return i.cpu().numpy(), p.cpu().numpy()

@@ -108,6 +108,7 @@ class BsrPlan:
         self._blocks = blk                      # kept for later re-layouts (conv_ws)
         self._ws_conv = {}                      # (c_in, c_out, ksize) -> workspace tensor (None: no such path)
         self._ws_gemm = None                    # dense-equivalent GEMM layout: None = not built yet, False = no such path
+        self.use_gemm_ws = True                 # False: GEMMs of this plan stay on the gather kernel (csrc/bsr_tcp.cuh)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -123,18 +124,23 @@ class BsrPlan:
         key = (int(c_in), int(c_out), int(ksize))
         if key in self._ws_conv:
             return
-        self._ws_conv.clear()                   # the plan holds one prepared geometry at a time
+        # the plan holds one prepared geometry at a time.  The C side is told to forget the old layout BEFORE its buffer
+        # can go back to the allocator (accel_plan_conv_ws_release), and the old buffer is only dropped afterwards.
         L = _lib.lib()
         nbytes = C.c_size_t()
         check(L.accel_plan_conv_ws_bytes(self._h, key[0], key[1], key[2], C.byref(nbytes)))
+        old = self._ws_conv
+        L.accel_plan_conv_ws_release(self._h)
         if nbytes.value == 0:
-            self._ws_conv[key] = None
+            self._ws_conv = {key: None}
+            del old
             return
         buf = torch.empty(int(nbytes.value) + 1024, dtype=torch.uint8, device=self.device)
         ptr = buf.data_ptr() + (-buf.data_ptr()) % 1024
         check(L.accel_plan_conv_ws_prepare(self._h, _ptr(self._blocks) if self.col_idx.size else None, key[0], key[1], key[2],
                                            ptr, int(nbytes.value), _stream()))
-        self._ws_conv[key] = buf
+        self._ws_conv = {key: buf}
+        del old
 
     def _prepare_gemm_ws(self) -> None:
         """Dense-equivalent layout for GEMMs (csrc/gemm_ws.cuh), built once per plan on the first large GEMM."""
@@ -187,8 +193,12 @@ class BsrPlan:
     def gemm(self, x: torch.Tensor, out_kind: str = "i32", n_channels: Optional[int] = None, chan_scale=None,
              bias=None, relu: bool = False, residual=None, res_scales=None, out: Optional[torch.Tensor] = None,
              sat_count: Optional[torch.Tensor] = None, chan_absmax: Optional[torch.Tensor] = None,
-             relu_out: bool = False) -> torch.Tensor:
-        """Y = epilogue(X @ W^T).  x int8 [M, K] (CUDA, row stride may exceed K) -> [M, n_channels]."""
+             relu_out: bool = False, out_t: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Y = epilogue(X @ W^T).  x int8 [M, K] (CUDA, row stride may exceed K) -> [M, n_channels].
+
+        ``out_t``: write the TRANSPOSED result instead, into a caller-owned ``[n_channels, M]`` tensor whose rows may be
+        strided (a slice of a larger buffer): channel-major output is what the block-row-sharded FC hands to the all-gather
+        (``parallel.ShardedBsrLinear``).  Returns ``out_t`` in that case."""
         if x.dtype != torch.int8 or x.dim() != 2 or not x.is_cuda:
             raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 2-D INT8 CUDA tensor")
         if x.stride(1) != 1:
@@ -196,15 +206,38 @@ class BsrPlan:
         M, K = x.shape
         n_channels = self.n_out_padded if n_channels is None else int(n_channels)
         dt = {"i8": torch.int8, "i32": torch.int32, "f32": torch.float32}[out_kind]
+        if out_t is not None:
+            if out is not None or residual is not None:
+                raise AcceleratorError(_lib.INVALID_CONFIG, "out_t excludes out / residual")
+            _check_out(out_t, (n_channels, M), dt)
+            if M > 1 and out_t.stride(1) != 1:
+                raise AcceleratorError(_lib.INVALID_CONFIG, "out_t rows must be contiguous")
+            e, keep = self._epilogue(out_kind, n_channels, chan_scale, bias, relu, None, None, sat_count, chan_absmax, relu_out)
+            if (self.use_gemm_ws and M >= GEMM_WS_MIN_ROWS and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0
+                    and chan_absmax is None):
+                self._prepare_gemm_ws()
+            lay = OutLayout(max(M, 1), 0, out_t.stride(0) if n_channels > 1 else max(M, 1), 1, 0, 0)
+            check(_lib.lib().accel_bsr_gemm_i8(self._h, _ptr(x), M, K, x.stride(0) if M else K, C.byref(e), _ptr(out_t),
+                                               C.byref(lay), _stream()))
+            return out_t
         if out is None:
             out = torch.empty((M, n_channels), dtype=dt, device=x.device)
-        if residual is not None and _is_cuda(residual):
-            residual = residual.contiguous()
-            if residual.shape != out.shape or residual.stride(0) != out.stride(0):
-                raise AcceleratorError(_lib.INVALID_CONFIG, "residual must have the output's shape and row stride")
+        _check_out(out, (M, n_channels), dt)
+        if out.dim() != 2 or (out.stride(1) != 1 and n_channels > 1):
+            raise AcceleratorError(_lib.INVALID_CONFIG, "output must be 2-D with unit column stride")
+        if residual is not None:
+            if not (_is_cuda(residual) and residual.dtype == torch.int8):
+                residual = to_device(residual, torch.int8, x.device)
+            if tuple(residual.shape) != tuple(out.shape):
+                raise AcceleratorError(_lib.INVALID_CONFIG, "residual must have the output's shape")
+            if residual.stride() != out.stride():
+                r2 = torch.empty_strided(tuple(out.shape), tuple(out.stride()), dtype=torch.int8, device=out.device)
+                r2.copy_(residual)
+                residual = r2
         e, keep = self._epilogue(out_kind, n_channels, chan_scale, bias, relu, residual, res_scales, sat_count,
                                  chan_absmax, relu_out)
-        if M >= GEMM_WS_MIN_ROWS and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0 and chan_absmax is None:
+        if (self.use_gemm_ws and M >= GEMM_WS_MIN_ROWS and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0
+                and chan_absmax is None):
             self._prepare_gemm_ws()
         lay = OutLayout(max(M, 1), 0, 1, out.stride(0) if M else n_channels, 0, 0)
         check(_lib.lib().accel_bsr_gemm_i8(self._h, _ptr(x), M, K, x.stride(0) if M else K, C.byref(e), _ptr(out),
@@ -228,16 +261,21 @@ class BsrPlan:
         dt = {"i8": torch.int8, "i32": torch.int32, "f32": torch.float32}[out_kind]
         if out is None:
             out = torch.empty((B, c_out, Ho, Wo), dtype=dt, device=x.device)
+        _check_out(out, (B, c_out, Ho, Wo), dt)
         out_pitch = _row_pitch(out)
         if out_pitch is None:
             raise AcceleratorError(_lib.INVALID_CONFIG, "output must be NCHW, dense or with padded rows")
         if residual is not None:
             if tuple(residual.shape) != tuple(out.shape):
                 raise AcceleratorError(_lib.INVALID_CONFIG, "residual shape must equal the output shape")
-            if _is_cuda(residual) and _row_pitch(residual) != out_pitch:
-                residual = residual.contiguous() if out_pitch == Wo else None
-                if residual is None:
-                    raise AcceleratorError(_lib.INVALID_CONFIG, "residual strides must equal the output strides")
+            # the kernels read the residual with the OUTPUT's layout: bring it to a CUDA int8 tensor first, then give it the
+            # output's strides (a dense host array next to a padded-row output would otherwise be read out of bounds)
+            if not (_is_cuda(residual) and residual.dtype == torch.int8):
+                residual = to_device(residual, torch.int8, x.device)
+            if _row_pitch(residual) != out_pitch:
+                r2 = torch.empty_strided(tuple(out.shape), tuple(out.stride()), dtype=torch.int8, device=out.device)
+                r2.copy_(residual)
+                residual = r2
         e, keep = self._epilogue(out_kind, c_out, chan_scale, bias, relu, residual, res_scales, sat_count, chan_absmax,
                                  relu_out)
         if ksize == 3 and stride in (1, 2) and pad == 1 and out_kind == "i8" and chan_absmax is None and W <= 62:
@@ -291,9 +329,14 @@ def conv_dual(plan: BsrPlan, plan_ds: BsrPlan, x: torch.Tensor, c_out: int, *, c
 def conv_pool(plan: BsrPlan, x: torch.Tensor, c_out: int, *, chan_scale, bias=None, relu: bool = True, ksize: int = 7,
               stride: int = 2, pad: int = 3, pool: int = 3, pool_stride: int = 2, pool_pad: int = 1,
               out: Optional[torch.Tensor] = None, sat_count: Optional[torch.Tensor] = None,
-              scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+              scratch: Optional[torch.Tensor] = None, fused_ok: Optional[bool] = None) -> torch.Tensor:
     """Convolution + ReLU/requant + max-pool (the ResNet stem).  One fused kernel when the library has one for the
-    geometry, else the convolution into ``scratch`` (allocated here when missing) followed by the pool."""
+    geometry, else the convolution into ``scratch`` (allocated here when missing) followed by the pool.
+
+    The fused kernel pools on the INT32 accumulators, which equals requant-then-pool only when every ``chan_scale[c] > 0``.
+    That is a property of ``chan_scale``, not of the plan: callers that know it pass ``fused_ok`` (``BsrLayer.sf_positive``,
+    decided on the host when the factors are built); otherwise host-side factors are checked here and device tensors are
+    read back once per call (a blocking sync - do not capture such a call into a CUDA graph)."""
     if x.dtype != torch.int8 or x.dim() != 4 or not x.is_cuda:
         raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 4-D INT8 CUDA tensor (NCHW)")
     in_pitch = _row_pitch(x)
@@ -309,11 +352,11 @@ def conv_pool(plan: BsrPlan, x: torch.Tensor, c_out: int, *, chan_scale, bias=No
     if out_pitch is None:
         raise AcceleratorError(_lib.INVALID_CONFIG, "output must be NCHW, dense or with padded rows")
     fused = ksize == 7 and stride == 2 and pad == 3 and (pool, pool_stride, pool_pad) == (3, 2, 1) and Cin * 7 <= 32 and c_out <= 64
-    if fused and not getattr(plan, "_pool_fusable", False):
-        # the pool is taken on the INT32 accumulators: bit-identical only for positive requant factors (checked once per plan)
-        sf_t = chan_scale if isinstance(chan_scale, torch.Tensor) else torch.as_tensor(np.asarray(chan_scale))
-        fused = bool((sf_t[:c_out] > 0).all().item())
-        plan._pool_fusable = fused
+    if fused:
+        if fused_ok is None:
+            sf_host = chan_scale.detach().cpu().numpy() if isinstance(chan_scale, torch.Tensor) else np.asarray(chan_scale)
+            fused_ok = bool((sf_host.reshape(-1)[:c_out] > 0).all())
+        fused = bool(fused_ok)
     if fused:
         plan._prepare_conv_ws(Cin, c_out, 7)
         e, keep = plan._epilogue("i8", c_out, chan_scale, bias, relu, None, None, sat_count, None)
@@ -332,6 +375,14 @@ def conv_pool(plan: BsrPlan, x: torch.Tensor, c_out: int, *, chan_scale, bias=No
 
 def _is_cuda(a) -> bool:
     return isinstance(a, torch.Tensor) and a.is_cuda
+
+
+def _check_out(out, shape, dtype) -> None:
+    """A caller-supplied output buffer must match what the kernel writes (an int8 buffer under out_kind='i32' would overrun)."""
+    if not _is_cuda(out) or out.dtype != dtype or tuple(out.shape) != tuple(shape):
+        raise AcceleratorError(_lib.INVALID_CONFIG,
+                               f"out must be a CUDA {dtype} tensor of shape {tuple(shape)}, got "
+                               f"{getattr(out, 'dtype', type(out))} {tuple(getattr(out, 'shape', ()))}")
 
 
 def _host(a) -> np.ndarray:

@@ -10,13 +10,15 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def test_resnet18_full_network_matches_cpu_golden():
+@pytest.mark.parametrize("sparsity", [70.0, 90.0])
+def test_resnet18_full_network_matches_cpu_golden(sparsity):
+    """BASELINE configs 3 (70 %) and 4 (90 %): the whole 224x224 network, bit for bit against the reference C++ golden chain."""
     import torch
     import bench
     from oracle import bsr_oracle as O
     from oracle import c_oracle
     from resnet_accel_b200 import layers as L
-    B, sparsity = 2, 70.0
+    B = 2
     net = L.BsrNetwork(L.resnet18_specs(), sparsity, B)
     x = np.random.default_rng(0).integers(-128, 128, (B, 3, 224, 224), dtype=np.int8)
     xd = torch.from_numpy(x).cuda()
@@ -37,30 +39,83 @@ def test_resnet18_full_network_matches_cpu_golden():
             assert np.array_equal(replay[b], ref.reshape(-1)), b
     else:  # port: layer by layer with the C restatement
         pytest.skip("oracle/_ref not available")
-    assert replay.any()
+    if sparsity <= 70.0:
+        assert replay.any()
+    else:
+        # with 10 % of the weights and the fixed synthetic scales the signal dies out before the logits (GPU and reference
+        # agree on that, bit for bit); the early tensors still carry data, and test_layers_at_90pct_with_random_inputs below
+        # exercises every layer of the 90 % network on full-range inputs
+        assert net.buffers["layer1.0.conv1"].any().item()
 
 
-def test_network_layers_match_oracle_port():
-    """Each conv layer of a down-scaled ResNet-18 (64x64 images) against the plain-C port, incl. residual + ReLU."""
+def test_layers_at_90pct_with_random_inputs():
+    """BASELINE config 4 (90 % block sparsity): every convolution / FC of the 224x224 ResNet-18, each fed its own full-range
+    random int8 input (and residual), against the plain-C port.  Batch 2."""
     import torch
+    from oracle import bsr_oracle as O
     from oracle import c_oracle
-    from resnet_accel_b200 import layers as L
-    B = 3
-    specs = L.resnet18_specs(image=64, num_classes=100)
-    net = L.BsrNetwork(specs, 70.0, B, bias_range=300)
-    x = np.random.default_rng(1).integers(-128, 128, (B, 3, 64, 64), dtype=np.int8)
+    from resnet_accel_b200 import layers as L, ops
+    B = 2
+    specs = L.resnet18_specs()
+    net = L.BsrNetwork(specs, 90.0, B, bias_range=500)
+    rng = np.random.default_rng(90)
+    for sp in specs:
+        if sp.kind not in ("conv", "fc"):
+            continue
+        lay = net.layers[sp.name]
+        bsr = {k: lay.bsr[k].cpu().numpy() for k in ("indptr", "indices", "data")}
+        total = lay.plan.n_block_rows * lay.plan.n_block_cols
+        assert lay.plan.num_blocks == total - int(total * 0.9), sp.name
+        bias, sf = lay.bias.cpu().numpy(), lay.sf.cpu().numpy()
+        if sp.kind == "fc":
+            A = rng.integers(-128, 128, (B, sp.c_in), dtype=np.int8)
+            got = lay.plan.gemm(torch.from_numpy(A).cuda(), "i32", n_channels=sp.c_out, bias=lay.bias).cpu().numpy()
+            want, _ = O.linear_bsr_layer(A, bsr["indptr"], bsr["indices"], bsr["data"], sp.c_out, bias=bias)
+            assert np.array_equal(got, want), sp.name
+            continue
+        x = rng.integers(-128, 128, (B, sp.c_in, sp.h, sp.w), dtype=np.int8)
+        xd = ops.alloc_padded(x.shape); xd.copy_(torch.from_numpy(x).cuda())
+        out = ops.alloc_padded((B, sp.c_out, sp.h_out, sp.w_out))
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if sp.residual:
+            r = rng.integers(-128, 128, (B, sp.c_out, sp.h_out, sp.w_out), dtype=np.int8)
+            rd = ops.alloc_padded(r.shape); rd.copy_(torch.from_numpy(r).cuda())
+            got = lay.plan.conv(xd, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=lay.sf, bias=lay.bias, relu=False,
+                                residual=rd, res_scales=(0.05, 0.05, 0.05), relu_out=True, out=out, sat_count=cnt).cpu().numpy()
+            want, sat = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], sp.c_out, sp.k, sp.stride, sp.pad,
+                                                bias=bias, relu=False, sf=sf, residual=r, res_scales=(0.05, 0.05, 0.05))
+            want = np.maximum(want, 0)
+        else:
+            got = lay.plan.conv(xd, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=lay.sf, bias=lay.bias, relu=sp.relu,
+                                out=out, sat_count=cnt).cpu().numpy()
+            want, sat = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], sp.c_out, sp.k, sp.stride, sp.pad,
+                                                bias=bias, relu=sp.relu, sf=sf)
+        assert np.array_equal(got, want), sp.name
+        assert int(cnt.item()) == sat, sp.name
+        assert got.any(), sp.name
+
+
+def _check_layers_against_port(net, specs, x, s_in_expected, res_scales_expected):
+    """Every conv layer of ``net`` against the plain-C port; the requant factors and residual scales are recomputed here
+    from the expected per-tensor scales (not read back from the network)."""
+    import torch
+    from oracle import bsr_oracle as O
+    from oracle import c_oracle
     net.forward(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
     t = {"input": x}
     prev = "input"
-    from oracle import bsr_oracle as O
     for sp in specs:
         src = t[sp.src] if sp.src else t[prev]
-        if sp.name in net.fused_pool:       # stem convolution fused with its max-pool: its own output is never materialised
+        if sp.kind in ("conv", "fc"):
             lay = net.layers[sp.name]
+            sf = O.channel_scale_factors(s_in_expected[sp.name], lay.w_scales, lay.s_out)
+            assert np.array_equal(lay.sf.cpu().numpy(), sf), sp.name
+        if sp.name in net.fused_pool:       # stem convolution fused with its max-pool: its own output is never materialised
             bsr = {k: lay.bsr[k].cpu().numpy() for k in ("indptr", "indices", "data")}
             t[sp.name], _ = c_oracle.conv_bsr_layer(src, bsr["indptr"], bsr["indices"], bsr["data"], sp.c_out, sp.k, sp.stride,
-                                                    sp.pad, bias=lay.bias.cpu().numpy(), relu=sp.relu, sf=lay.sf.cpu().numpy())
+                                                    sp.pad, bias=None if lay.bias is None else lay.bias.cpu().numpy(),
+                                                    relu=sp.relu, sf=sf)
             prev = sp.name
             continue
         got = net.buffers[sp.name].cpu().numpy()
@@ -68,14 +123,12 @@ def test_network_layers_match_oracle_port():
             want = np.stack([O.maxpool2d_int8(src[b], sp.k, sp.stride, sp.pad) for b in range(src.shape[0])])
             assert np.array_equal(got, want), sp.name
         if sp.kind == "conv":
-            lay = net.layers[sp.name]
             bsr = {k: lay.bsr[k].cpu().numpy() for k in ("indptr", "indices", "data")}
-            bias = lay.bias.cpu().numpy()
-            sf = lay.sf.cpu().numpy()
+            bias = None if lay.bias is None else lay.bias.cpu().numpy()
             if sp.residual:
                 want, _ = c_oracle.conv_bsr_layer(src, bsr["indptr"], bsr["indices"], bsr["data"], sp.c_out, sp.k, sp.stride,
                                                   sp.pad, bias=bias, relu=False, sf=sf, residual=t[sp.residual],
-                                                  res_scales=(L.S_ACT_OUT, L.S_ACT_OUT, L.S_ACT_OUT))
+                                                  res_scales=res_scales_expected[sp.name])
                 want = np.maximum(want, 0)
             else:
                 want, _ = c_oracle.conv_bsr_layer(src, bsr["indptr"], bsr["indices"], bsr["data"], sp.c_out, sp.k, sp.stride,
@@ -85,6 +138,39 @@ def test_network_layers_match_oracle_port():
         prev = sp.name
 
 
+def test_network_layers_match_oracle_port():
+    """Each conv layer of a down-scaled ResNet-18 (64x64 images) against the plain-C port, incl. residual + ReLU.
+    Synthetic recipe: every layer reads at S_ACT_IN and writes at S_ACT_OUT."""
+    from resnet_accel_b200 import layers as L
+    B = 3
+    specs = L.resnet18_specs(image=64, num_classes=100)
+    net = L.BsrNetwork(specs, 70.0, B, bias_range=300)
+    x = np.random.default_rng(1).integers(-128, 128, (B, 3, 64, 64), dtype=np.int8)
+    s_in = {sp.name: L.S_ACT_IN for sp in specs}
+    res = {sp.name: (L.S_ACT_OUT, L.S_ACT_OUT, L.S_ACT_OUT) for sp in specs}
+    _check_layers_against_port(net, specs, x, s_in, res)
+
+
+def test_chained_scales_differ_from_module_constants():
+    """scales chain through the network.  Input quantised at 0.031, every convolution writes at 0.043: a layer
+    reads at its producer's output scale, the residual add uses (own output, identity tensor, own output)."""
+    from resnet_accel_b200 import layers as L
+    B, s_input, s_out = 2, 0.031, 0.043
+    specs = L.resnet18_specs(image=64, num_classes=100)
+    net = L.BsrNetwork(specs, 70.0, B, bias_range=200, s_input=s_input, s_out=s_out, chain_scales=True)
+    x = np.random.default_rng(2).integers(-128, 128, (B, 3, 64, 64), dtype=np.int8)
+    s_in, res = {}, {}
+    for sp in specs:
+        if sp.kind in ("conv", "fc"):
+            s_in[sp.name] = s_input if sp.name == "conv1" else s_out        # pools keep the scale, so everything else reads s_out
+            res[sp.name] = (s_out, s_out, s_out)
+    assert net.scale_of["maxpool"] == s_out and net.scale_of["input"] == s_input
+    _check_layers_against_port(net, specs, x, s_in, res)
+    # an engine loaded from files chains the same way: its layer1 convolutions read at s_out, not at s_in
+    eng_scales = L.input_scales(specs, s_input, s_out)
+    assert eng_scales["conv1"] == s_input and eng_scales["layer1.0.conv1"] == s_out and eng_scales["fc"] == s_out
+
+
 def test_resnet_inference_engine_roundtrip(tmp_path):
     """ResNetInference.load_model on the directory layout of resnet_inference.hpp reproduces the network it was saved from."""
     import torch
@@ -92,7 +178,7 @@ def test_resnet_inference_engine_roundtrip(tmp_path):
     from resnet_accel_b200 import layers as L
     B = 2
     specs = L.resnet18_specs(image=64, num_classes=50)
-    ref = L.BsrNetwork(specs, 70.0, B)
+    ref = L.BsrNetwork(specs, 70.0, B, chain_scales=True)          # the engine chains scales: so must the network it is saved from
     for name, lay in ref.layers.items():
         dense = O.bsr_to_dense(lay.bsr["indptr"].cpu().numpy(), lay.bsr["indices"].cpu().numpy(), lay.bsr["data"].cpu().numpy(),
                                lay.bsr["num_block_cols"])

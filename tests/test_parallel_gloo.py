@@ -38,6 +38,17 @@ def _worker(rank, world, port, q):
         local = O.bsr_gemm_i32(A, mine["indptr"], mine["indices"], mine["data"]) if br1 > br0 else np.zeros((A.shape[0], 0), np.int32)
         got = P.all_gather_channels(torch.from_numpy(np.ascontiguousarray(local)), ranges).numpy()
         ok_rows = np.array_equal(got, full)
+        # --- the direct-write layout of ShardedBsrLinear: the rank's slice is written TRANSPOSED into its place of the
+        #     shard-major buffer, the all-gather runs in place on it, the result is assembled from (or is a view of) it
+        for balance in ("auto", "rows") if (len(bsr["indptr"]) - 1) % world == 0 else ("auto",):
+            lin = P.ShardedBsrLinear(bsr, N, balance=balance, build_plan=False)
+            buf = lin.buffer(A.shape[0], torch.int32, "cpu")
+            b0, b1 = lin.ranges[rank]
+            if b1 > b0:
+                loc = O.bsr_gemm_i32(A, lin.mine["indptr"], lin.mine["indices"], lin.mine["data"])
+                buf[rank, : loc.shape[1]] = torch.from_numpy(np.ascontiguousarray(loc.T))
+            lin.gather(buf)
+            ok_rows = ok_rows and np.array_equal(lin.result(buf).numpy(), full[:, :N])
         # --- batch sharding: no collective on the data path; gather only to check
         lo, hi = P.shard_batch(A.shape[0], rank, world)
         part = O.bsr_gemm_i32(A[lo:hi], bsr["indptr"], bsr["indices"], bsr["data"])

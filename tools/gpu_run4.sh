@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out/r2
+O=gpurun_out/r2
+LAYERS=layer1.0.conv1,layer1.0.conv2,layer2.0.conv1,layer2.1.conv1,layer2.1.conv2,layer3.0.conv1,layer3.1.conv1,layer4.0.conv1,layer4.1.conv1
+for f in 0 1 2 3; do
+  echo "== dbg=$f" | tee -a $O/ws_iso.txt
+  GRAPH=1 LAYER=$LAYERS ACCEL_DBG_FLAGS=$f timeout 300 python tools/ws_probe.py 2>&1 | tail -12 | tee -a $O/ws_iso.txt
+done
+for f in 0 1 2 3; do
+  echo "== stem dbg=$f" | tee -a $O/ws_iso.txt
+  ACCEL_DBG_FLAGS=$f timeout 300 python tools/stem_probe.py 2>&1 | tail -4 | tee -a $O/ws_iso.txt
+done
