@@ -225,6 +225,25 @@ ACCEL_API int accel_requant_i32_i8(const int32_t* acc, int8_t* out, int64_t n_ou
                          accel_stream_t stream);
 ACCEL_API int accel_add_residual_i8(const int8_t* main_, const int8_t* res, int8_t* out, int64_t n, float s_main, float s_res,
                           float s_out, accel_stream_t stream);
+/* relu_int8 / relu6_int8 / relu_int32, in place (golden_models.cpp:278-283, :323-330, :298-303).  relu6: upper clamp
+ * int8(6.0f / scale), truncated as the reference computes it. */
+ACCEL_API int accel_relu_i8(int8_t* data, int64_t n, accel_stream_t stream);
+ACCEL_API int accel_relu6_i8(int8_t* data, int64_t n, float scale, accel_stream_t stream);
+ACCEL_API int accel_relu_i32(int32_t* data, int64_t n, accel_stream_t stream);
+/* gemm_bsr_int8 (sw/golden/gemm_bsr_int8.py:16-104): the reference's float32 "golden" with per-row scales, replayed
+ * operation by operation in its (block-row, block, local-row) order - SURVEY.md A.2 lists its quirks; it is a compatibility
+ * path, not the numerical oracle.  A int8 [M, K] (lda); BSR of B[K, N] with square blocks: indptr / indices / data [nnz, b, b]
+ * and blk_row[nnz] = block-row of every stored block.  NumPy's promotion rules decide the arithmetic dtype and are passed in:
+ *   - the re-quantisation  clip(rint(block / scale))  (:74-79) runs in float64 when the blocks OR the scales are float64:
+ *     div_f64 says so, `data` and `scales_div` [n_scales] are both in that dtype;
+ *   - the de-quantising products and the += (:94-102): scale_a_f64 (scale_A is a float64 NumPy scalar; a Python float is
+ *     "weak" and multiplies in float32) and scales_f64 (dtype of `scales` [n_scales], the caller's own array).
+ * q_scratch: nnz*b*b bytes.  C float32 [M, N] (ldc), overwritten. */
+ACCEL_API int accel_gemm_bsr_int8_fp32(const int8_t* A, int64_t M, int64_t lda, const int32_t* indptr, const int32_t* indices,
+                             const void* data, const void* scales_div, int32_t div_f64, const int32_t* blk_row, int64_t nnz,
+                             int32_t n_block_rows, int32_t block, int64_t K, int64_t N, double scale_a, int32_t scale_a_f64,
+                             const void* scales, int32_t scales_f64, int32_t n_scales, int8_t* q_scratch, float* C, int64_t ldc,
+                             accel_stream_t stream);
 /* in_pitch / out_pitch: bytes between rows of the input / output planes (0 = dense) */
 ACCEL_API int accel_maxpool_i8(const int8_t* x, int8_t* out, int64_t n_planes, int32_t h, int32_t w, int32_t pool,
                      int32_t stride, int32_t pad, int32_t in_pitch, int32_t out_pitch, accel_stream_t stream);

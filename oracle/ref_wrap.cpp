@@ -9,6 +9,8 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <stdexcept>
+#include <vector>
 
 #include "bsr_packer.hpp"
 #include "golden_models.hpp"
@@ -106,4 +108,31 @@ REF_API void ref_conv_layer_image(const int8_t* in, const int8_t* w, const int32
   for (size_t c = 0; c < Cout; ++c)
     g::requantize_int32_to_int8(scratch + c * P, out + c * P, P, in_scale_per_channel[c], out_scale);
   if (residual) g::add_residual_int8(out, residual, out, Cout * P, s_main, s_res, s_out);
+}
+
+// serialize_for_hardware / deserialize_from_hardware (bsr_packer.hpp:489-575) on the reference's own pack_to_bsr of a dense
+// int8 matrix.  Returns the blob size (or -1 if `cap` is too small); round-trips it through the reference's reader and
+// returns -2 if verify_serialization fails.
+REF_API long ref_serialize_for_hardware(const int8_t* dense, size_t rows, size_t cols, uint8_t* out, size_t cap) {
+  resnet_accel::BSRMatrix bsr = resnet_accel::pack_to_bsr(dense, rows, cols);
+  std::vector<std::uint8_t> blob = resnet_accel::serialize_for_hardware(bsr);
+  if (!resnet_accel::verify_serialization(bsr)) return -2;
+  if (blob.size() > cap) return -1;
+  std::memcpy(out, blob.data(), blob.size());
+  return static_cast<long>(blob.size());
+}
+// The reference's reader on a caller-supplied blob: fills the structure arrays, returns nnz (or -1 when it throws).
+REF_API long ref_deserialize_from_hardware(const uint8_t* blob, size_t size, int64_t* hdr3, int64_t* row_ptr, int64_t* col_idx,
+                                           int8_t* data) {
+  try {
+    resnet_accel::BSRMatrix bsr = resnet_accel::deserialize_from_hardware(blob, size);
+    hdr3[0] = static_cast<int64_t>(bsr.nnz_blocks); hdr3[1] = static_cast<int64_t>(bsr.num_block_rows);
+    hdr3[2] = static_cast<int64_t>(bsr.num_block_cols);
+    for (size_t i = 0; i < bsr.row_ptr.size(); ++i) row_ptr[i] = static_cast<int64_t>(bsr.row_ptr[i]);
+    for (size_t i = 0; i < bsr.col_idx.size(); ++i) col_idx[i] = static_cast<int64_t>(bsr.col_idx[i]);
+    std::memcpy(data, bsr.data.data(), bsr.data.size());
+    return static_cast<long>(bsr.nnz_blocks);
+  } catch (const std::exception&) {
+    return -1;
+  }
 }

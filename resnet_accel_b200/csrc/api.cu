@@ -1193,6 +1193,62 @@ int accel_requant_i32_i8(const int32_t* acc, int8_t* out, int64_t n_outer, int64
   return ACCEL_OK;
 }
 
+int accel_relu_i8(int8_t* data, int64_t n, accel_stream_t stream) {
+  if (n <= 0) return ACCEL_OK;
+  if (!data) return fail(ACCEL_INVALID_CONFIG, "null buffer");
+  accel::relu_i8_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(data, n, 127);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_relu6_i8(int8_t* data, int64_t n, float scale, accel_stream_t stream) {
+  if (n <= 0) return ACCEL_OK;
+  if (!data) return fail(ACCEL_INVALID_CONFIG, "null buffer");
+  // the reference's threshold, evaluated the way it is written there (golden_models.cpp:326): a float -> int8 cast of
+  // 6.0f / scale (truncation toward zero; like the reference this is only meaningful while 6 / scale fits an int8)
+  const std::int8_t max_val = static_cast<std::int8_t>(6.0f / scale);
+  accel::relu_i8_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(data, n, static_cast<int32_t>(max_val));
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_relu_i32(int32_t* data, int64_t n, accel_stream_t stream) {
+  if (n <= 0) return ACCEL_OK;
+  if (!data) return fail(ACCEL_INVALID_CONFIG, "null buffer");
+  accel::relu_i32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(data, n);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_gemm_bsr_int8_fp32(const int8_t* A, int64_t M, int64_t lda, const int32_t* indptr, const int32_t* indices,
+                             const void* data, const void* scales_div, int32_t div_f64, const int32_t* blk_row, int64_t nnz,
+                             int32_t n_block_rows, int32_t block, int64_t K, int64_t N, double scale_a, int32_t scale_a_f64,
+                             const void* scales, int32_t scales_f64, int32_t n_scales, int8_t* q_scratch, float* C, int64_t ldc,
+                             accel_stream_t stream) {
+  if (M < 0 || K < 0 || N < 0 || block <= 0 || n_block_rows < 0 || ldc < N || n_scales <= 0)
+    return fail(ACCEL_INVALID_CONFIG, "bad shape");
+  if (K % block) return fail(ACCEL_INVALID_CONFIG, "K must be a multiple of the block size (the reference's A-slice @ block^T needs whole blocks)");
+  if (M == 0 || N == 0) return ACCEL_OK;
+  if (!A || !indptr || !C || !scales || (nnz > 0 && (!data || !scales_div || !indices || !blk_row || !q_scratch)))
+    return fail(ACCEL_INVALID_CONFIG, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nnz > 0) {
+    const int64_t tot = nnz * block * block;
+    // block / scale is float64 as soon as either operand is (NumPy promotion): the wrapper passes both in that dtype
+    if (div_f64)
+      accel::fp32compat_requant_kernel<double><<<grid_for(tot, 256), 256, 0, st>>>(static_cast<const double*>(data), blk_row, nnz, block,
+                                                                                 block, static_cast<const double*>(scales_div), n_scales, q_scratch);
+    else
+      accel::fp32compat_requant_kernel<float><<<grid_for(tot, 256), 256, 0, st>>>(static_cast<const float*>(data), blk_row, nnz, block,
+                                                                                block, static_cast<const float*>(scales_div), n_scales, q_scratch);
+    CU(cudaGetLastError());
+  }
+  accel::fp32compat_gemm_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(A, M, lda, indptr, indices, q_scratch, n_block_rows, block, K, N,
+                                                                       scale_a, scale_a_f64, scales, scales_f64, n_scales, C, ldc);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
 int accel_add_residual_i8(const int8_t* main_, const int8_t* res, int8_t* out, int64_t n, float s_main, float s_res,
                           float s_out, accel_stream_t stream) {
   if (n <= 0) return ACCEL_OK;

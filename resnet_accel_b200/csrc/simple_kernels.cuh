@@ -246,6 +246,83 @@ __global__ void requant_i32_i8_kernel(const int32_t* __restrict__ acc, int8_t* _
     if ((threadIdx.x & 31) == 0 && sat) atomicAdd(sat_count, static_cast<unsigned long long>(sat));
   }
 }
+// relu_int8 / relu6_int8 / relu_int32 (golden_models.cpp:278-283, :323-330, :298-303), in place.  `hi` is the upper clamp:
+// 127 for plain ReLU, int8(6.0f / scale) (computed on the host exactly as the reference does) for ReLU6.
+__global__ void relu_i8_kernel(int8_t* __restrict__ d, int64_t n, int32_t hi) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int v = d[i];
+    if (v < 0) v = 0;
+    if (v > hi) v = hi;
+    d[i] = static_cast<int8_t>(v);
+  }
+}
+__global__ void relu_i32_kernel(int32_t* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (d[i] < 0) d[i] = 0;
+}
+
+// ---- gemm_bsr_int8 (sw/golden/gemm_bsr_int8.py:16-104): the reference's float32 "golden" with per-row scales, replayed
+// operation by operation.  Compatibility path: it is order-dependent float arithmetic on tiny shapes, so
+// one thread owns one output element and walks (block-row, block, local row) in the reference's order.
+// Step 1: re-quantise every stored block row with the scale of its global row (:74-79); T = float or double selects the
+// dtype NumPy's promotion gives block / scale.
+template <typename T>
+__global__ void fp32compat_requant_kernel(const T* __restrict__ data, const int32_t* __restrict__ blk_row, int64_t nnz, int32_t bh,
+                                          int32_t bw, const T* __restrict__ scales, int32_t n_scales, int8_t* __restrict__ q) {
+  const int64_t total = nnz * bh * bw;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = i / (bh * bw);
+    const int r = static_cast<int>((i / bw) % bh);
+    const int64_t g = static_cast<int64_t>(blk_row[b]) * bh + r;
+    const T s = g < n_scales ? scales[g] : scales[0];
+    T v = rint(data[i] / s);                       // IEEE divide, round half to even (np.rint)
+    v = v < T(-128) ? T(-128) : (v > T(127) ? T(127) : v);
+    q[i] = static_cast<int8_t>(v);
+  }
+}
+// Step 2: C[m, n].  a64 / s64: scale_A / scales_B are float64 (NumPy then carries the products, and the += , in double and
+// rounds to float32 on the store); otherwise every product and the add are float32.
+__global__ void fp32compat_gemm_kernel(const int8_t* __restrict__ A, int64_t M, int64_t lda, const int32_t* __restrict__ indptr,
+                                       const int32_t* __restrict__ indices, const int8_t* __restrict__ q, int32_t nbr, int32_t b,
+                                       int64_t K, int64_t N, double scale_a, int32_t a64, const void* __restrict__ scales,
+                                       int32_t s64, int32_t n_scales, float* __restrict__ C, int64_t ldc) {
+  const int64_t total = M * N;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = idx / N, n = idx - m * N;
+    float c = 0.f;
+    for (int br = 0; br < nbr; ++br) {
+      const int64_t rs = static_cast<int64_t>(br) * b;
+      for (int i = indptr[br]; i < indptr[br + 1]; ++i) {
+        const int64_t cs = static_cast<int64_t>(indices[i]) * b;
+        if (n < cs || n >= cs + b) continue;
+        const int j = static_cast<int>(n - cs);
+        int t = 0;                                  // (A[:, rs:rs+b] @ Q^T)[m, j]
+        for (int k = 0; k < b; ++k) t += static_cast<int>(A[m * lda + rs + k]) * static_cast<int>(q[(static_cast<int64_t>(i) * b + j) * b + k]);
+        const float t32 = __int2float_rn(t);
+        for (int r = 0; r < b; ++r) {
+          if (rs + r >= K) break;
+          const int64_t g = rs + r;
+          const int64_t gi = g < n_scales ? g : 0;
+          if (!a64 && !s64) {
+            const float x = __fmul_rn(t32, static_cast<float>(scale_a));
+            c = __fadd_rn(c, __fmul_rn(x, static_cast<const float*>(scales)[gi]));
+          } else {
+            const double x = a64 ? __dmul_rn(static_cast<double>(t32), scale_a)
+                                 : static_cast<double>(__fmul_rn(t32, static_cast<float>(scale_a)));
+            const double s = s64 ? static_cast<const double*>(scales)[gi] : static_cast<double>(static_cast<const float*>(scales)[gi]);
+            c = static_cast<float>(__dadd_rn(static_cast<double>(c), __dmul_rn(x, s)));
+          }
+        }
+      }
+    }
+    C[m * ldc + n] = c;
+  }
+}
+
 __global__ void add_residual_i8_kernel(const int8_t* __restrict__ a, const int8_t* __restrict__ b,
                                        int8_t* __restrict__ out, int64_t n, float sa, float sb, float so) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;

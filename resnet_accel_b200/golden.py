@@ -67,11 +67,61 @@ def gemm_bsr_int8_golden(activations, bsr_layer: Dict):
     return out.cpu().numpy() if as_numpy else out
 
 
+def _is_f64_scalar(v) -> bool:
+    """NumPy promotion (NEP 50): Python floats are weak (the float32 array keeps its dtype), np.float64 scalars and 0-d
+    float64 arrays are strong (the product is carried in float64)."""
+    if isinstance(v, np.ndarray):
+        return v.dtype == np.float64
+    return isinstance(v, np.floating) and np.dtype(type(v)) == np.float64
+
+
 def gemm_bsr_int8(A_int8, bsr_B: Dict, scale_A, scales_B):
-    """sw/golden/gemm_bsr_int8.py:16-104 is a float32 'golden' whose arithmetic is order-dependent and
-    unpinned by the reference's tests.  This build offers the INT32 path
-    (:func:`gemm_bsr_int8_golden`) and the fused per-channel de-quantisation (``BsrPlan.gemm(..., "f32")``);
-    the quirky replay is deliberately not provided on the device."""
-    raise AcceleratorError(INVALID_CONFIG,
-                           "gemm_bsr_int8 (FP32 compat golden) is not part of the device path; use "
-                           "gemm_bsr_int8_golden or BsrPlan.gemm(out_kind='f32')")
+    """sw/golden/gemm_bsr_int8.py:16-104 on the GPU: the reference's float32 'golden' with per-row scales.
+
+    Its arithmetic is not ``A @ B``: every stored block is re-quantised with the scales of its rows, the
+    INT32 tile ``A[:, block-row span] @ block^T`` is added to the output once per local row with that row's scale, in
+    float32 (or float64, when the caller's scales are float64) and in (block-row, block, local-row) order.  The reference's
+    own tests only pin its output shape; this replay is bit-exact against the reference function itself
+    (tests/golden/golden_fp32_cases.npz).  A compatibility path on CUDA cores - the numerical oracle is
+    :func:`gemm_bsr_int8_golden`."""
+    import ctypes as C
+    from . import _lib
+    as_numpy = not isinstance(A_int8, torch.Tensor)
+    dev = ops._require_cuda()
+    data = bsr_B["data"]
+    data_np = data.detach().cpu().numpy() if isinstance(data, torch.Tensor) else np.asarray(data)
+    scales_np = scales_B.detach().cpu().numpy() if isinstance(scales_B, torch.Tensor) else np.asarray(scales_B)
+    if scales_np.ndim != 1 or scales_np.size == 0:
+        raise ValueError("scales_B must be a non-empty 1-D array")
+    K, N = (int(v) for v in bsr_B["shape"])
+    bh, bw = (int(v) for v in bsr_B["blocksize"])
+    if bh != bw:
+        raise ValueError(f"matmul: A[:, block rows] @ block.T needs square blocks, got {bh}x{bw}")     # NumPy raises here too
+    if K % bh:
+        raise ValueError("matmul: the last block-row is partial (K is not a multiple of the block size)")
+    x = ops.to_device(A_int8, torch.int8, dev)
+    if x.dim() != 2 or x.shape[1] < K:
+        raise ValueError("A_int8 must be [M, K]")
+    indptr = np.ascontiguousarray(np.asarray(ops._host(bsr_B["indptr"])), dtype=np.int32)
+    indices = np.ascontiguousarray(np.asarray(ops._host(bsr_B["indices"])), dtype=np.int32)
+    nbr, nnz = len(indptr) - 1, int(indices.size)
+    s64 = scales_np.dtype == np.float64
+    div64 = s64 or data_np.dtype == np.float64
+    if scales_np.dtype not in (np.float32, np.float64):
+        scales_np = scales_np.astype(np.float32)
+    fdt = np.float64 if div64 else np.float32
+    data_d = ops.to_device(np.ascontiguousarray(data_np.reshape(-1), dtype=fdt), torch.float64 if div64 else torch.float32, dev)
+    sdiv_d = ops.to_device(np.ascontiguousarray(scales_np, dtype=fdt), torch.float64 if div64 else torch.float32, dev)
+    s_d = ops.to_device(np.ascontiguousarray(scales_np), torch.float64 if s64 else torch.float32, dev)
+    blk_row = np.repeat(np.arange(nbr, dtype=np.int32), np.diff(indptr))
+    ip_d, ix_d, br_d = (ops.to_device(a, torch.int32, dev) for a in (indptr, indices if nnz else np.zeros(1, np.int32),
+                                                                    blk_row if nnz else np.zeros(1, np.int32)))
+    q = torch.empty(max(nnz * bh * bw, 1), dtype=torch.int8, device=dev)
+    M = int(x.shape[0])
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    a64 = _is_f64_scalar(scale_A)
+    _lib.check(_lib.lib().accel_gemm_bsr_int8_fp32(
+        ops._ptr(x), M, x.stride(0) if M else K, ops._ptr(ip_d), ops._ptr(ix_d), ops._ptr(data_d), ops._ptr(sdiv_d), int(div64),
+        ops._ptr(br_d), nnz, nbr, bh, K, N, C.c_double(float(scale_A)), int(a64), ops._ptr(s_d), int(s64), int(scales_np.size),
+        ops._ptr(q), ops._ptr(out), N, ops._stream()))
+    return out.cpu().numpy() if as_numpy else out

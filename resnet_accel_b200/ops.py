@@ -497,6 +497,32 @@ def add_residual_i8(a: torch.Tensor, b: torch.Tensor, s_main: float, s_res: floa
     return out
 
 
+def relu_int8(x: torch.Tensor) -> torch.Tensor:
+    """relu_int8 (golden_models.cpp:278-283), in place on a contiguous CUDA int8 tensor; returns it."""
+    _check_inplace(x, torch.int8)
+    check(_lib.lib().accel_relu_i8(_ptr(x), x.numel(), _stream()))
+    return x
+
+
+def relu6_int8(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """relu6_int8 (golden_models.cpp:323-330): clamp to [0, int8(6.0f / scale)], in place; returns the tensor."""
+    _check_inplace(x, torch.int8)
+    check(_lib.lib().accel_relu6_i8(_ptr(x), x.numel(), float(scale), _stream()))
+    return x
+
+
+def relu_int32(x: torch.Tensor) -> torch.Tensor:
+    """relu_int32 (golden_models.cpp:298-303), in place; returns the tensor."""
+    _check_inplace(x, torch.int32)
+    check(_lib.lib().accel_relu_i32(_ptr(x), x.numel(), _stream()))
+    return x
+
+
+def _check_inplace(x, dtype) -> None:
+    if not _is_cuda(x) or x.dtype != dtype or not x.is_contiguous():
+        raise AcceleratorError(_lib.INVALID_CONFIG, f"expected a contiguous CUDA {dtype} tensor")
+
+
 def maxpool_i8(x: torch.Tensor, pool: int, stride: int, pad: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     in_pitch = _row_pitch(x) if x.dim() == 4 else None
     if in_pitch is None:
