@@ -1,25 +1,28 @@
 #!/usr/bin/env python3
-"""Headline benchmark: ResNet-18 BSR-INT8 images/sec @70 % block sparsity (BASELINE.json `metric`).
+"""Benchmark of the B200-native BSR-INT8 hot path (BASELINE.json `metric`: ResNet-18 BSR-INT8 images/sec @70 % sparsity).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--sparsity S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload W] [--batch B] [--sparsity S]
 
-One process per GPU (torchrun for N > 1; RANK / LOCAL_RANK / WORLD_SIZE from the environment).
-A "step" is one pass of the hot path over one batch of synthetic images: the ResNet-18 conv
-backbone + pools + FC, every conv/FC as a 14x14-BSR INT8 layer with fused per-channel requant
-(BASELINE.json configs[2]/[3] shape family: batch 256 per GPU, 224x224).  The batch is sharded
-by GPU (weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
+One process per GPU (torchrun for N > 1; RANK / LOCAL_RANK / WORLD_SIZE from the environment).  Rank 0 prints ONE JSON line.
 
-  value      images/s, inputs resident in HBM, whole network replayed as one CUDA graph, L2 flushed
-             between timed steps, CUDA-event time, max over ranks.
-  e2e        same metric through the public API with HOST buffers: pinned-host -> device copy of
-             the int8 images and device -> host read of the INT32 logits inside the timed region.
-  roofline   the tensor-core convolution / FC launches of one step (conv_ws_kernel for the 3x3 layers, stem_ws_kernel for
-             conv1 + max-pool, bsr_tcp_kernel for the FC): algorithmic bytes / event-timed duration vs the measured HBM
-             peak (MEASURED_PEAKS.json); `traffic` = DRAM bytes of the same launches from the committed ncu capture
-             (profiles/r01_traffic.json, written by tools/ncu_launches.py).
-  cpu_baseline  the reference's C++ golden path (oracle/_ref: conv2d_int8_im2col + relu_int32 +
-             requantize_int32_to_int8 + add_residual_int8, hw/sim/cpp/src/golden_models.cpp) on a
-             bounded sample of the same workload on the host cores.
+Workloads (`--workload`, default `resnet18` = the configuration the metric is quoted on):
+  resnet18             ResNet-18 at 224x224, every conv/FC a 14x14-BSR INT8 layer with fused per-channel requant, batch 256
+                       per GPU, batch-sharded over the GPUs (weak scaling, no data-path collective).   BASELINE configs 3 / 4.
+  gemm4096             synthetic BSR INT8 GEMM 4096 x 4096 x 4096 at `--sparsity` (SURVEY.md 8d recipe).      BASELINE config 2.
+  mnist                MNIST-CNN INT8 with FC1 pruned to `--sparsity` by block L2 norm, batch 64.               BASELINE config 1.
+  resnet50_fc_sharded  ResNet-50, batch-sharded trunk, block-row-sharded FC with NCCL all-gathers.              BASELINE config 5.
+
+A "step" is one pass of the hot path over one batch of synthetic input.
+  value      units/s, inputs resident in HBM, the step replayed as one CUDA graph (where the workload has one), L2 flushed
+             between timed steps, CUDA-event time on the launching stream, max over ranks.
+  e2e        the same metric through the public API with HOST buffers: pinned-host -> device copy of the step's input and
+             device -> host read of its result inside the timed region (`ResNetInference.run_inference_pipelined`, ...).
+  roofline   per-kernel table (`kernels`: name, us, algorithmic bytes, dense-equivalent ops, fractions) from CUDA events
+             around every launch of an eager forward, and the totals: algorithmic bytes / time vs the measured HBM peak
+             (MEASURED_PEAKS.json), dense-equivalent ops / time vs the measured INT8 tensor peak (profiles/r02_int8_peak.json).
+  bit_exact  the step's output for a sample of its inputs compared with the CPU reference, outside the timed region.
+  sustained  the same step replayed back to back for `--sustain-seconds` (clocks under a seconds-long load).
+  cpu_baseline  the reference's CPU path on a bounded sample of the same workload on the host cores (rank 0, N = 1).
 
 `--impl reference` times only that CPU path (no GPU code) and prints the same line shape.
 """
@@ -40,30 +43,34 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ResNet-18 BSR-INT8 images/sec @70% sparsity"
 UNIT = "images/s"
+WORKLOADS = ("resnet18", "gemm4096", "mnist", "resnet50_fc_sharded")
 
 
 # ----------------------------------------------------------------------------------------- helpers
-def measured_traffic():
-    """DRAM bytes (read + write) of the conv / fc launches of one step, from the committed ncu capture of this command."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def _json(path):
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, path)) as f:
             return json.load(f)
     except Exception:
         return None
 
 
 def measured_peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            d = json.load(f)
-        return float(d.get("hbm_gbs", 6650.0)), 2.0 * float(d.get("bf16_tflops_sustained", 1400.0)), "measured"
-    return 6650.0, 2.0 * 1400.0, "fallback"          # B200_PROFILING.md fallback figures
+    """(HBM GB/s, INT8 dense TOPS burst, INT8 dense TOPS sustained, source strings)."""
+    d = _json("MEASURED_PEAKS.json")
+    hbm, hbm_src = (float(d["hbm_gbs"]), "MEASURED_PEAKS.json (driver, copy bandwidth)") if d and "hbm_gbs" in d else \
+        (6650.0, "fallback of B200_PROFILING.md")
+    p = _json("profiles/r02_int8_peak.json")
+    if p and "int8_tops_burst" in p:
+        return hbm, float(p["int8_tops_burst"]), float(p["int8_tops_sustained"]), hbm_src, \
+            "profiles/r02_int8_peak.json (cuBLASLt INT8 8192^3 on this pool: best of 10 / 4 s back to back)"
+    bf = float(d.get("bf16_tflops", 1590.0)) if d else 1590.0
+    bfs = float(d.get("bf16_tflops_sustained", 1400.0)) if d else 1400.0
+    return hbm, 2.0 * bf, 2.0 * bfs, hbm_src, "2 x measured bf16 (no INT8 measurement found)"
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi / NVML clocks and throttle reasons sampled while the timed regions run (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -73,7 +80,6 @@ class ClockSampler:
         self.nvml_rows, self._stop, self._thr = [], threading.Event(), None
 
     def _nvml_loop(self):
-        """NVML from a thread, every ~2 ms: the timed regions last tens of milliseconds, shorter than nvidia-smi's period."""
         try:
             import pynvml as N
             import torch
@@ -89,7 +95,7 @@ class ClockSampler:
             while not self._stop.is_set():
                 sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
                 bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
-                self.nvml_rows.append((sm, mx, [n for n, b in names if bits & b]))
+                self.nvml_rows.append((time.time(), sm, mx, [n for n, b in names if bits & b]))
                 time.sleep(0.002)
         except Exception:
             pass
@@ -108,6 +114,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def window(self, t0: float, t1: float):
+        """Median SM clock of the NVML samples taken inside [t0, t1]."""
+        v = [sm for t, sm, _, _ in self.nvml_rows if t0 <= t <= t1]
+        return (float(np.median(v)) if v else None), len(v)
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
@@ -115,7 +126,7 @@ class ClockSampler:
         if self._thr:
             self._thr.join(timeout=1.0)
         sm, mx, reasons = [], 0.0, set()
-        for v, m, rs in self.nvml_rows:
+        for _, v, m, rs in self.nvml_rows:
             sm.append(v); mx = max(mx, m); reasons.update(rs)
         for r in self.rows:
             try:
@@ -130,7 +141,51 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------- CPU reference arm
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this process to the CPUs NVML names as local to its GPU (its NUMA node), BEFORE any pinned host buffer is
+    allocated: first-touch then places those buffers on the same node.  Returns a short description for the JSON line."""
+    try:
+        import pynvml as N
+        import torch
+        N.nvmlInit()
+        try:
+            h = N.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)).encode())
+        except Exception:
+            h = N.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = N.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"cpus": f"{allowed[0]}-{allowed[-1]} ({len(allowed)})", "bound": True}
+        return {"cpus": None, "bound": False}
+    except Exception as e:      # no NVML / not permitted: run unbound
+        return {"cpus": None, "bound": False, "why": repr(e)[:80]}
+
+
+def h2d_ceiling_gbs(nbytes: int, seconds: float = 0.5) -> float:
+    """Bare pinned-host -> device copy loop of this rank (all ranks run it at the same time): the host-side ceiling that
+    bounds `e2e`, measured with nothing else on the GPU."""
+    import torch
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n, t0 = 0, time.time()
+    e0.record()
+    while time.time() - t0 < seconds:
+        for _ in range(8):
+            dst.copy_(src, non_blocking=True)
+        n += 8
+        torch.cuda.current_stream().synchronize()
+    e1.record(); torch.cuda.synchronize()
+    return n * nbytes / (e0.elapsed_time(e1) / 1e3) / 1e9
+
+
+# ----------------------------------------------------------------------------------------- CPU reference arm (ResNet-18)
 def host_network(sparsity: float):
     """Synthetic ResNet-18 weights on the host, built with numpy + the oracle only (no GPU code)."""
     from oracle import bsr_oracle as O
@@ -183,40 +238,111 @@ def cpu_forward_image(x, specs, layers, s_out):
     return t[specs[-1].name]
 
 
-def cpu_reference_rate(sparsity: float, n_images: int, threads: int, repeats: int = 1):
+def cpu_reference_rate(sparsity: float, n_images: int, threads: int, repeats: int = 1, images=None):
+    """(images/s, per-repeat seconds, logits of the last repeat) of the reference C++ golden chain, one image per thread."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import c_oracle
     if not c_oracle.have_ref():
         raise RuntimeError("oracle/_ref/libref_golden.so missing (built by __graft_entry__.build() in the dev container)")
     specs, layers, s_out = host_network(sparsity)
-    rng = np.random.default_rng(0)
-    imgs = rng.integers(-128, 128, (n_images, 3, 224, 224), dtype=np.int8)
-    times = []
+    imgs = images if images is not None else np.random.default_rng(0).integers(-128, 128, (n_images, 3, 224, 224), dtype=np.int8)
+    times, outs = [], None
     with ThreadPoolExecutor(max_workers=threads) as ex:
         for _ in range(repeats):
             t0 = time.perf_counter()
-            list(ex.map(lambda im: cpu_forward_image(im, specs, layers, s_out), imgs))
+            outs = list(ex.map(lambda im: cpu_forward_image(im, specs, layers, s_out), imgs))
             times.append(time.perf_counter() - t0)
-    return n_images / min(times), times
+    return len(imgs) / min(times), times, np.stack([o.reshape(-1) for o in outs])
 
 
-def run_reference(args, rank: int):
+# ----------------------------------------------------------------------------------------- workload descriptions
+def workload_config(args, world: int) -> dict:
+    """The `config` object - identical for the GPU arm and the reference arm."""
+    w = args.workload
+    if w == "resnet18":
+        return {"workload": "resnet18_full_bsr14_int8", "sparsity_pct": args.sparsity, "batch_per_gpu": args.batch, "image": 224,
+                "block": 14, "parallelism": f"batch-shard x{world} (no collective)"}
+    if w == "gemm4096":
+        return {"workload": "bsr_gemm_4096x4096x4096_int8", "sparsity_pct": args.sparsity, "rows_per_gpu": 4096, "block": 14,
+                "parallelism": f"row-shard x{world} (no collective)"}
+    if w == "mnist":
+        return {"workload": "mnist_cnn_int8_fc1_bsr14", "fc1_sparsity_pct": args.sparsity, "batch_per_gpu": 64, "block": 14,
+                "parallelism": f"batch-shard x{world} (no collective)"}
+    return {"workload": "resnet50_bsr14_int8_fc_block_row_sharded", "sparsity_pct": args.sparsity, "batch_per_gpu": args.batch,
+            "image": 224, "block": 14,
+            "parallelism": f"trunk batch-shard x{world}; fc block-rows x{world} + 2 NCCL all-gathers (features, logits)"}
+
+
+def workload_metric(args):
+    w = args.workload
+    if w == "resnet18":
+        return (METRIC if abs(args.sparsity - 70.0) < 1e-9 else f"ResNet-18 BSR-INT8 images/sec @{args.sparsity:g}% sparsity"), UNIT
+    if w == "gemm4096":
+        return f"BSR-INT8 GEMM 4096x4096x4096 @{args.sparsity:g}% block sparsity, GEMMs/sec", "GEMMs/s"
+    if w == "mnist":
+        return f"MNIST-CNN INT8 (FC1 {args.sparsity:g}% block-sparse) images/sec", UNIT
+    return f"ResNet-50 BSR-INT8 images/sec @{args.sparsity:g}% sparsity, block-row-sharded FC", UNIT
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
+    metric, unit = workload_metric(args)
     threads = os.cpu_count() or 1
-    n_images = max(threads, 1) * args.ref_images_per_thread
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_reference_rate(args.sparsity, max(1, threads), threads)
-    rate, times = cpu_reference_rate(args.sparsity, n_images, threads, repeats=max(1, args.steps))
-    line = {"metric": METRIC, "value": rate, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+    cfg = workload_config(args, world)
+    if args.workload == "resnet18":
+        n_images = max(threads, 1) * args.ref_images_per_thread
+        for _ in range(args.warmup if args.warmup < 2 else 1):
+            cpu_reference_rate(args.sparsity, max(1, threads), threads)
+        rate, times, _ = cpu_reference_rate(args.sparsity, n_images, threads, repeats=max(1, args.steps))
+        kind, sample = "reference", (f"{n_images} images per step through golden_models.cpp (dense conv2d_int8_im2col path), "
+                                     "one image per host thread")
+    else:
+        rate, times, kind, sample = cpu_port_rate(args, threads)
+    line = {"metric": metric, "value": rate, "unit": unit, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * min(times), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {"workload": "resnet18_full_bsr14_int8", "sparsity_pct": args.sparsity, "image": 224,
-                       "images_per_step": n_images},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
-                             "sample": f"{n_images} images per step through golden_models.cpp (dense conv2d_int8_im2col path), one image per host thread"},
-            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def cpu_port_rate(args, threads: int):
+    """CPU arm of the secondary workloads: the plain-C / NumPy port of the reference algorithm (the reference's own Python
+    golden for them is a pure-Python triple loop, ~1 us per MAC) on a bounded sample."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import bsr_oracle as O
+    from oracle import c_oracle
+    if args.workload == "gemm4096":
+        rng = np.random.default_rng(0)
+        W = rng.integers(-128, 128, (4096, 4096), dtype=np.int8)
+        W = (W * O.create_sparse_mask((4096, 4096), args.sparsity, 14, 42).astype(np.int8)).astype(np.int8)
+        A = rng.integers(-128, 128, (4096, 4096), dtype=np.int8)
+        bsr = O.build_bsr_14x14_int8_direct(W)
+        rows_per_thread = 8
+        rows = threads * rows_per_thread
+        chunks = [A[i * rows_per_thread:(i + 1) * rows_per_thread] for i in range(threads)]
+        times = []
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            for _ in range(max(1, min(args.steps, 3))):
+                t0 = time.perf_counter()
+                list(ex.map(lambda a: c_oracle.bsr_gemm_i32(a, bsr["indptr"], bsr["indices"], bsr["data"]), chunks))
+                times.append(time.perf_counter() - t0)
+        return (rows / 4096.0) / min(times), times, "port", (f"{rows} of 4096 activation rows through oracle/c (gemm_bsr_int8_golden "
+                                                            "restated in C), scaled linearly, one row slice per host thread")
+    if args.workload == "mnist":
+        w = dict(np.load(os.path.join(ROOT, "tests", "golden", "mnist_int8.npz")))
+        imgs = np.concatenate([w["inputs_u8"], np.random.default_rng(64).integers(0, 256, (32, 28, 28), dtype=np.uint8)], 0)
+        sc = O.mnist_activation_scales(O.mnist_float_forward(O.mnist_preprocess(imgs), w))
+        fc1 = O.mnist_prune_fc1(w["fc1_weight_int8"], args.sparsity / 100.0)
+        times = []
+        for _ in range(max(1, min(args.steps, 5))):
+            t0 = time.perf_counter()
+            O.mnist_cnn_int8_forward(imgs, w, sc, fc1)
+            times.append(time.perf_counter() - t0)
+        return 64 / min(times), times, "port", "the 64-image batch through the NumPy restatement of the golden chain, one thread"
+    raise SystemExit("--impl reference: no CPU arm for workload " + args.workload)
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -225,32 +351,31 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    # before the first pinned allocation; a single rank keeps every host core (the CPU baseline runs on them)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else {"cpus": None, "bound": False, "why": "single rank"}
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from resnet_accel_b200 import layers as L
 
-    B = args.batch
-    net = L.BsrNetwork(L.resnet18_specs(), args.sparsity, B)
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    x_dev = torch.randint(-128, 128, (B, 3, 224, 224), dtype=torch.int8, device="cuda", generator=gen)
-    x_host = x_dev.cpu().pin_memory()
-    logits_host = torch.empty((B, 1000), dtype=torch.int32).pin_memory()
-    net.capture(x_dev)
+    W = build_workload(args, rank, local_rank, world)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-    work = net.work()
-    conv_names = [sp.name for sp in net.specs if sp.kind in ("conv", "fc")]
-    n_launch_step = net.n_launches
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, K, W):
-        for _ in range(W):
+    def allmax(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step_fn, K, Wn):
+        for _ in range(Wn):
             flush.zero_()
             step_fn()
         barrier()
@@ -263,127 +388,461 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             e1.record()
             evs.append((e0, e1))
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        if dist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return allmax(sum(a.elapsed_time(b) for a, b in evs))
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # (1) kernel-only: inputs resident in HBM, graph replay
-    ms_total = timed(lambda: net.replay(), args.steps, args.warmup)
-    # (2) end to end through the public API with HOST buffers.  Two-deep pipeline, all inside the timed region:
-    #     copy stream: pinned host -> device staging buffer of step i+1   |  compute stream: staging -> network input,
-    #     graph replay, INT32 logits -> pinned host.  Events on the compute stream bracket all K steps.
-    copy_stream = torch.cuda.Stream()
-    staging = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
-    staged = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    # (1) kernel-only: inputs resident in HBM
+    ms_total = timed(W.step, args.steps, args.warmup)
+    # (2) end to end through the public API with HOST buffers, all copies inside the timed region
+    for _ in range(2):
+        W.e2e(max(args.warmup, 3))
+    barrier()
+    ms_e2e = allmax(W.e2e(args.steps))
+    barrier()
+    # (3) sustained: the step back to back for seconds (clocks under load)
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_est = max(8, int(args.sustain_seconds * 1e3 / max(ms_total / args.steps, 1e-3)))
+        barrier()
+        t_w0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_est):
+            W.step()
+        e1.record(); torch.cuda.synchronize()
+        t_w1 = time.time()
+        ms_s = allmax(e0.elapsed_time(e1))
+        mhz, ns = sampler.window(t_w0, t_w1) if rank == 0 else (None, 0)
+        sustained = {"seconds": ms_s / 1e3, "steps": n_est, "value": world * W.units_per_step * n_est / (ms_s / 1e3), "unit": W.unit,
+                     "sm_mhz_median": mhz, "clock_samples": ns, "l2": "not flushed (back to back)"}
+    # (4) host-copy ceiling of the box, all ranks at once
+    ceiling = None
+    if W.h2d_bytes:
+        barrier()
+        g = h2d_ceiling_gbs(W.h2d_bytes)
+        if dist is not None:
+            t = torch.tensor([g], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            g = float(t.item())
+        ceiling = g
+    clocks = sampler.stop() if rank == 0 else None
+    # (5) per-kernel table + bit-exactness, outside every timed region
+    kernels = W.kernel_table(flush)
+    bit_exact, cpu_base = W.check_and_cpu_baseline(rank, world)
 
-    def e2e_run(K):
+    if rank == 0:
+        hbm_peak, i8_burst, i8_sus, hbm_src, i8_src = measured_peaks()
+        ms_step = ms_total / args.steps
+        value = world * W.units_per_step * args.steps / (ms_total / 1e3)
+        e2e_val = world * W.units_per_step * args.steps / (ms_e2e / 1e3)
+        k_us = sum(k["us"] for k in kernels)
+        k_bytes = sum(k["bytes"] for k in kernels)
+        k_ops = sum(k["useful_ops"] for k in kernels)
+        k_dense = sum(k["dense_ops"] for k in kernels)
+        for k in kernels:
+            k["hbm_frac"] = k["bytes"] / (k["us"] * 1e-6) / 1e9 / hbm_peak if k["us"] else None
+            k["dense_equiv_tensor_frac"] = k["dense_ops"] / (k["us"] * 1e-6) / 1e12 / i8_burst if k["us"] else None
+        ach_gbs = k_bytes / (k_us * 1e-6) / 1e9 if k_us else 0.0
+        dense_tops = k_dense / (k_us * 1e-6) / 1e12 if k_us else 0.0
+        hbm_frac, tensor_frac = ach_gbs / hbm_peak, dense_tops / i8_burst
+        bound = "tensor" if tensor_frac >= hbm_frac else "hbm"
+        metric, unit = workload_metric(args)
+        cfg = workload_config(args, world)
+        cfg.update({"l2": "value: flushed between timed steps (256 MiB memset); e2e: per-step working set >> 126 MB L2"
+                    if args.workload in ("resnet18", "resnet50_fc_sharded") else
+                    "value: flushed between timed steps (256 MiB memset)", **W.config_extra})
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8", "data": "synthetic", "config": cfg,
+            "roofline": {"bound": bound,
+                         "achieved": dense_tops if bound == "tensor" else ach_gbs,
+                         "peak": i8_burst if bound == "tensor" else hbm_peak,
+                         "unit": "TOP/s" if bound == "tensor" else "GB/s",
+                         "frac": max(hbm_frac, tensor_frac),
+                         "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": hbm_frac, "peak_source": hbm_src},
+                         "tensor": {"dense_equiv_tops": dense_tops, "useful_tops": k_ops / (k_us * 1e-6) / 1e12 if k_us else 0.0,
+                                    "peak_tops_burst": i8_burst, "peak_tops_sustained": i8_sus, "dense_equiv_frac": tensor_frac,
+                                    "useful_frac": (k_ops / (k_us * 1e-6) / 1e12 / i8_burst) if k_us else 0.0, "peak_source": i8_src},
+                         "traffic": W.measured_traffic(), "traffic_source": W.traffic_source,
+                         "kernel": W.kernel_note, "kernel_ms_per_step": k_us / 1e3, "algorithmic_bytes_per_step": k_bytes,
+                         "useful_ops_per_step": k_ops, "dense_equiv_ops_per_step": k_dense, "kernels": kernels},
+            "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": int(W.h2d_bytes) * world,
+                    "d2h_bytes_per_step": int(W.d2h_bytes) * world, "api": W.e2e_api,
+                    "h2d_ceiling_gbs_all_ranks": ceiling, "h2d_needed_gbs_all_ranks": W.h2d_bytes * world / (ms_step / 1e3) / 1e9,
+                    "numa": numa},
+            "gpu_launches": W.launches_per_step * args.steps,
+            "bit_exact": bit_exact,
+            "clocks": clocks,
+            "sustained": sustained,
+        }
+        line.update(W.extra_line())
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------- workloads (GPU arm)
+class _Workload:
+    unit = UNIT
+    config_extra: dict = {}
+    traffic_source = None
+    kernel_note = ""
+    e2e_api = ""
+    h2d_bytes = 0
+    d2h_bytes = 0
+
+    def measured_traffic(self):
+        return None
+
+    def extra_line(self):
+        return {}
+
+
+def _time_eager(fn, flush, reps=3):
+    """Per-launch (name, us) from CUDA events recorded on the launching stream around every launch of an eager forward."""
+    import torch
+    acc = {}
+    order = []
+    for r in range(reps + 1):
+        flush.zero_()
+        ev = []
+        fn(ev)
+        torch.cuda.synchronize()
+        if r == 0:
+            continue                # warm-up
+        for name, a, b in ev:
+            if name not in acc:
+                acc[name] = 0.0
+                order.append(name)
+            acc[name] += a.elapsed_time(b) * 1e3
+    return [(n, acc[n] / reps) for n in order]
+
+
+class ResNet18Workload(_Workload):
+    def __init__(self, args, rank, world):
+        import torch
+        from resnet_accel_b200 import layers as L
+        self.args, self.world = args, world
+        B = args.batch
+        self.engine = L.ResNetInference(batch=B)
+        self.engine.load_synthetic(args.sparsity)
+        self.net = self.engine.net
+        gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        self.x_dev = torch.randint(-128, 128, (B, 3, 224, 224), dtype=torch.int8, device="cuda", generator=gen)
+        self.x_host = [self.x_dev.cpu().pin_memory(), self.x_dev.cpu().pin_memory()]      # one pinned buffer per in-flight step
+        self.logits_host = [torch.empty((B, 1000), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.net.capture(self.x_dev)
+        self.units_per_step = B
+        self.h2d_bytes, self.d2h_bytes = int(self.x_dev.numel()), B * 1000 * 4
+        self.launches_per_step = self.net.n_launches
+        self.config_extra = {"graph": "one CUDA graph per step", "e2e_pipeline": "2-deep: H2D of step i+1 overlaps step i"}
+        self.e2e_api = "ResNetInference.run_inference_pipelined(pinned host int8 batches -> pinned host int32 logits)"
+        self.kernel_note = ("conv_ws_kernel (3x3 layers, stride-2 layers with their downsample fused) + stem_ws_kernel (conv1 + "
+                            "max-pool) + avgpool + gemm_ws_kernel (fc); algorithmic bytes of the reference's layer sequence "
+                            "(unfused), dense-equivalent ops = the dense layer's 2*MACs")
+        t = _json("profiles/r02_traffic.json") or _json("profiles/r01_traffic.json")
+        self._traffic = t
+        self.traffic_source = (t or {}).get("source")
+
+    def step(self):
+        self.net.replay()
+
+    def e2e(self, K):
+        import torch
         cur = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(cur)
-        copy_stream.wait_event(e0)                                  # the first copy starts inside the timed region
-        for i in range(K):
-            b = i & 1
-            with torch.cuda.stream(copy_stream):
-                if i >= 2:
-                    copy_stream.wait_event(consumed[b])             # the staging buffer was read by step i-2
-                staging[b].copy_(x_host, non_blocking=True)
-                staged[b].record(copy_stream)
-            cur.wait_event(staged[b])
-            net.static_in.copy_(staging[b], non_blocking=True)
-            consumed[b].record(cur)
-            net.graph.replay()
-            logits_host.copy_(net.buffers["fc"], non_blocking=True)
+        self.engine.run_inference_pipelined([self.x_host[i & 1] for i in range(K)], [self.logits_host[i & 1] for i in range(K)])
         e1.record(cur)
         cur.synchronize()
         return e0.elapsed_time(e1)
 
-    for _ in range(2):
-        e2e_run(max(args.warmup, 3))
-    barrier()
-    ms_e2e = e2e_run(args.steps)
-    barrier()
-    if dist is not None:
-        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    def measured_traffic(self):
+        return (self._traffic or {}).get("conv_fc_dram_bytes_per_step")
 
-    # (3) dominant kernel: every conv/fc launch of one step, event-timed on the launching stream
-    def conv_only():
-        net.forward(net.static_in)
-    # eager forward = same launches as the graph (the two pools are ~5 % of the step and carry no algorithmic conv bytes)
-    for _ in range(2):
-        conv_only()
-    torch.cuda.synchronize()
-    reps = 3
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = 0.0
-    for _ in range(reps):
-        flush.zero_()
-        e0.record(); conv_only(); e1.record()
+    def kernel_table(self, flush):
+        work = {l["name"]: l for l in self.net.work()["layers"]}
+        rows = _time_eager(lambda ev: self.net.forward(self.net.static_in, launch_events=ev), flush)
+        fused = dict(self.net.fused_ds)
+        fused.update(self.net.fused_pool)
+        out = []
+        for name, us in rows:
+            parts = [name] + ([fused[name]] if name in fused else [])
+            out.append({"name": "+".join(parts), "us": us, "bytes": sum(work[p]["bytes"] for p in parts),
+                        "useful_ops": sum(work[p]["ops"] for p in parts), "dense_ops": sum(work[p]["dense_ops"] for p in parts)})
+        return out
+
+    def check_and_cpu_baseline(self, rank, world):
+        """GPU logits of a few of the step's own images against the reference C++ golden chain; the same CPU run is the
+        cpu_baseline sample at N = 1."""
+        if rank != 0:
+            return None, None
+        threads = len(os.sched_getaffinity(0)) or 1
+        n_img = min(threads * self.args.ref_images_per_thread if world == 1 else min(4, threads), self.args.batch)
+        if self.args.no_cpu_baseline:
+            return None, None
+        try:
+            imgs = self.x_host[0][:n_img].numpy()
+            rate, _, ref_logits = cpu_reference_rate(self.args.sparsity, n_img, threads, images=imgs)
+            self.net.replay(self.x_dev)
+            got = self.net.buffers["fc"][:n_img].cpu().numpy()
+            ok = bool(np.array_equal(got, ref_logits))
+            base = {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
+                    "sample": f"{n_img} images through golden_models.cpp (dense conv2d_int8_im2col path), one image per host thread"}
+            return {"ok": ok, "checked": f"INT32 logits of {n_img} images of the timed batch vs oracle/_ref (reference C++ golden)"}, \
+                (base if world == 1 else None)
+        except Exception as e:      # keep the GPU line even if the prebuilt reference library is absent
+            return {"ok": None, "checked": f"unavailable: {e}"}, None
+
+    def extra_line(self):
+        return {"sat_count": int(self.net.sat.item())}
+
+
+class Gemm4096Workload(_Workload):
+    unit = "GEMMs/s"
+
+    def __init__(self, args, rank, world):
+        import torch
+        from resnet_accel_b200 import exporters as E, ops
+        n = 4096
+        rng = np.random.default_rng(0)
+        Wm = rng.integers(-128, 128, (n, n), dtype=np.int8)
+        Wm = (Wm * E.create_sparse_mask((n, n), args.sparsity, block_size=14, seed=42).astype(np.int8)).astype(np.int8)
+        self.A = rng.integers(-128, 128, (n, n), dtype=np.int8)
+        self.bsr = E.build_bsr_14x14_int8_direct(torch.from_numpy(Wm).cuda(), device=True)
+        self.plan = ops.BsrPlan(self.bsr["indptr"], self.bsr["indices"], self.bsr["data"], n_block_cols=self.bsr["num_block_cols"])
+        self.x = torch.from_numpy(self.A).cuda()
+        self.out = torch.empty((n, self.plan.n_out_padded), dtype=torch.int32, device="cuda")
+        self.x_host = torch.from_numpy(self.A).pin_memory()
+        self.out_host = torch.empty((n, self.plan.n_out_padded), dtype=torch.int32).pin_memory()
+        self.x_stage = torch.empty_like(self.x)
+        self.units_per_step, self.launches_per_step = 1, 1
+        self.h2d_bytes, self.d2h_bytes = n * n, n * self.plan.n_out_padded * 4
+        nb = self.plan.num_blocks
+        self.work = {"bytes": n * n + nb * 196 + 4 * (self.plan.n_block_rows + 1) + 4 * nb + n * self.plan.n_out_padded * 4,
+                     "ops": 2 * n * nb * 196, "dense": 2 * n * n * n}
+        self.e2e_api = "BsrPlan.gemm on a staged copy of the pinned host activations; INT32 result copied back to pinned host"
+        self.kernel_note = "gemm_ws_kernel<2, 0>: dense-equivalent CTA-pair GEMM, INT32 output"
+        self.config_extra = {"output": "int32 [4096, 4102]"}
+        self.args = args
+
+    def step(self):
+        self.plan.gemm(self.x, "i32", out=self.out)
+
+    def e2e(self, K):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            self.x_stage.copy_(self.x_host, non_blocking=True)
+            self.plan.gemm(self.x_stage, "i32", out=self.out)
+            self.out_host.copy_(self.out, non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def kernel_table(self, flush):
+        import torch
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); self.step(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return [{"name": "gemm_ws_kernel", "us": float(np.median(ts)), "bytes": self.work["bytes"], "useful_ops": self.work["ops"],
+                 "dense_ops": self.work["dense"]}]
+
+    def check_and_cpu_baseline(self, rank, world):
+        if rank != 0 or self.args.no_cpu_baseline:
+            return None, None
+        from oracle import c_oracle
+        import torch
+        rows = np.sort(np.random.default_rng(1).choice(4096, 64, replace=False))
+        rp, ci, blk = (self.bsr[k].cpu().numpy() for k in ("indptr", "indices", "data"))
+        t0 = time.perf_counter()
+        ref = c_oracle.bsr_gemm_i32(self.A[rows], rp, ci, blk)
+        dt = time.perf_counter() - t0
+        self.step()
+        ok = bool(np.array_equal(self.out[torch.from_numpy(rows).cuda()].cpu().numpy(), ref))
+        base = {"value": (64 / 4096.0) / dt, "unit": self.unit, "cores": 1, "kind": "port",
+                "sample": "64 of 4096 activation rows through oracle/c (gemm_bsr_int8_golden restated in C), scaled linearly"}
+        return {"ok": ok, "checked": "64 sampled output rows vs oracle/c"}, (base if world == 1 else None)
+
+
+class MnistWorkload(_Workload):
+    def __init__(self, args, rank, world):
+        import torch
+        from resnet_accel_b200.mnist import MnistCnnInt8
+        self.args = args
+        self.w = dict(np.load(os.path.join(ROOT, "tests", "golden", "mnist_int8.npz")))
+        self.imgs = np.concatenate([self.w["inputs_u8"], np.random.default_rng(64).integers(0, 256, (32, 28, 28), dtype=np.uint8)], 0)
+        self.net = MnistCnnInt8(self.w, batch=64, fc1_sparsity=args.sparsity / 100.0)
+        self.scales = self.net.calibrate(self.imgs)
+        self.net.build()
+        self.net.run(self.imgs)
+        self.host_in = torch.from_numpy(self.imgs).pin_memory()
+        self.host_out = torch.empty((64, 10), dtype=torch.float32).pin_memory()
+        self.units_per_step, self.launches_per_step = 64, 6
+        self.h2d_bytes, self.d2h_bytes = 64 * 28 * 28, 64 * 10 * 4
+        self.e2e_api = "MnistCnnInt8.run(pinned host uint8 images) -> logits copied to pinned host"
+        self.kernel_note = "bsr_tc / bsr_tcp kernels (conv1, conv2, fc1, fc2) + maxpool; launch-latency-bound at batch 64"
+        self.config_extra = {"graph": "one CUDA graph per step"}
+
+    def step(self):
+        self.net.graph.replay()
+
+    def e2e(self, K):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            y = self.net.run(self.host_in.cuda(non_blocking=True))
+            self.host_out.copy_(y, non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def kernel_table(self, flush):
+        import torch
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); self.step(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        wk = self.net.work()
+        return [{"name": "mnist_cnn_graph (6 launches)", "us": float(np.median(ts)), "bytes": wk["bytes"], "useful_ops": wk["ops"],
+                 "dense_ops": wk["ops"]}]
+
+    def check_and_cpu_baseline(self, rank, world):
+        if rank != 0 or self.args.no_cpu_baseline:
+            return None, None
+        from oracle import bsr_oracle as O
+        fc1 = O.mnist_prune_fc1(self.w["fc1_weight_int8"], self.args.sparsity / 100.0) if self.args.sparsity > 0 else \
+            O.build_bsr_14x14_int8_direct(self.w["fc1_weight_int8"])
+        t0 = time.perf_counter()
+        ref = O.mnist_cnn_int8_forward(self.imgs, self.w, self.scales, fc1)
+        dt = time.perf_counter() - t0
+        got = self.net.run(self.imgs).cpu().numpy()
+        ok = bool(np.array_equal(got, ref["logits"]))
+        base = {"value": 64 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "the 64-image batch through the NumPy restatement of the golden chain"}
+        return {"ok": ok, "checked": "de-quantised logits of the 64-image batch vs the oracle chain"}, (base if world == 1 else None)
+
+
+class ResNet50ShardedWorkload(_Workload):
+    def __init__(self, args, rank, world):
+        import torch
+        from resnet_accel_b200 import layers as L
+        self.args, self.rank, self.world = args, rank, world
+        B = args.batch
+        self.net = L.ShardedFcNetwork(L.resnet50_specs(), args.sparsity, B)
+        gen = torch.Generator(device="cuda").manual_seed(77 + rank)
+        self.x = L.ops.alloc_padded((B, 3, 224, 224))
+        self.x.copy_(torch.randint(-128, 128, (B, 3, 224, 224), dtype=torch.int8, device="cuda", generator=gen))
+        self.x_host = self.x.cpu().pin_memory()
+        self.logits_host = torch.empty((world * B, 1000), dtype=torch.int32).pin_memory()
+        self.net.forward(self.x)
         torch.cuda.synchronize()
-        kms += e0.elapsed_time(e1)
-    kms /= reps
-    conv_bytes = sum(l["bytes"] for l in work["layers"] if l["name"] in conv_names)
-    conv_ops = sum(l["ops"] for l in work["layers"] if l["name"] in conv_names)
-    dense_ops = sum(l["dense_ops"] for l in work["layers"] if l["name"] in conv_names)
+        self.graph = torch.cuda.CUDAGraph()            # the trunk (no collective inside) is one graph; the head stays eager
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.net.trunk_forward(self.x)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            self.net.trunk_forward(self.x)
+        self.units_per_step = B
+        self.launches_per_step = self.net.trunk.n_launches + 1
+        self.h2d_bytes, self.d2h_bytes = int(self.x.numel()), world * B * 1000 * 4
+        self.e2e_api = "pinned host images -> trunk graph -> feature all-gather -> sharded FC -> logits all-gather -> pinned host"
+        self.kernel_note = "ResNet-50 trunk (conv_ws 3x3 + gather kernels for the 1x1 layers) + gemm_ws FC shard; see collective_us"
+        self.config_extra = {"graph": "trunk = one CUDA graph; head (2 all-gathers + FC shard) eager on the same stream"}
+        self._coll = None
 
-    if rank == 0:
-        hbm_peak, int8_peak_tops, src = measured_peaks()
-        traffic = measured_traffic()
-        ms_step = ms_total / args.steps
-        value = world * B * args.steps / (ms_total / 1e3)
-        e2e_val = world * B * args.steps / (ms_e2e / 1e3)
-        ach_gbs = conv_bytes / (kms / 1e3) / 1e9
-        ach_tops = conv_ops / (kms / 1e3) / 1e12
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8", "data": "synthetic",
-            "config": {"workload": "resnet18_full_bsr14_int8", "sparsity_pct": args.sparsity, "batch_per_gpu": B,
-                       "image": 224, "block": 14, "parallelism": f"batch-shard x{world} (no collective)",
-                       "l2": "value: flushed between timed steps (256 MiB memset); e2e: per-step working set 1.4 GB >> 126 MB L2",
-                       "graph": "one CUDA graph per step", "e2e_pipeline": "2-deep: H2D of step i+1 overlaps step i"},
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": (traffic or {}).get("conv_fc_dram_bytes_per_step"),
-                         "traffic_source": (traffic or {}).get("source"), "peak_source": src,
-                         "kernel": f"conv_ws_kernel (3x3 layers, downsamples fused) + stem_ws_kernel (conv1 + max-pool) + "
-                                   f"bsr_tcp_kernel (fc): {sum(1 for n in conv_names if n not in net.fused_ds.values())} "
-                                   "launches per step; algorithmic bytes of the reference's layer sequence (unfused) over "
-                                   "the event-timed eager forward",
-                         "useful_tops": ach_tops, "tensor_frac_of_2x_bf16_sustained": ach_tops / int8_peak_tops,
-                         # the weight-stationary kernels contract every 32-channel chunk that holds a stored block:
-                         # the work the tensor pipe does is the dense layer's, of which `useful` is the stored share
-                         "dense_equiv_tops": dense_ops / (kms / 1e3) / 1e12,
-                         "dense_equiv_tensor_frac": dense_ops / (kms / 1e3) / 1e12 / int8_peak_tops,
-                         "kernel_ms_per_step": kms, "algorithmic_bytes_per_step": conv_bytes,
-                         "useful_ops_per_step": conv_ops},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel()) * world,
-                    "d2h_bytes_per_step": int(logits_host.numel() * 4) * world},
-            "gpu_launches": n_launch_step * args.steps,
-            "clocks": clocks,
-            "sat_count": int(net.sat.item()),
-        }
-        # CPU baseline (bounded sample) on rank 0 at N=1 only
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                threads = os.cpu_count() or 1
-                n_img = threads * args.ref_images_per_thread
-                rate, _ = cpu_reference_rate(args.sparsity, n_img, threads)
-                line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
-                                        "sample": f"{n_img} images through golden_models.cpp (dense conv2d_int8_im2col path), one image per host thread"}
-            except Exception as e:  # keep the GPU line even if the prebuilt reference library is absent
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    def step(self):
+        self.graph.replay()
+        self.net.head_forward()
+
+    def e2e(self, K):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            self.x.copy_(self.x_host, non_blocking=True)
+            self.graph.replay()
+            y = self.net.head_forward()
+            self.logits_host.copy_(y, non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def kernel_table(self, flush):
+        import torch
+        from resnet_accel_b200 import parallel
+        work = {l["name"]: l for l in self.net.trunk.work()["layers"]}
+        rows = _time_eager(lambda ev: self.net.trunk.forward(self.x, launch_events=ev), flush)
+        fused = dict(self.net.trunk.fused_ds); fused.update(self.net.trunk.fused_pool)
+        out = []
+        for name, us in rows:
+            parts = [name] + ([fused[name]] if name in fused else [])
+            out.append({"name": "+".join(parts), "us": us, "bytes": sum(work[p]["bytes"] for p in parts),
+                        "useful_ops": sum(work[p]["ops"] for p in parts), "dense_ops": sum(work[p]["dense_ops"] for p in parts)})
+        # the head, piece by piece: feature all-gather, FC shard, logits all-gather
+        def t(fn, n=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / n
+        net = self.net
+        mine = net.features[net.rank * net.batch:(net.rank + 1) * net.batch]
+        us_feat = t(lambda: parallel.gather_rows(mine, net.features, net.group))
+        us_fc = t(lambda: net.fc.local_gemm(net.features, "i32", bias=net.fc_bias))
+        buf = net.fc.local_gemm(net.features, "i32", bias=net.fc_bias)
+        us_log = t(lambda: net.fc.gather(buf))
+        M, K = net.features.shape
+        nb = net.fc.plan.num_blocks if net.fc.plan is not None else 0
+        out.append({"name": "fc (block-row shard)", "us": us_fc, "bytes": M * K + nb * 196 + M * net.fc.wmax * 4,
+                    "useful_ops": 2 * M * nb * 196, "dense_ops": 2 * M * K * net.fc.wmax})
+        self._coll = {"feature_all_gather_us": us_feat, "feature_bytes_total": int(M * K), "logits_all_gather_us": us_log,
+                      "logits_bytes_total": int(net.fc.world * net.fc.wmax * M * 4), "fc_shard_us": us_fc,
+                      "logits_result": "view of the gather buffer (no copy)" if net.fc.even else "one column copy per shard"}
+        return out
+
+    def check_and_cpu_baseline(self, rank, world):
+        """Bit-exactness of the sharded head: the FC of ALL feature rows on one GPU (unsharded plan) vs the gathered logits."""
+        import torch
+        from resnet_accel_b200 import ops
+        b = self.net.fc_bsr
+        full = ops.BsrPlan(b["indptr"], b["indices"], b["data"], n_block_cols=b["num_block_cols"])
+        self.step()
+        want = full.gemm(self.net.features, "i32", n_channels=1000, bias=self.net.fc_bias)
+        got = self.net.fc.result(self.net._buf)
+        ok = bool(torch.equal(got, want))
+        if world > 1:
+            import torch.distributed as dist
+            t_ = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+            ok = bool(t_.item())
+        if rank != 0:
+            return None, None
+        return {"ok": ok, "checked": "gathered logits of every rank vs the unsharded FC of the gathered features (single plan)"}, None
+
+    def extra_line(self):
+        return {"collective": self._coll}
+
+
+def build_workload(args, rank, local_rank, world):
+    return {"resnet18": ResNet18Workload, "gemm4096": Gemm4096Workload, "mnist": MnistWorkload,
+            "resnet50_fc_sharded": ResNet50ShardedWorkload}[args.workload](args, rank, world)
 
 
 def main():
@@ -392,17 +851,23 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--sparsity", type=float, default=70.0)
+    ap.add_argument("--workload", default="resnet18", choices=WORKLOADS)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--sparsity", type=float, default=None)
     ap.add_argument("--ref-images-per-thread", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0)
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = {"resnet18": 256, "resnet50_fc_sharded": 128}.get(args.workload, 64)
+    if args.sparsity is None:
+        args.sparsity = 90.0 if args.workload == "mnist" else 70.0
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -247,11 +247,24 @@ class BsrNetwork:
                 self.buffers.pop(sp.name, None)
         self.n_launches = sum(1 for _ in specs) - len(self.fused_ds) - len(self.fused_pool)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, launch_events: Optional[list] = None) -> torch.Tensor:
+        """Enqueue every layer on the current stream.  ``launch_events``: when a list is passed, one
+        ``(layer name, start event, end event)`` triple per kernel launch is appended (per-kernel timing for the roofline
+        table; the events are recorded on the launching stream)."""
         prev = "input"
         t: Dict[str, torch.Tensor] = {"input": x}
         t.update(self.buffers)
+        pending = None
         for sp in self.specs:
+            if launch_events is not None:
+                if pending is not None:
+                    pending[2].record()
+                    launch_events.append(tuple(pending))
+                    pending = None
+                launched = not (sp.name in self.fused_pool.values() or (sp.kind == "conv" and sp.name in self.fused_ds.values()))
+                if launched:
+                    pending = [sp.name, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+                    pending[1].record()
             if sp.name in self.fused_pool.values():
                 prev = sp.name                          # written by the stem convolution it is fused with
                 continue
@@ -288,6 +301,9 @@ class BsrNetwork:
                 L = self.layers[sp.name]
                 L.plan.gemm(src.reshape(src.shape[0], -1), "i32", n_channels=sp.c_out, bias=L.bias, out=out)
             prev = sp.name
+        if launch_events is not None and pending is not None:
+            pending[2].record()
+            launch_events.append(tuple(pending))
         return self.buffers[self.specs[-1].name]
 
     def capture(self, x: torch.Tensor) -> None:
@@ -416,10 +432,49 @@ class ResNetInference:
                                        group_rows=(8 if sp.kind == "fc" else 0))
         self.net = BsrNetwork(self.specs, 0.0, self.batch, layers=layers, s_input=self.s_in, s_out=self.s_out)
 
+    def load_synthetic(self, sparsity_pct: float = 70.0, bias_range: int = 0, chain_scales: bool = False) -> None:
+        """Random-init weights of the architecture instead of files (the benchmark recipe of SURVEY.md 8d: He weights, the
+        reference's block-mask recipe, per-channel INT8) - there are no checkpoints offline."""
+        self.net = BsrNetwork(self.specs, sparsity_pct, self.batch, bias_range=bias_range, s_input=self.s_in, s_out=self.s_out,
+                              chain_scales=chain_scales)
+
     def _require(self) -> BsrNetwork:
         if self.net is None:
             raise RuntimeError("Weights not loaded")          # AcceleratorError::NOT_READY in the C++ twin
         return self.net
+
+    def run_inference_pipelined(self, host_batches, host_logits) -> None:
+        """The serving loop for HOST buffers: ``host_batches[i]`` (pinned int8 [batch, 3, H, W]) -> ``host_logits[i]`` (pinned
+        int32 [batch, num_classes]) for every i, two batches in flight - the host-to-device copy of batch i+1 runs on a copy
+        stream while batch i computes, the logits go back asynchronously.  Returns when the work is ENQUEUED; synchronise the
+        current stream (or record an event) before reading the logits.  Buffers may repeat (a ring of pinned buffers)."""
+        net = self._require()
+        cur = torch.cuda.current_stream()
+        if net.graph is None:
+            net.capture(host_batches[0].to("cuda"))
+        if getattr(self, "_pipe", None) is None:
+            dev_in = net.static_in
+            self._pipe = {"copy": torch.cuda.Stream(), "stage": [torch.empty_like(dev_in), torch.empty_like(dev_in)],
+                          "staged": [torch.cuda.Event(), torch.cuda.Event()], "consumed": [torch.cuda.Event(), torch.cuda.Event()],
+                          "used": [False, False]}
+        P = self._pipe
+        start = torch.cuda.Event()
+        start.record(cur)
+        P["copy"].wait_event(start)                     # copies of this call start after the work already enqueued
+        out_name = self.specs[-1].name
+        for i, (xb, yb) in enumerate(zip(host_batches, host_logits)):
+            b = i & 1
+            with torch.cuda.stream(P["copy"]):
+                if P["used"][b]:
+                    P["copy"].wait_event(P["consumed"][b])          # the staging buffer was read by its previous batch
+                P["stage"][b].copy_(xb, non_blocking=True)
+                P["staged"][b].record(P["copy"])
+            cur.wait_event(P["staged"][b])
+            net.static_in.copy_(P["stage"][b], non_blocking=True)
+            P["consumed"][b].record(cur)
+            P["used"][b] = True
+            net.graph.replay()
+            yb.copy_(net.buffers[out_name], non_blocking=True)
 
     def run_inference(self, images: torch.Tensor) -> torch.Tensor:
         """int8 [batch, 3, H, W] -> INT32 logits [batch, num_classes] (the FC accumulators, as the reference keeps them)."""
