@@ -76,6 +76,10 @@ typedef struct accel_epilogue {
   float res_scale_out;
   unsigned long long* sat_count; /* device counter += #values clipped by the int8 requant; may be NULL */
   int32_t* chan_absmax;      /* device [n_channels], atomicMax of |acc| per channel; may be NULL */
+  int32_t acc_bound;         /* optional promise by the caller: |accumulator + bias| <= acc_bound for EVERY possible int8 input
+                                (128 * the largest row L1 norm of the INT8 weights + the largest |bias|).  Below 2^22 the
+                                weight-stationary kernels then run their conversion-free epilogue (same results bit for bit);
+                                0 = unknown, the general epilogue. */
 } accel_epilogue;
 
 /* Convolution geometry: input int8 NCHW, weights viewed [Cout, Cin*k*k] with K index
@@ -98,7 +102,8 @@ ACCEL_API int accel_device_check(void);
  * accumulators complete, epilogue done, CTA exit).  The buffer must hold 8 int64 per CTA of the largest launch. */
 ACCEL_API void accel_debug_set_timeline(long long* dev_buffer);
 /* Developer aid: event counters of this process.  which = 0: launches of the weight-stationary convolution kernels,
- * 1: launches of the dense-equivalent GEMM kernel (gemm_ws_kernel). */
+ * 1: launches of the dense-equivalent GEMM kernel (gemm_ws_kernel), 2: conv launches that ran the conversion-free epilogue
+ * (accel_epilogue.acc_bound). */
 ACCEL_API long long accel_debug_counter(int which);
 
 /* --- weight plan: replaces AccelDriver.load_sparse_weights (sw/host/accel.py:177-236) and

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaccel_b200.so")
+LIB_PATH = os.environ.get("ACCEL_B200_LIB") or os.path.join(_HERE, "libaccel_b200.so")      # override: developer builds
 
 # status codes (accel_status; mirrors AcceleratorError::Code, accelerator_driver.hpp:337-345)
 OK, INIT_FAILED, TIMEOUT, DMA_ERROR, ILLEGAL_COMMAND, INVALID_CONFIG, MEMORY_ERROR, NOT_READY = 0, -1, -2, -3, -4, -5, -6, -7
@@ -35,7 +35,7 @@ class OutLayout(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("flags", C.c_int32), ("n_channels", C.c_int32), ("chan_scale", C.c_void_p), ("bias", C.c_void_p),
                 ("residual", C.c_void_p), ("res_scale_main", C.c_float), ("res_scale_res", C.c_float),
-                ("res_scale_out", C.c_float), ("sat_count", C.c_void_p), ("chan_absmax", C.c_void_p)]
+                ("res_scale_out", C.c_float), ("sat_count", C.c_void_p), ("chan_absmax", C.c_void_p), ("acc_bound", C.c_int32)]
 
 
 class ConvGeom(C.Structure):

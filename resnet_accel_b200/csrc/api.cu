@@ -72,9 +72,11 @@ bool g_ws_s2_narrow = std::getenv("ACCEL_WS_S2_NARROW") != nullptr;   // develop
 bool g_no_pdl = std::getenv("ACCEL_NO_PDL") != nullptr;            // developer switch: plain stream-ordered launches
 bool g_no_twin = std::getenv("ACCEL_NO_TWIN") != nullptr;          // developer switch: one image per tile even for 7-pixel rows
 bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
+bool g_no_fast_epi = std::getenv("ACCEL_NO_FAST_EPI") != nullptr;  // developer switch: conversion instructions in every epilogue
 bool g_no_gemm_ws = std::getenv("ACCEL_NO_GEMM_WS") != nullptr;    // developer switch: GEMMs stay on the gather kernels
 int g_gemm_ws_cg = std::getenv("ACCEL_GEMM_WS_CG") ? std::atoi(std::getenv("ACCEL_GEMM_WS_CG")) : 2;   // 1: no CTA pairs
 int g_gemm_ws_stages = std::getenv("ACCEL_GEMM_WS_STAGES") ? std::atoi(std::getenv("ACCEL_GEMM_WS_STAGES")) : 0;
+long long g_ws_fast_launches = 0;    // accel_debug_counter(2): conv_ws launches that took the conversion-free epilogue
 long long g_gw_launches = 0;         // accel_debug_counter(1)
 // cudaFuncSetAttribute is per device: one flag and one status per device ordinal
 std::once_flag g_attr_once_dev[kMaxDevices];
@@ -101,30 +103,41 @@ cudaError_t launch_overlapped(void (*kfn)(Params), unsigned grid, unsigned block
 }
 
 using WsKernelFn = void (*)(accel::WsLaunch);
+// conv_ws_kernel<mode, residual mode, saturation counting, conversion-free epilogue>.  The conversion-free epilogue is only
+// instantiated for residual mode 4 (integer add): A/B on one box, batch 256 - residual layers 81 -> 78 us (layer1), but the
+// layers without a residual lose 2-3 us to its extra FP instructions (their XU pipe was not the limiter)
 template <int MODE, int RES>
-WsKernelFn ws_kernel_pick(bool sat) {
-  return sat ? static_cast<WsKernelFn>(accel::conv_ws_kernel<MODE, RES, true>) : static_cast<WsKernelFn>(accel::conv_ws_kernel<MODE, RES, false>);
+WsKernelFn ws_kernel_pick(bool sat, bool fast) {
+  if constexpr (RES == 4) {
+    if (fast)
+      return sat ? static_cast<WsKernelFn>(accel::conv_ws_kernel<MODE, RES, true, true>)
+                 : static_cast<WsKernelFn>(accel::conv_ws_kernel<MODE, RES, false, true>);
+  }
+  return sat ? static_cast<WsKernelFn>(accel::conv_ws_kernel<MODE, RES, true, false>)
+             : static_cast<WsKernelFn>(accel::conv_ws_kernel<MODE, RES, false, false>);
 }
-WsKernelFn ws_kernel_ptr(int mode, int resmode, bool sat) {
-  if (mode == accel::kWsModeS2) return resmode == 0 ? ws_kernel_pick<accel::kWsModeS2, 0>(sat) : nullptr;
+WsKernelFn ws_kernel_ptr(int mode, int resmode, bool sat, bool fast) {
+  if (mode == accel::kWsModeS2) return resmode == 0 ? ws_kernel_pick<accel::kWsModeS2, 0>(sat, fast) : nullptr;
   if (mode == accel::kWsModeTwin) {
     switch (resmode) {
-      case 0: return ws_kernel_pick<accel::kWsModeTwin, 0>(sat);
-      case 1: return ws_kernel_pick<accel::kWsModeTwin, 1>(sat);
-      case 2: return ws_kernel_pick<accel::kWsModeTwin, 2>(sat);
-      case 3: return ws_kernel_pick<accel::kWsModeTwin, 3>(sat);
-      default: return ws_kernel_pick<accel::kWsModeTwin, 4>(sat);
+      case 0: return ws_kernel_pick<accel::kWsModeTwin, 0>(sat, fast);
+      case 1: return ws_kernel_pick<accel::kWsModeTwin, 1>(sat, fast);
+      case 2: return ws_kernel_pick<accel::kWsModeTwin, 2>(sat, fast);
+      case 3: return ws_kernel_pick<accel::kWsModeTwin, 3>(sat, fast);
+      default: return ws_kernel_pick<accel::kWsModeTwin, 4>(sat, fast);
     }
   }
   switch (resmode) {
-    case 0: return ws_kernel_pick<accel::kWsModeS1, 0>(sat);
-    case 1: return ws_kernel_pick<accel::kWsModeS1, 1>(sat);
-    case 2: return ws_kernel_pick<accel::kWsModeS1, 2>(sat);
-    case 3: return ws_kernel_pick<accel::kWsModeS1, 3>(sat);
-    default: return ws_kernel_pick<accel::kWsModeS1, 4>(sat);
+    case 0: return ws_kernel_pick<accel::kWsModeS1, 0>(sat, fast);
+    case 1: return ws_kernel_pick<accel::kWsModeS1, 1>(sat, fast);
+    case 2: return ws_kernel_pick<accel::kWsModeS1, 2>(sat, fast);
+    case 3: return ws_kernel_pick<accel::kWsModeS1, 3>(sat, fast);
+    default: return ws_kernel_pick<accel::kWsModeS1, 4>(sat, fast);
   }
 }
-const void* ws_kernel_fn(int mode, int resmode, bool sat) { return reinterpret_cast<const void*>(ws_kernel_ptr(mode, resmode, sat)); }
+const void* ws_kernel_fn(int mode, int resmode, bool sat, bool fast) {
+  return reinterpret_cast<const void*>(ws_kernel_ptr(mode, resmode, sat, fast));
+}
 
 using GwKernelFn = void (*)(accel::GwLaunch);
 GwKernelFn gw_kernel_ptr(int cg, int outk) {
@@ -151,8 +164,8 @@ void set_kernel_attrs() {
   }
   for (int m = 0; m < 3; ++m)
     for (int r = 0; r < 5; ++r)
-      for (int t = 0; t < 2; ++t)
-        if (const void* f = ws_kernel_fn(m, r, t != 0))
+      for (int t = 0; t < 4; ++t)
+        if (const void* f = ws_kernel_fn(m, r, (t & 1) != 0, (t & 2) != 0))
           if (g_attr_err == cudaSuccess) g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWs);
   if (g_attr_err == cudaSuccess)
     g_attr_err = cudaFuncSetAttribute(reinterpret_cast<const void*>(accel::stem_ws_kernel),
@@ -504,6 +517,7 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   p.image_stride = lay->image_stride;
   std::memcpy(p.masks, W.masks, sizeof(p.masks));
   p.dbg = g_dbg_flags;
+  p.timeline = g_timeline;
   p.dual = (W.c_out <= 64 && stride == 1) ? 1 : 0;
   if (plan_ds) {
     p.wblob2 = plan_ds->ws.blob;
@@ -518,12 +532,15 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   const int smem = fixed + p.a_slots * p.a_stage_bytes;
   const int resmode = !epi->residual ? 0 : (p.res_fast == 3 ? 4 : (p.res_fast == 2 ? 3 : (p.res_fast == 1 ? 1 : 2)));
   const int mode = stride == 2 ? accel::kWsModeS2 : (p.twin ? accel::kWsModeTwin : accel::kWsModeS1);
-  WsKernelFn kfn = ws_kernel_ptr(mode, resmode, epi->sat_count != nullptr);
+  // conversion-free epilogue: the caller promised |accumulator + bias| < 2^22 (both launches of a fused stride-2 pair must)
+  const bool fast = !g_no_fast_epi && epi->acc_bound > 0 && epi->acc_bound < (1 << 22) && resmode == 4 && !plan_ds;
+  WsKernelFn kfn = ws_kernel_ptr(mode, resmode, epi->sat_count != nullptr, fast);
   if (!kfn) return kWsNotApplicable;
   cudaError_t e = launch_overlapped(kfn, static_cast<unsigned>(per_group * p.n_groups), accel::kWsThreads, smem, st, L);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_ws_kernel launch");
   ++g_ws_launches;
+  g_ws_fast_launches += fast ? 1 : 0;
   return ACCEL_OK;
 }
 
@@ -605,9 +622,12 @@ void accel_debug_set_timeline(long long* dev_buffer) {
   g_timeline = dev_buffer;
   const char* f = std::getenv("ACCEL_DBG_FLAGS");
   g_dbg_flags = f ? std::atoi(f) : 0;
+  g_no_fast_epi = std::getenv("ACCEL_NO_FAST_EPI") != nullptr;
 }
 
-long long accel_debug_counter(int which) { return which == 0 ? g_ws_launches : (which == 1 ? g_gw_launches : -1); }
+long long accel_debug_counter(int which) {
+  return which == 0 ? g_ws_launches : which == 1 ? g_gw_launches : which == 2 ? g_ws_fast_launches : -1;
+}
 
 int accel_device_check(void) {
   int dev = 0;

@@ -74,6 +74,7 @@ struct WsParams {
   int32_t x_store_end;         // pixels of a row that are stored (W rounded up to 16)
   int64_t image_stride;        // c_out * chan_stride
   int32_t dbg;                 // developer aid: bit 0 = epilogue does no work, bit 1 = issuer issues no MMAs
+  long long* timeline;         // developer aid: 16 clock64 stamps per CTA when non-null (accel_debug_set_timeline)
   uint16_t masks[kWsMaxGroups * kWsMaxChunks];
   // stride-2 mode (3x3 / stride 2 / pad 1, optionally fused with the 1x1 / stride 2 convolution that reads the same input:
   // the ResNet downsample).  Rows: the loader stages 2R+1 input rows and the B window of tap kh takes every second one.
@@ -181,42 +182,86 @@ __device__ __forceinline__ uint32_t relu4_s8(uint32_t x, uint32_t relu_mask) {
   asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(sign) : "r"(x));
   return x & ~(sign & relu_mask);
 }
-template <int RESMODE, bool SAT>
-__device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)[16], const uint32_t (&u)[16], int bias, float sf,
-                                          int relu_lo, int out_lo, const uint4& rbytes, int& amin, int& amax) {
+struct WsEpiConst {        // per-thread (= per-channel) constants of the epilogue
+  int bias, relu_lo, out_lo, lo_c, hi_c;
+  float sf;
+  // FAST path (see ws_epi16): bias + 0x4B400000, clamp bounds that implement relu_int32 + int8 saturation in the float
+  // domain, and the thresholds beyond which a value counts as clipped
+  int bias_m;
+  float lo_f, hi_f, trip_lo, trip_hi;
+};
+// relu_int32 followed by the requant equals a clamp of the requantised value - on the side the sign of the factor picks
+constexpr float kWsMagic = 12582912.0f;        // 1.5 * 2^23: float(kWsMagic + n) has n in its low mantissa bits for |n| < 2^22
+__device__ __forceinline__ void ws_fast_consts(WsEpiConst& k, bool relu) {
+  k.bias_m = k.bias + 0x4B400000;
+  k.lo_f = -128.f; k.hi_f = 127.f; k.trip_lo = -128.5f; k.trip_hi = 127.5f;
+  if (relu) {
+    if (k.sf > 0.f) { k.lo_f = 0.f; k.trip_lo = -INFINITY; }            // acc < 0 -> 0: the negative side never clips
+    else if (k.sf < 0.f) { k.hi_f = 0.f; k.trip_hi = INFINITY; }        // acc < 0 <=> product > 0 -> 0
+    else { k.lo_f = k.hi_f = 0.f; k.trip_lo = -INFINITY; k.trip_hi = INFINITY; }
+  }
+}
+
+// FAST (chosen on the host, accel_epilogue::acc_bound): no conversion instructions at all.  ncu on the layer1 kernels showed
+// the XU pipe (I2F / F2I run there, 16 lanes per clock and SM) 75 % busy - the epilogue, not the tensor pipe, bounded them.
+// With |accumulator + bias| < 2^22 guaranteed by the host (128 * the largest row L1 norm of the INT8 weights + the largest
+// |bias|), float(acc) is the integer add  bits = z + u + (bias + 0x4B400000)  followed by an exact  - 1.5 * 2^23;  relu_int32
+// and the int8 saturation become one clamp in the float domain (requant is monotone in the accumulator; the clamp bounds
+// depend on the sign of the channel's factor), and round-to-nearest-even + float -> int is  + 1.5 * 2^23  again, whose low
+// byte is the int8.  Same results bit for bit (the multiply by sf is the same single float32 multiply).
+template <int RESMODE, bool SAT, bool FAST>
+__device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)[16], const uint32_t (&u)[16], const WsEpiConst& k,
+                                          const uint4& rbytes, int& amin, int& amax, float& fmn, float& fmx) {
   uint32_t packed[4];
   const uint32_t rw[4] = {rbytes.x, rbytes.y, rbytes.z, rbytes.w};
-  const uint32_t relu_mask = out_lo == 0 ? 0xFFFFFFFFu : 0u;        // out_lo is 0 (relu_int8) or -128 (none)
+  const uint32_t relu_mask = k.out_lo == 0 ? 0xFFFFFFFFu : 0u;        // out_lo is 0 (relu_int8) or -128 (none)
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
     uint32_t q[4];
+    if constexpr (FAST) {
+      static_assert(RESMODE == 0 || RESMODE == 4, "the conversion-free epilogue covers no residual / the integer residual add");
+      float f[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int e = 4 * w + b;
-      const int acc = max(static_cast<int>(z[e] + u[e]) + bias, relu_lo);
-      if constexpr (SAT) {
-        amax = max(amax, acc);
-        amin = min(amin, acc);
+      for (int b = 0; b < 4; ++b) {
+        const int e = 4 * w + b;
+        const float t = __int_as_float(static_cast<int>(z[e] + u[e]) + k.bias_m);
+        f[b] = __fmul_rn(__fadd_rn(t, -kWsMagic), k.sf);
       }
-      const float f = __fmul_rn(__int2float_rn(acc), sf);
-      q[b] = cvt_sat_s8_raw(f);
-      if constexpr (RESMODE != 0 && RESMODE != 4) {
-        const float rf = b == 0 ? i2f_s8_byte<0>(rw[w]) : b == 1 ? i2f_s8_byte<1>(rw[w]) : b == 2 ? i2f_s8_byte<2>(rw[w])
-                                                                                                     : i2f_s8_byte<3>(rw[w]);
-        const float a = __fmul_rn(i2f_s8_byte<0>(q[b]), p.epi.res_scale_main);
-        const float r = __fmul_rn(rf, p.epi.res_scale_res);
-        const float sm = __fadd_rn(a, r);
-        float d;
-        if constexpr (RESMODE == 3) {      // the multiply alone already rounds to the reference's int8 for every pair
-          d = __fmul_rn(sm, p.res_rcp);
-        } else if constexpr (RESMODE == 1) {      // exact for every (int8, int8) pair: verified on the host
-          const float q0 = __fmul_rn(sm, p.res_rcp);
-          const float er = __fmaf_rn(-q0, p.epi.res_scale_out, sm);
-          d = __fmaf_rn(er, p.res_rcp, q0);
-        } else {
-          d = __fdiv_rn(sm, p.epi.res_scale_out);
+      if constexpr (SAT) {
+        fmx = fmaxf(fmaxf(fmx, f[0]), fmaxf(f[1], fmaxf(f[2], f[3])));
+        fmn = fminf(fminf(fmn, f[0]), fminf(f[1], fminf(f[2], f[3])));
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) q[b] = __float_as_uint(__fadd_rn(fminf(fmaxf(f[b], k.lo_f), k.hi_f), kWsMagic));
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int e = 4 * w + b;
+        const int acc = max(static_cast<int>(z[e] + u[e]) + k.bias, k.relu_lo);
+        if constexpr (SAT) {
+          amax = max(amax, acc);
+          amin = min(amin, acc);
         }
-        q[b] = cvt_sat_s8_raw(d);
+        const float f = __fmul_rn(__int2float_rn(acc), k.sf);
+        q[b] = cvt_sat_s8_raw(f);
+        if constexpr (RESMODE != 0 && RESMODE != 4) {
+          const float rf = b == 0 ? i2f_s8_byte<0>(rw[w]) : b == 1 ? i2f_s8_byte<1>(rw[w]) : b == 2 ? i2f_s8_byte<2>(rw[w])
+                                                                                                       : i2f_s8_byte<3>(rw[w]);
+          const float a = __fmul_rn(i2f_s8_byte<0>(q[b]), p.epi.res_scale_main);
+          const float r = __fmul_rn(rf, p.epi.res_scale_res);
+          const float sm = __fadd_rn(a, r);
+          float d;
+          if constexpr (RESMODE == 3) {      // the multiply alone already rounds to the reference's int8 for every pair
+            d = __fmul_rn(sm, p.res_rcp);
+          } else if constexpr (RESMODE == 1) {      // exact for every (int8, int8) pair: verified on the host
+            const float q0 = __fmul_rn(sm, p.res_rcp);
+            const float er = __fmaf_rn(-q0, p.epi.res_scale_out, sm);
+            d = __fmaf_rn(er, p.res_rcp, q0);
+          } else {
+            d = __fdiv_rn(sm, p.epi.res_scale_out);
+          }
+          q[b] = cvt_sat_s8_raw(d);
+        }
       }
     }
     uint32_t pk = pack4_b0(q[0], q[1], q[2], q[3]);
@@ -248,20 +293,19 @@ struct WsChunk {           // one 16-pixel chunk of this thread's channel
   int64_t off;             // element offset of the chunk in the output / residual tensor
 };
 __device__ __forceinline__ void ws_chunk_load(const WsParams& p, uint32_t acc, const WsChunk& c, uint32_t (&z)[16], uint32_t (&u)[16]) {
+  if (p.dbg & 256) return;      // developer aid: no TMEM loads (stage isolation)
   tmem_ld16(acc + c.p0, z);
   tmem_ld16(acc + p.u_off + 1 + c.p0, u);
 }
-struct WsEpiConst {        // per-thread (= per-channel) constants of the epilogue
-  int bias, relu_lo, out_lo, lo_c, hi_c;
-  float sf;
-};
-template <int RESMODE, bool SAT>
+template <int RESMODE, bool SAT, bool FAST>
 __device__ __forceinline__ void ws_chunk_finish(const WsParams& p, const WsChunk& c, const uint32_t (&z)[16], const uint32_t (&u)[16],
                                                 const uint4& rb, const WsEpiConst& k, uint32_t& sat) {
   int amin = INT_MAX, amax = INT_MIN;
-  uint4 o = ws_epi16<RESMODE, SAT>(p, z, u, k.bias, k.sf, k.relu_lo, k.out_lo, rb, amin, amax);
+  float fmn = 0.f, fmx = 0.f;
+  uint4 o = ws_epi16<RESMODE, SAT, FAST>(p, z, u, k, rb, amin, amax, fmn, fmx);
   if constexpr (SAT) {
-    if (c.lane_ok && (amax > k.hi_c || amin < k.lo_c)) sat += ws_sat_recount(z, u, k.bias, k.sf, k.relu_lo, c.n_valid);
+    const bool trip = FAST ? (fmx >= k.trip_hi || fmn < k.trip_lo) : (amax > k.hi_c || amin < k.lo_c);
+    if (c.lane_ok && trip) sat += ws_sat_recount(z, u, k.bias, k.sf, k.relu_lo, c.n_valid);
   }
   if (c.n_valid < 16) {      // pixels beyond the image width are stored as zeros (the row padding stays zero)
     uint32_t ow[4] = {o.x, o.y, o.z, o.w};
@@ -272,7 +316,7 @@ __device__ __forceinline__ void ws_chunk_finish(const WsParams& p, const WsChunk
     }
     o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
-  if (c.lane_ok) stg128(p.out + c.off, o);
+  if (c.lane_ok && !(p.dbg & 512)) stg128(p.out + c.off, o);
 }
 
 // this warp's k-th chunk of a tile: chunk pairs alternate between the two warp sets (32 contiguous bytes per thread)
@@ -304,11 +348,11 @@ __device__ __forceinline__ void ws_epi_prefetch(const WsParams& p, const WsEpiGe
     rpre[k] = make_uint4(0u, 0u, 0u, 0u);
     if constexpr (RESMODE != 0) {
       WsChunk c;
-      if (ws_chunk_at(p, g, k, c) && c.lane_ok) rpre[k] = ldg128(p.epi.residual + c.off);
+      if (ws_chunk_at(p, g, k, c) && c.lane_ok && !(p.dbg & 512)) rpre[k] = ldg128(p.epi.residual + c.off);
     }
   }
 }
-template <int RESMODE, bool SAT>
+template <int RESMODE, bool SAT, bool FAST>
 __device__ __forceinline__ void ws_epi_tile(const WsParams& p, uint32_t acc, const WsEpiGeom& g, const WsEpiConst& kc,
                                             const uint4 (&rpre)[kWsMaxMyChunks], uint32_t& sat) {
   uint32_t za[16], ua[16], zb[16], ub[16];
@@ -321,12 +365,12 @@ __device__ __forceinline__ void ws_epi_tile(const WsParams& p, uint32_t acc, con
     tmem_ld_wait();
     has_b = ws_chunk_at(p, g, k + 1, cb);
     if (has_b) ws_chunk_load(p, acc, cb, zb, ub);
-    if (ca.live) ws_chunk_finish<RESMODE, SAT>(p, ca, za, ua, rpre[k], kc, sat);
+    if (ca.live) ws_chunk_finish<RESMODE, SAT, FAST>(p, ca, za, ua, rpre[k], kc, sat);
     if (!has_b) break;
     tmem_ld_wait();
     has_a = k + 2 < kWsMaxMyChunks && ws_chunk_at(p, g, k + 2, ca);
     if (has_a) ws_chunk_load(p, acc, ca, za, ua);
-    if (cb.live) ws_chunk_finish<RESMODE, SAT>(p, cb, zb, ub, rpre[k + 1], kc, sat);
+    if (cb.live) ws_chunk_finish<RESMODE, SAT, FAST>(p, cb, zb, ub, rpre[k + 1], kc, sat);
   }
   tmem_ld_wait();
 }
@@ -342,16 +386,23 @@ __device__ __forceinline__ uint2 ldg64(const void* p) {
   return v;
 }
 // ---- stride-2 epilogue: 16 full-resolution pixels -> the 8 even ones -> 8 output bytes
-template <bool SAT>
+template <bool SAT, bool FAST>
 __device__ __forceinline__ uint2 ws_epi8_even(const uint32_t (&z)[16], const uint32_t* u, const WsEpiConst& k, int n_valid, bool lane_ok,
                                               uint32_t& sat) {
   uint32_t q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int acc = max(static_cast<int>(z[2 * e] + (u ? u[2 * e] : 0u)) + k.bias, k.relu_lo);
-    const float f = __fmul_rn(__int2float_rn(acc), k.sf);
-    if constexpr (SAT) sat += (lane_ok && e < n_valid && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
-    q[e] = cvt_sat_s8_raw(f);
+    if constexpr (FAST) {        // conversion-free arithmetic, see ws_epi16
+      const float t = __int_as_float(static_cast<int>(z[2 * e] + (u ? u[2 * e] : 0u)) + k.bias_m);
+      const float f = __fmul_rn(__fadd_rn(t, -kWsMagic), k.sf);
+      if constexpr (SAT) sat += (lane_ok && e < n_valid && (f >= k.trip_hi || f < k.trip_lo)) ? 1u : 0u;
+      q[e] = __float_as_uint(__fadd_rn(fminf(fmaxf(f, k.lo_f), k.hi_f), kWsMagic));
+    } else {
+      const int acc = max(static_cast<int>(z[2 * e] + (u ? u[2 * e] : 0u)) + k.bias, k.relu_lo);
+      const float f = __fmul_rn(__int2float_rn(acc), k.sf);
+      if constexpr (SAT) sat += (lane_ok && e < n_valid && !(f < 127.5f && f >= -128.5f)) ? 1u : 0u;
+      q[e] = cvt_sat_s8_raw(f);
+    }
   }
   // bytes past the row end are stored as zeros (the row padding stays zero)
   const uint32_t relu_mask = k.out_lo == 0 ? 0xFFFFFFFFu : 0u;
@@ -369,7 +420,7 @@ struct WsEpiRole {
   uint64_t* acc_full;
   uint64_t* acc_empty;
 };
-template <int RESMODE, bool SAT>
+template <int RESMODE, bool SAT, bool FAST>
 __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, int lane) {
   uint32_t sat = 0, n = 0;
   for (uint32_t it = r.item0; it < r.n_items; it += r.item_step, ++n) {
@@ -386,7 +437,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRo
     if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_prefetch<RESMODE>(p, eg, rpre);      // residual bytes: before the MMAs are done
     mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
     tc_fence_after();
-    if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_tile<RESMODE, SAT>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, rpre, sat);
+    if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_tile<RESMODE, SAT, FAST>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, rpre, sat);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&r.acc_empty[ab]);
@@ -394,7 +445,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRo
   return sat;
 }
 
-template <int RESMODE, bool SAT>
+template <int RESMODE, bool SAT, bool FAST>
 __device__ __forceinline__ uint32_t ws_epi_loop_twin(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, int lane) {
   uint32_t sat = 0, n = 0;
   const uint64_t keep64 = p.W >= 8 ? ~0ull : ((1ull << (8 * p.W)) - 1ull);
@@ -425,9 +476,11 @@ __device__ __forceinline__ uint32_t ws_epi_loop_twin(const WsParams& p, const Ws
         }
         tmem_ld_wait();
         int amin = INT_MAX, amax = INT_MIN;
-        const uint4 o = ws_epi16<RESMODE, SAT>(p, z, u, kc.bias, kc.sf, kc.relu_lo, kc.out_lo, rb, amin, amax);
+        float fmn = 0.f, fmx = 0.f;
+        const uint4 o = ws_epi16<RESMODE, SAT, FAST>(p, z, u, kc, rb, amin, amax, fmn, fmx);
         if constexpr (SAT) {
-          if (r.ch_ok && (amax > kc.hi_c || amin < kc.lo_c)) {
+          const bool trip = FAST ? (fmx >= kc.trip_hi || fmn < kc.trip_lo) : (amax > kc.hi_c || amin < kc.lo_c);
+          if (r.ch_ok && trip) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const int a = max(static_cast<int>(z[e] + u[e]) + kc.bias, kc.relu_lo);
@@ -447,7 +500,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop_twin(const WsParams& p, const Ws
   return sat;
 }
 
-template <bool SAT>
+template <bool SAT, bool FAST>
 __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, const WsEpiConst& kc2,
                                                    int lane) {
   uint32_t sat = 0, n = 0;
@@ -473,10 +526,10 @@ __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEp
         tmem_ld_wait();
         const int n_valid = max(0, min(8, p.Wo - x0));
         const int64_t off = obase + static_cast<int64_t>(y0 + row) * p.out_pitch + x0;
-        const uint2 o = ws_epi8_even<SAT>(z, u, kc, n_valid, r.ch_ok, sat);
+        const uint2 o = ws_epi8_even<SAT, FAST>(z, u, kc, n_valid, r.ch_ok, sat);
         if (r.ch_ok) stg64(p.out + off, o);
         if (p.has_ds) {
-          const uint2 o2 = ws_epi8_even<SAT>(v, nullptr, kc2, n_valid, r.ch_ok, sat);
+          const uint2 o2 = ws_epi8_even<SAT, FAST>(v, nullptr, kc2, n_valid, r.ch_ok, sat);
           if (r.ch_ok) stg64(p.out2 + off, o2);
         }
       }
@@ -488,11 +541,36 @@ __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEp
   return sat;
 }
 
+// One chunk (32 input channels) of MMAs: nine taps (+ the fused 1x1 / stride 2 tap) from one staged activation tile.
+// FIRST: the first chunk of a tile - the host forces all nine taps on, and the first MMA into Z1 / U / V overwrites.  Later
+// chunks issue the taps of `mask` and always accumulate.  Tap order per kh: kw = 1 into Z1, then the two U taps - with
+// aliasing kw = 0 (U + 2) first (it overwrites; the aliased columns keep Z1's zeros), without (twin tiles) kw = 2 (U + 0).
+struct WsIssue {
+  bool leader;
+  uint32_t a_hi, b_hi, idesc, row16, u_off, v_col;
+};
+template <bool FIRST, bool ALIAS>
+__device__ __forceinline__ void ws_issue_chunk(const WsIssue& I, uint32_t z1, uint32_t wl, uint32_t xl, uint32_t mask, bool ds) {
+  constexpr uint32_t kTap16 = kWsTapBytes >> 4;
+  const uint64_t ah = static_cast<uint64_t>(I.a_hi) << 32, bh = static_cast<uint64_t>(I.b_hi) << 32;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const uint64_t bd = bh | (xl + kh * I.row16);
+    const uint32_t first = (FIRST && kh == 0) ? 0u : 1u;          // accumulate flag of the first Z1 / U MMA of a tile
+    if (I.leader && (FIRST || (mask & (1u << (kh * 3 + 1))))) mma_i8_ss(z1, ah | (wl + (kh * 3 + 1) * kTap16), bd, I.idesc, first);
+    constexpr int kwa = ALIAS ? 0 : 2, kwb = ALIAS ? 2 : 0;       // kwa overwrites on the first chunk
+    const uint32_t ua = z1 + I.u_off + (ALIAS ? 2u : 0u), ub = z1 + I.u_off + (ALIAS ? 0u : 2u);
+    if (I.leader && (FIRST || (mask & (1u << (kh * 3 + kwa))))) mma_i8_ss(ua, ah | (wl + (kh * 3 + kwa) * kTap16), bd, I.idesc, first);
+    if (I.leader && (FIRST || (mask & (1u << (kh * 3 + kwb))))) mma_i8_ss(ub, ah | (wl + (kh * 3 + kwb) * kTap16), bd, I.idesc, 1u);
+    if (kh == 1 && ds && I.leader) mma_i8_ss(z1 + I.v_col, ah | (wl + 9 * kTap16), bd, I.idesc, FIRST ? 0u : 1u);
+  }
+}
+
 // One instantiation per (tile mode, residual mode, saturation counting): every launch runs exactly one epilogue variant, so
 // the others cost it neither registers nor instruction-cache space (measured: the twin paths inside one big kernel slowed
 // the layer1 convolutions from 63 to 84 us).  MODE 0 = stride 1, 1 = stride 2 (+ fused 1x1), 2 = twin tiles.
 constexpr int kWsModeS1 = 0, kWsModeS2 = 1, kWsModeTwin = 2;
-template <int MODE, int RESMODE, bool SAT>
+template <int MODE, int RESMODE, bool SAT, bool FAST>
 __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_constant__ WsLaunch L) {
   constexpr bool TWIN = MODE == kWsModeTwin;
   extern __shared__ uint8_t smem_dyn[];
@@ -525,6 +603,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
 
   // The next kernel on the stream may take over SMs as CTAs of this grid retire (its prologue and resident weight
   // load then overlap our tail); everything here that reads what the previous kernel wrote sits behind griddep_wait().
+  long long* tl = p.timeline ? p.timeline + static_cast<size_t>(blockIdx.x) * 128 : nullptr;
+  if (tl && threadIdx.x == 0) { tl[0] = clock64(); long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); tl[14] = g; }   // 0: CTA entry (14: ns)
   griddep_launch();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWsMaxASlots; ++s) { mbar_init(&a_full[s], kWsLoadThreads); mbar_init(&a_empty[s], 1); }
@@ -541,10 +621,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tl && threadIdx.x == 0) tl[1] = clock64();                       // 1: prologue done (barriers, TMEM)
 
   if (warp < kWsEpiWarps) {
     // =================================================================== epilogue: thread = output channel
-    griddep_wait();          // residuals, the output buffer (still being read) and the counters belong to earlier kernels
+    griddep_wait();
+    if (tl && threadIdx.x == 0) tl[2] = clock64();                     // 2: epilogue past griddepcontrol.wait          // residuals, the output buffer (still being read) and the counters belong to earlier kernels
     const int q = warp & 3, half = warp >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sub = dual ? static_cast<uint32_t>(lane >> 4) : 0u;          // which tile of the pair
@@ -558,7 +640,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     kc.relu_lo = (p.epi.flags & ACCEL_RELU) ? 0 : INT_MIN;
     kc.out_lo = (p.epi.flags & ACCEL_RELU_OUT) ? 0 : -128;
     kc.lo_c = INT_MIN; kc.hi_c = INT_MAX;
-    if (sat_on && ch_ok) ws_sat_bounds(sf, kc.lo_c, kc.hi_c);
+    if (sat_on && ch_ok && !FAST) ws_sat_bounds(sf, kc.lo_c, kc.hi_c);
+    ws_fast_consts(kc, (p.epi.flags & ACCEL_RELU) != 0);
     WsEpiRole er;
     er.item0 = item0; er.item_step = item_step; er.n_items = n_items; er.n_tiles = n_tiles; er.dual = dual; er.sub = sub;
     er.tmem_acc = tmem_base + lane_base;
@@ -566,105 +649,106 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     er.ch_ok = ch_ok;
     er.warp_has_ch = dual ? (q * 16 < p.c_out) : (static_cast<int>(g) * kWsCo + q * 32 < p.c_out);
     er.acc_full = acc_full; er.acc_empty = acc_empty;
-    uint32_t sat;
-    if constexpr (MODE == kWsModeS2) {
+    uint32_t sat = 0;
+    if (p.dbg & 16) {
+      // developer aid: no accumulator hand-over at all (the issuer skips it too)
+    } else if constexpr (MODE == kWsModeS2) {
       WsEpiConst kc2 = kc;
       if (p.has_ds) {
         kc2.sf = ch_ok ? p.epi2.chan_scale[co] : 0.f;
         kc2.bias = (ch_ok && p.epi2.bias) ? p.epi2.bias[co] : 0;
         kc2.relu_lo = (p.epi2.flags & ACCEL_RELU) ? 0 : INT_MIN;
         kc2.out_lo = (p.epi2.flags & ACCEL_RELU_OUT) ? 0 : -128;
+        ws_fast_consts(kc2, (p.epi2.flags & ACCEL_RELU) != 0);
       }
-      sat = ws_epi_loop_s2<SAT>(p, er, kc, kc2, lane);
+      sat = ws_epi_loop_s2<SAT, FAST>(p, er, kc, kc2, lane);
     } else if constexpr (TWIN) {
-      sat = ws_epi_loop_twin<RESMODE, SAT>(p, er, kc, lane);
+      sat = ws_epi_loop_twin<RESMODE, SAT, FAST>(p, er, kc, lane);
     } else {
-      sat = ws_epi_loop<RESMODE, SAT>(p, er, kc, lane);
+      sat = ws_epi_loop<RESMODE, SAT, FAST>(p, er, kc, lane);
     }
+    if (tl && threadIdx.x == 0) tl[3] = clock64();                     // 3: epilogue loop done (warp 0)
     if (sat_on) {
       const uint32_t wsum = __reduce_add_sync(0xffffffffu, sat);
       if (lane == 0 && wsum) atomicAdd(p.epi.sat_count, static_cast<unsigned long long>(wsum));
     }
   } else if (warp == kWsWarpIssue) {
     // =================================================================== MMA issuer
+    // One elected thread.  Measured (tools/ws_timeline.py, stage isolation): the first version of this loop kept the
+    // overwrite / accumulate state of Z1, U and V in variables and tested the tap masks in every chunk; every descriptor,
+    // accumulator address and predicate then travelled through R2UR and the ~170 instructions per chunk of nine 64-cycle
+    // MMAs took ~660 cycles - more than the 576 cycles the tensor pipe needs, i.e. every convolution was bound by this one
+    // thread.  Now the first chunk of a tile (all taps, fixed overwrite pattern) and the later chunks (tap masks, always
+    // accumulate) are separate code and the descriptors are base + slot * stride adds, which ptxas keeps in the uniform
+    // datapath (UTCIMMA reads uniform registers).
     if (elect_one()) {
+      const bool leader = true;
       const uint32_t idesc = idesc_i8_bmn(dual ? 64u : static_cast<uint32_t>(kWsCo), static_cast<uint32_t>(p.N));
       const uint64_t adesc0 = smem_desc_kmajor(0, 128, 256);
       const uint64_t bdesc0 = smem_desc_any(0, p.b_lbo, p.b_sbo, p.b_layout);
-      const uint32_t a_hi = static_cast<uint32_t>(adesc0 >> 32), b_hi = static_cast<uint32_t>(bdesc0 >> 32);
-      const uint32_t b_lo0 = static_cast<uint32_t>(bdesc0);
-      const uint32_t a_lo0 = static_cast<uint32_t>(adesc0);
-      const uint32_t row16 = p.row_stride >> 4;
-      const uint32_t u_off = static_cast<uint32_t>(p.u_off);
-      // the first U-type MMA of a tile overwrites: with aliasing it must be the shifted one (kw = 0 at U + 2, so that the
-      // aliased columns keep Z1's zeros), without aliasing the unshifted one (kw = 2 at U + 0, which covers U's first columns)
+      WsIssue I;
+      I.leader = leader;
+      I.a_hi = static_cast<uint32_t>(adesc0 >> 32); I.b_hi = static_cast<uint32_t>(bdesc0 >> 32);
+      I.idesc = idesc; I.row16 = p.row_stride >> 4; I.u_off = static_cast<uint32_t>(p.u_off); I.v_col = static_cast<uint32_t>(p.v_col);
+      // shared memory ends below 256 KB: (address >> 4) fits the 14-bit field, so slot addressing is a plain add
+      const uint32_t wl0 = static_cast<uint32_t>(adesc0) + (w_addr >> 4), w_step = static_cast<uint32_t>(p.w_chunk_bytes) >> 4;
+      const uint32_t xl0 = static_cast<uint32_t>(bdesc0) + (a_addr >> 4), a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+      const uint32_t a_slots = static_cast<uint32_t>(p.a_slots), w_slots = static_cast<uint32_t>(p.w_slots);
+      const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (p.dbg & 2) != 0, fence = (p.dbg & 8) != 0;
+      const bool one_set = MODE == kWsModeS2 && p.acc_single;
       constexpr bool alias = !TWIN;
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0;
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0, st_i = 0;
       for (uint32_t it = item0; it < n_items; it += item_step, ++n) {
-        const bool one_set = MODE == kWsModeS2 && p.acc_single;
         const uint32_t ab = one_set ? 0u : (n & 1u);
-        mbar_wait(&acc_empty[ab], (one_set ? (n & 1u) : ((n >> 1) & 1u)) ^ 1u);
+        if (!(p.dbg & 16)) mbar_wait(&acc_empty[ab], (one_set ? (n & 1u) : ((n >> 1) & 1u)) ^ 1u);
         tc_fence_after();
         const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
         for (uint32_t sub = 0; sub < n_sub; ++sub) {
           const uint32_t z1 = tmem_base + ab * kWsAccCols + ((sub * 16u) << 16);
-          uint32_t z_on = 0u, u_on = 0u, v_on = 0u;     // first MMA into Z1 / U / V overwrites, the rest accumulate
           for (uint32_t j = 0; j < n_chunks; ++j) {
             uint32_t wslot;
-            if (p.w_resident) {
+            if (w_resident) {
               wslot = j;
               if (n == 0 && sub == 0) mbar_wait(&w_full[j], 0u);
             } else {
               wslot = ws;
               mbar_wait(&w_full[ws], wph);
             }
+            if (tl && leader && n == 0 && sub == 0 && j == 0) tl[4] = clock64();   // 4: issuer has the first weights
             mbar_wait(&a_full[as], aph);
-            // the stage was written by cp.async (generic proxy) and is read by tcgen05.mma (async proxy): one proxy fence per
-            // stage on the consumer side, by the single issuing thread, after the barrier has made the writes visible to it
-            fence_proxy_async_smem();
+            if (tl && st_i >= 32 && st_i < 64) tl[64 + (st_i - 32)] = clock64();      // issuer saw stage st_i
+            ++st_i;
+            if (tl && leader && n == 0 && sub == 0 && j == 0) tl[5] = clock64();   // 5: issuer has the first activation stage
+            // The stage was written by cp.async (generic proxy) and is read by tcgen05.mma (async proxy).  A proxy fence per
+            // stage on the consumer side was measured: +2 to +3 us on every convolution (layer1 58.2 -> 60.3,
+            // layer2 34.6 -> 36.9, layer3 33.4 -> 36.0 us).  Default off, as in CUTLASS's sm100 cp.async mainloop where
+            // cp.async.mbarrier.arrive + the consumer's mbarrier wait is the whole hand-over; ACCEL_DBG_FLAGS bit 3 turns
+            // it on (tests/test_gpu_conv_ws.py soaks both settings against the gather kernels).
+            if (fence && leader) fence_proxy_async_smem();
             tc_fence_after();
-            const uint32_t mask = (p.dbg & 2) ? 0u : p.masks[g * kWsMaxChunks + j];
-            const uint32_t wl = a_lo0 | (((w_addr + wslot * static_cast<uint32_t>(p.w_chunk_bytes)) >> 4) & 0x3FFFu);
-            const uint32_t xl = b_lo0 | (((a_addr + as * static_cast<uint32_t>(p.a_stage_bytes)) >> 4) & 0x3FFFu);
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (xl + kh * row16);
-              // order kw = 1, 0, 2 (chunk 0 issues all nine taps): Z1's first MMA zeroes [0, N), the first kw = 0 MMA
-              // zeroes U + 2 + [0, N), and kw = 2 accumulates into U + [0, N) whose first two columns alias Z1's tail
-              if (mask & (1u << (kh * 3 + 1))) {
-                mma_i8_ss(z1, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 1) * (kWsTapBytes >> 4)), bd, idesc, z_on);
-                z_on = 1u;
-              }
-              if (alias) {       // kw = 0 (U + 2) first: it overwrites, the aliased columns keep Z1's zeros
-                if (mask & (1u << (kh * 3 + 0))) {
-                  mma_i8_ss(z1 + u_off + 2, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 0) * (kWsTapBytes >> 4)), bd, idesc, u_on);
-                  u_on = 1u;
-                }
-                if (mask & (1u << (kh * 3 + 2)))
-                  mma_i8_ss(z1 + u_off, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 2) * (kWsTapBytes >> 4)), bd, idesc, 1u);
-              } else {           // kw = 2 (U + 0) first: it covers U's first columns
-                if (mask & (1u << (kh * 3 + 2))) {
-                  mma_i8_ss(z1 + u_off, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 2) * (kWsTapBytes >> 4)), bd, idesc, u_on);
-                  u_on = 1u;
-                }
-                if (mask & (1u << (kh * 3 + 0)))
-                  mma_i8_ss(z1 + u_off + 2, (static_cast<uint64_t>(a_hi) << 32) | (wl + (kh * 3 + 0) * (kWsTapBytes >> 4)), bd, idesc, 1u);
-              }
-              if (kh == 1 && p.has_ds && (p.masks2[g * kWsMaxChunks + j] & 1u) && !(p.dbg & 2)) {   // fused 1x1 / stride 2
-                mma_i8_ss(z1 + static_cast<uint32_t>(p.v_col), (static_cast<uint64_t>(a_hi) << 32) | (wl + 9 * (kWsTapBytes >> 4)), bd, idesc, v_on);
-                v_on = 1u;
+            const uint32_t wl = wl0 + wslot * w_step, xl = xl0 + as * a_step;
+            if (!no_mma) {
+              if (j == 0) {
+                ws_issue_chunk<true, alias>(I, z1, wl, xl, 0x1FFu, has_ds);
+              } else {
+                const uint32_t mask = p.masks[g * kWsMaxChunks + j];
+                const bool ds = has_ds && (p.masks2[g * kWsMaxChunks + j] & 1u);
+                ws_issue_chunk<false, alias>(I, z1, wl, xl, mask, ds);
               }
             }
-            mma_commit(&a_empty[as]);
-            if (++as == static_cast<uint32_t>(p.a_slots)) { as = 0; aph ^= 1u; }
-            if (!p.w_resident) {
-              mma_commit(&w_empty[ws]);
-              if (++ws == static_cast<uint32_t>(p.w_slots)) { ws = 0; wph ^= 1u; }
+            if (p.dbg & 128) mbar_arrive(&a_empty[as]); else
+            if (leader) mma_commit(&a_empty[as]);
+            if (++as == a_slots) { as = 0; aph ^= 1u; }
+            if (!w_resident) {
+              if (leader) mma_commit(&w_empty[ws]);
+              if (++ws == w_slots) { ws = 0; wph ^= 1u; }
             }
           }
         }
-        mma_commit(&acc_full[ab]);
+        if (leader && !(p.dbg & 16)) mma_commit(&acc_full[ab]);
+        if (tl && leader && n == 0) tl[6] = clock64();                  // 6: first item issued
       }
+      if (tl && leader) { tl[7] = clock64(); tl[12] = n; }              // 7: issuer done, 12: items
     }
     __syncwarp();
     tc_fence_before();
@@ -675,7 +759,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     // about one row per 4 cycles (measured: 685 cycles per 8 KB stage); 16-byte LDGSTS copies issued by two warps are
     // several times faster and zero-fill the padding just the same.
     griddep_wait();          // the activations are the previous kernel's output
-    const int lt = static_cast<int>(threadIdx.x) - kWsWarpLoad * 32;           // 0..191
+    const int lt = static_cast<int>(threadIdx.x) - kWsWarpLoad * 32;           // 0..63
+    if (tl && lt == 0) tl[8] = clock64();                              // 8: loaders past griddepcontrol.wait
     const int x16s = p.P >> 4, rows = p.rows_in;
     const int n_ops = kWsCk * rows * (p.twin ? 2 : x16s);
     constexpr int kOps = TWIN ? kWsLoadOps + 1 : kWsLoadOps;      // twin tiles: 576 eight-byte copies per stage
@@ -697,7 +782,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       nbytes[k] = o < n_ops ? (TWIN ? min(8, p.W) : max(0, min(16, p.W - xq * 16))) : -1;
       if (TWIN) yrow[k] |= xq << 16;                                // image B of the pair may not exist (odd batch)
     }
-    uint32_t as = 0, aph = 0;
+    uint32_t as = 0, aph = 0, st_l = 0;
     const int64_t chunk_stride = static_cast<int64_t>(kWsCk) * p.H * p.in_pitch;
     for (uint32_t it = item0; it < n_items; it += item_step) {
       const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
@@ -721,6 +806,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
         const int8_t* src0 = p.x + static_cast<int64_t>(img) * p.C * p.H * p.in_pitch;
         for (uint32_t j = 0; j < n_chunks; ++j) {
           mbar_wait(&a_empty[as], aph ^ 1u);
+          if (tl && lt == 0 && st_l >= 32 && st_l < 64) tl[16 + (st_l - 32)] = clock64();     // loader got the slot of stage st_l
           const uint32_t dst0 = a_addr + as * static_cast<uint32_t>(p.a_stage_bytes);
 #pragma unroll
           for (int k = 0; k < kOps; ++k)
@@ -733,10 +819,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
           // fence.proxy.async per stage after its mbarrier wait (a fence in each of the 64 loader threads measured ~1000
           // cycles per stage in round 1; the single consumer-side fence is what the PTX memory model asks for)
           cp_async_mbar_arrive(&a_full[as]);
+          if (tl && lt == 0 && st_l >= 32 && st_l < 64) tl[96 + (st_l - 32)] = clock64();     // loader issued stage st_l
+          ++st_l;
           if (++as == static_cast<uint32_t>(p.a_slots)) { as = 0; aph ^= 1u; }
         }
       }
     }
+    if (tl && lt == 0) tl[9] = clock64();                              // 9: loaders done
   }
   else {
     // =================================================================== weight loader (bulk copies)
@@ -773,10 +862,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (tl && threadIdx.x == 0) tl[10] = clock64();                      // 10: all roles done
   if (warp == kWsWarpIssue) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, 512);
   }
+  if (tl && threadIdx.x == 0) { tl[11] = clock64(); long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); tl[13] = g; }
 }
 
 }  // namespace accel

@@ -116,6 +116,10 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
 __device__ __forceinline__ void cp_async16_zfill_s(uint32_t smem_dst, const void* gmem_src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
+// same through L1 (.ca): a warp's 16-byte pieces of one 128-byte line travel to L2 as one request
+__device__ __forceinline__ void cp_async16_zfill_ca_s(uint32_t smem_dst, const void* gmem_src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async8_zfill_s(uint32_t smem_dst, const void* gmem_src, int src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
@@ -134,6 +138,12 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s_s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {   // shared-window address
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }

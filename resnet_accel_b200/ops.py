@@ -109,6 +109,8 @@ class BsrPlan:
         self._ws_conv = {}                      # (c_in, c_out, ksize) -> workspace tensor (None: no such path)
         self._ws_gemm = None                    # dense-equivalent GEMM layout: None = not built yet, False = no such path
         self.use_gemm_ws = True                 # False: GEMMs of this plan stay on the gather kernel (csrc/bsr_tcp.cuh)
+        self._row_l1_max = None                 # largest sum of |w| over one output channel's stored weights (lazy)
+        self._bound_cache = {}                  # bias identity -> acc_bound
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -162,6 +164,36 @@ class BsrPlan:
     def n_out_padded(self) -> int:
         return self.n_block_rows * BLOCK
 
+    def acc_bound(self, bias=None, may_sync: bool = True) -> int:
+        """``accel_epilogue.acc_bound``: no int8 input can drive ``|accumulator + bias|`` past
+        ``128 * max_channel(sum |w|) + max |bias|``.  Below 2**22 the weight-stationary kernels run their conversion-free
+        epilogue (csrc/conv_ws.cuh, ws_epi16).  One device reduction per plan and per bias tensor, cached; with ``may_sync``
+        False (stream capture) an uncached bound is reported as 0 = unknown."""
+        if self._row_l1_max is None:
+            if not may_sync:
+                return 0
+            if self.col_idx.size == 0:
+                self._row_l1_max = 0
+            else:
+                l1 = self._blocks.view(-1, BLOCK, BLOCK).to(torch.int32).abs().sum(2)            # [nnz, 14]
+                owner = torch.repeat_interleave(torch.arange(self.n_block_rows, device=self.device),
+                                                torch.as_tensor(np.diff(self.row_ptr), device=self.device))
+                rows = torch.zeros((self.n_block_rows, BLOCK), dtype=torch.int64, device=self.device).index_add_(0, owner, l1)
+                self._row_l1_max = int(rows.max().item())
+        if bias is None:
+            bmax = 0
+        elif _is_cuda(bias):
+            key = (bias.data_ptr(), bias.numel(), bias._version)
+            if key not in self._bound_cache:
+                if not may_sync:
+                    return 0
+                self._bound_cache[key] = int(bias.to(torch.int64).abs().max().item()) if bias.numel() else 0
+            bmax = self._bound_cache[key]
+        else:
+            b = np.asarray(_host(bias), dtype=np.int64)
+            bmax = int(np.abs(b).max()) if b.size else 0
+        return min(128 * self._row_l1_max + bmax, 2**31 - 1)
+
     # ------------------------------------------------------------------------------------
     def _epilogue(self, out_kind: str, n_channels: int, chan_scale, bias, relu: bool, residual, res_scales,
                   sat_count, chan_absmax, relu_out: bool = False) -> Tuple[Epilogue, list]:
@@ -188,6 +220,8 @@ class BsrPlan:
             e.sat_count = sat_count.data_ptr()
         if chan_absmax is not None:
             e.chan_absmax = chan_absmax.data_ptr()
+        if out_kind == "i8":                                 # cached after the first call with this bias tensor
+            e.acc_bound = self.acc_bound(bias, may_sync=not torch.cuda.is_current_stream_capturing())
         return e, keep
 
     def gemm(self, x: torch.Tensor, out_kind: str = "i32", n_channels: Optional[int] = None, chan_scale=None,

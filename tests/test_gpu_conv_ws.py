@@ -11,20 +11,23 @@ from oracle import c_oracle
 pytestmark = pytest.mark.gpu
 
 
-def _case(B, Cin, H, W, Cout, density, seed, residual=True, relu=False, relu_out=True, bias_on=True):
+def _case(B, Cin, H, W, Cout, density, seed, residual=True, relu=False, relu_out=True, bias_on=True,
+          res_scales=(0.05, 0.02, 0.04), wmax=128, sf_fn=None, x_fill=None, bias_mag=1000, expect_fast=None):
     import torch
     from resnet_accel_b200 import _lib, ops
     from resnet_accel_b200.ops import BsrPlan
     rng = np.random.default_rng(seed)
     K = Cin * 9
-    Wm = rng.integers(-128, 128, (Cout, K), dtype=np.int8)
+    Wm = rng.integers(-wmax, wmax, (Cout, K)).astype(np.int8)
     nbr, nbc = -(-Cout // 14), -(-K // 14)
     keep = rng.random((nbr, nbc)) < density
     Wm = Wm * np.repeat(np.repeat(keep, 14, 0), 14, 1)[:Cout, :K].astype(np.int8)
     bsr = O.build_bsr_14x14_int8_direct(Wm)
     x = rng.integers(-128, 128, (B, Cin, H, W), dtype=np.int8)
-    bias = rng.integers(-1000, 1000, Cout, dtype=np.int32) if bias_on else None
-    sf = rng.uniform(1e-4, 2e-3, Cout).astype(np.float32)
+    if x_fill is not None:
+        x[B // 2:] = x_fill                  # half of the images constant: the accumulators reach their bound
+    bias = rng.integers(-bias_mag, bias_mag, Cout, dtype=np.int32) if bias_on else None
+    sf = rng.uniform(1e-4, 2e-3, Cout).astype(np.float32) if sf_fn is None else sf_fn(rng, Cout).astype(np.float32)
     res = rng.integers(-128, 128, (B, Cout, H, W), dtype=np.int8) if residual else None
     plan = BsrPlan(bsr["indptr"], bsr["indices"], bsr["data"], n_block_cols=bsr["num_block_cols"])
     xd = ops.alloc_padded(x.shape)
@@ -39,13 +42,15 @@ def _case(B, Cin, H, W, Cout, density, seed, residual=True, relu=False, relu_out
         rd.copy_(torch.from_numpy(res).cuda())
     out = ops.alloc_padded((B, Cout, H, W))
     cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
-    before = _lib.lib().accel_debug_counter(0)
+    before, before_fast = _lib.lib().accel_debug_counter(0), _lib.lib().accel_debug_counter(2)
     plan.conv(xd, 3, 1, 1, Cout, out_kind="i8", chan_scale=sf, bias=bias, relu=relu, residual=rd,
-              res_scales=(0.05, 0.02, 0.04), sat_count=cnt, relu_out=relu_out, out=out)
+              res_scales=res_scales, sat_count=cnt, relu_out=relu_out, out=out)
     torch.cuda.synchronize()
     assert _lib.lib().accel_debug_counter(0) == before + 1, "the weight-stationary kernel did not run"
+    if expect_fast is not None:
+        assert _lib.lib().accel_debug_counter(2) - before_fast == int(expect_fast), "wrong epilogue variant"
     ref, sat = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, 3, 1, 1, bias=bias,
-                                       relu=relu, sf=sf, residual=res, res_scales=(0.05, 0.02, 0.04))
+                                       relu=relu, sf=sf, residual=res, res_scales=res_scales)
     if relu_out:
         ref = np.maximum(ref, 0)
     got = out.cpu().numpy()
@@ -82,6 +87,40 @@ def test_conv_ws_epilogue_variants():
     _case(2, 64, 14, 14, 64, 0.3, seed=1, residual=False, relu=True, relu_out=False)
     _case(2, 64, 14, 14, 64, 0.3, seed=2, residual=False, relu=False, relu_out=False, bias_on=False)
     _case(2, 64, 14, 14, 64, 0.3, seed=3, residual=True, relu=True, relu_out=False)
+
+
+def _signed_sf(rng, n):
+    """Factors of both signs, a zero, and large ones that drive most outputs into saturation."""
+    sf = rng.uniform(1e-5, 3e-3, n) * rng.choice([-1.0, 1.0], n)
+    sf[::7] = 0.0
+    sf[3::11] *= 40.0
+    return sf
+
+
+@pytest.mark.parametrize("residual,relu,relu_out", [(False, True, False), (False, False, False), (True, True, True),
+                                                     (True, False, False), (False, False, True)])
+def test_conv_ws_conversion_free_epilogue(residual, relu, relu_out, monkeypatch):
+    """accel_epilogue.acc_bound < 2^22 selects the epilogue without int<->float conversions (ws_epi16<FAST>): same bytes and
+    the same saturation count as the oracle, for factors of both signs / zero / saturating, accumulators AT the bound
+    (constant +-extreme images against weights of one magnitude), and the general epilogue gives the same answer."""
+    from resnet_accel_b200 import _lib
+    same = (0.03, 0.03, 0.03)                   # matched scales: the integer residual add (residual mode 4)
+    fast = residual                             # only the residual kernels carry the conversion-free variant (api.cu)
+    for seed, fill in ((1, None), (2, -128), (3, 127)):
+        _case(4, 32, 14, 14, 64, 1.0, seed=seed, residual=residual, relu=relu, relu_out=relu_out, res_scales=same, wmax=100,
+              sf_fn=_signed_sf, x_fill=fill, bias_mag=200000, expect_fast=fast)
+    _case(2, 64, 56, 56, 64, 0.3, seed=4, residual=residual, relu=relu, relu_out=relu_out, res_scales=same, sf_fn=_signed_sf,
+          expect_fast=fast)
+    # a bound of 2^22 or more (dense 128-magnitude weights, K = 576) keeps the general epilogue
+    _case(2, 64, 14, 14, 64, 1.0, seed=5, residual=residual, relu=relu, relu_out=relu_out, res_scales=same, expect_fast=False)
+    monkeypatch.setenv("ACCEL_NO_FAST_EPI", "1")
+    _lib.lib().accel_debug_set_timeline(None)
+    try:
+        _case(4, 32, 14, 14, 64, 1.0, seed=2, residual=residual, relu=relu, relu_out=relu_out, res_scales=same, wmax=100,
+              sf_fn=_signed_sf, x_fill=-128, bias_mag=200000, expect_fast=False)
+    finally:
+        monkeypatch.delenv("ACCEL_NO_FAST_EPI")
+        _lib.lib().accel_debug_set_timeline(None)
 
 
 def test_conv_ws_many_tiles_persistent():
