@@ -72,6 +72,7 @@ bool g_ws_s2_narrow = std::getenv("ACCEL_WS_S2_NARROW") != nullptr;   // develop
 bool g_no_pdl = std::getenv("ACCEL_NO_PDL") != nullptr;            // developer switch: plain stream-ordered launches
 bool g_no_twin = std::getenv("ACCEL_NO_TWIN") != nullptr;          // developer switch: one image per tile even for 7-pixel rows
 bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
+int g_stem_rows = std::getenv("ACCEL_STEM_ROWS") ? std::atoi(std::getenv("ACCEL_STEM_ROWS")) : 0;      // developer switch: pooled rows per stem item
 bool g_no_fast_epi = std::getenv("ACCEL_NO_FAST_EPI") != nullptr;  // developer switch: conversion instructions in every epilogue
 bool g_no_gemm_ws = std::getenv("ACCEL_NO_GEMM_WS") != nullptr;    // developer switch: GEMMs stay on the gather kernels
 int g_gemm_ws_cg = std::getenv("ACCEL_GEMM_WS_CG") ? std::atoi(std::getenv("ACCEL_GEMM_WS_CG")) : 2;   // 1: no CTA pairs
@@ -623,6 +624,7 @@ void accel_debug_set_timeline(long long* dev_buffer) {
   const char* f = std::getenv("ACCEL_DBG_FLAGS");
   g_dbg_flags = f ? std::atoi(f) : 0;
   g_no_fast_epi = std::getenv("ACCEL_NO_FAST_EPI") != nullptr;
+  g_stem_rows = std::getenv("ACCEL_STEM_ROWS") ? std::atoi(std::getenv("ACCEL_STEM_ROWS")) : 0;
 }
 
 long long accel_debug_counter(int which) {
@@ -1065,16 +1067,33 @@ int accel_conv_pool_bsr_i8(const accel_plan* plan, const int8_t* input_nchw, con
   p.Hc = Hc; p.Wc = Wc; p.Hp = Hp; p.Wp = Wp;
   p.c_out = W.c_out; p.in_pitch = static_cast<int32_t>(in_pitch); p.out_pitch = out_pitch;
   p.n_pairs = (g->batch + 1) / 2;
-  const int64_t n_items = static_cast<int64_t>(p.n_pairs) * Hp;
+  // an item is a strip of G pooled rows of an image pair = 2G + 1 conv rows (2G for the first strip); pick the G with the
+  // fewest conv rows on the busiest SM
+  int best_g = 1;
+  int64_t best_cost = INT64_MAX;
+  for (int G = 1; G <= Hp; ++G) {
+    const int64_t strips = (Hp + G - 1) / G, items = static_cast<int64_t>(p.n_pairs) * strips;
+    const int64_t cost = ((items + sm_count() - 1) / sm_count()) * (2 * G + 1);
+    if (cost < best_cost) { best_cost = cost; best_g = G; }
+  }
+  if (g_stem_rows > 0) best_g = g_stem_rows < Hp ? g_stem_rows : Hp;
+  p.G = best_g;
+  p.n_strips = (Hp + best_g - 1) / best_g;
+  const int64_t n_items = static_cast<int64_t>(p.n_pairs) * p.n_strips;
   if (n_items > INT_MAX) return fail(ACCEL_INVALID_CONFIG, "too many rows");
   p.n_items = static_cast<int32_t>(n_items);
-  p.d_hp = accel::make_fastdiv(static_cast<uint32_t>(Hp));
-  p.x = input_nchw; p.wblob = W.blob; p.epi = *epi; p.out = out;
+  p.d_strips = accel::make_fastdiv(static_cast<uint32_t>(p.n_strips));
+  p.wblob = W.blob; p.epi = *epi; p.out = out;
   p.chan_stride = Hp * out_pitch;
   p.image_stride = static_cast<int64_t>(W.c_out) * p.chan_stride;
+  p.x = input_nchw;
+  p.timeline = g_timeline;
+  p.raw_slot_bytes = (g->c_in * 7 * (16 + g->w + 32) + 127) & ~127;
+  if (g->c_in * 7 * (g->w / 32 + 1) > 6 * 32 || accel::kStSmemFixed + accel::kStRawSlots * p.raw_slot_bytes > kSmemWs)
+    return fail(ACCEL_ILLEGAL_COMMAND, "fused convolution + max-pool: input rows too long for the raw ring");
   p.dbg = g_dbg_flags;
   const int ctas = n_items < sm_count() ? static_cast<int>(n_items) : sm_count();
-  const int smem = 1024 + accel::kStSmemBar + accel::kStWBytes + accel::kStSlots * accel::kStStageBytes;
+  const int smem = accel::kStSmemFixed + accel::kStRawSlots * p.raw_slot_bytes;
   cudaError_t e = launch_overlapped(accel::stem_ws_kernel, static_cast<unsigned>(ctas), accel::kStThreads, smem,
                                     static_cast<cudaStream_t>(stream), p);
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -165,16 +165,6 @@ __global__ void repack_blocks_kernel(const int8_t* __restrict__ blocks, uint8_t*
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-  return v;
-}
 __device__ __forceinline__ int8_t cvt_sat_s8(float f) {   // round-half-even + saturate in one instruction
   int v;
   asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(v) : "f"(f));

@@ -55,6 +55,21 @@ def test_stem_fused_vs_oracle(B, Cin, H, W, Cout, density):
     _stem_case(B, Cin, H, W, Cout, density, seed=B + Cin + H + W + Cout)
 
 
+@pytest.mark.parametrize("rows", [1, 2, 3, 5, 100])
+def test_stem_strip_heights(rows, monkeypatch):
+    """An item of the fused kernel is a strip of G pooled rows (chosen on the host for the least work per SM); every strip
+    height gives the same bytes and the same saturation count, including strips that do not divide the pooled height."""
+    from resnet_accel_b200 import _lib
+    monkeypatch.setenv("ACCEL_STEM_ROWS", str(rows))
+    _lib.lib().accel_debug_set_timeline(None)          # re-reads the developer switches
+    try:
+        _stem_case(3, 3, 64, 64, 64, 0.5, seed=21)      # 16 pooled rows, odd batch
+        _stem_case(2, 3, 44, 96, 40, 0.5, seed=22)      # 11 pooled rows
+    finally:
+        monkeypatch.delenv("ACCEL_STEM_ROWS")
+        _lib.lib().accel_debug_set_timeline(None)
+
+
 def test_stem_many_rows_persistent():
     _stem_case(40, 3, 96, 160, 64, 0.3, seed=3)
 

@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out/r2
 O=gpurun_out/r2
-for f in 0 1 2 3; do ACCEL_DBG_FLAGS=$f python tools/stem_probe.py; done 2>&1 | tee $O/stem_iso.txt
-ncu --set full --clock-control none --import-source on -k regex:stem_ws_kernel -s 4 -c 1 -o $O/prof_stem python tools/stem_probe.py > $O/ncu_stem.log 2>&1
-ls -la $O/prof_stem.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:stem_ws_kernel -s 4 -c 1 -f -o $O/prof_stem python tools/stem_probe.py > $O/ncu_stem.log 2>&1
+ls -la $O/prof_stem*.ncu-rep
