@@ -234,14 +234,16 @@ __device__ __forceinline__ uint4 ws_epi16(const WsParams& p, const uint32_t (&z)
 #pragma unroll
       for (int b = 0; b < 4; ++b) q[b] = __float_as_uint(__fadd_rn(fminf(fmaxf(f[b], k.lo_f), k.hi_f), kWsMagic));
     } else {
+      int acc4[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc4[b] = max(static_cast<int>(z[4 * w + b] + u[4 * w + b]) + k.bias, k.relu_lo);
+      if constexpr (SAT) {                   // range of the chunk, two values per three-input min / max
+        amax = __vimax3_s32(__vimax3_s32(amax, acc4[0], acc4[1]), acc4[2], acc4[3]);
+        amin = __vimin3_s32(__vimin3_s32(amin, acc4[0], acc4[1]), acc4[2], acc4[3]);
+      }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const int e = 4 * w + b;
-        const int acc = max(static_cast<int>(z[e] + u[e]) + k.bias, k.relu_lo);
-        if constexpr (SAT) {
-          amax = max(amax, acc);
-          amin = min(amin, acc);
-        }
+        const int acc = acc4[b];
         const float f = __fmul_rn(__int2float_rn(acc), k.sf);
         q[b] = cvt_sat_s8_raw(f);
         if constexpr (RESMODE != 0 && RESMODE != 4) {

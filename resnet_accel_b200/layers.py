@@ -320,6 +320,22 @@ class BsrNetwork:
             self.forward(self.static_in)
         self.graph = g
 
+    def capture_alt(self) -> None:
+        """A second graph of the same network whose first kernel reads ``static_in_alt`` instead of ``static_in`` (every other
+        buffer is shared): a host loop that alternates the two graphs can copy batch i+1 straight into the idle input while
+        batch i computes, with no device-to-device staging copy (``ResNetInference.run_inference_pipelined``)."""
+        if self.graph is None:
+            raise RuntimeError("capture() first")
+        if getattr(self, "graph_alt", None) is not None:
+            return
+        self.static_in_alt = ops.alloc_padded(tuple(self.static_in.shape))
+        self.static_in_alt.copy_(self.static_in)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward(self.static_in_alt)
+        self.graph_alt = g
+
     def replay(self, x: Optional[torch.Tensor] = None) -> torch.Tensor:
         if x is not None:
             self.static_in.copy_(x, non_blocking=True)
@@ -445,36 +461,46 @@ class ResNetInference:
 
     def run_inference_pipelined(self, host_batches, host_logits) -> None:
         """The serving loop for HOST buffers: ``host_batches[i]`` (pinned int8 [batch, 3, H, W]) -> ``host_logits[i]`` (pinned
-        int32 [batch, num_classes]) for every i, two batches in flight - the host-to-device copy of batch i+1 runs on a copy
-        stream while batch i computes, the logits go back asynchronously.  Returns when the work is ENQUEUED; synchronise the
-        current stream (or record an event) before reading the logits.  Buffers may repeat (a ring of pinned buffers)."""
+        int32 [batch, num_classes]) for every i, two batches in flight: two CUDA graphs of the network alternate, each reading
+        its own input buffer, so the host-to-device copy of batch i+1 lands in the idle graph's input on a copy stream while
+        batch i computes (no staging copy on the device), and the logits are read back on a third stream under the next
+        batch's kernels.  Returns when the work is ENQUEUED; synchronise the current stream (or record an event) before
+        reading the logits.  Buffers may repeat (a ring of pinned buffers)."""
         net = self._require()
         cur = torch.cuda.current_stream()
         if net.graph is None:
             net.capture(host_batches[0].to("cuda"))
+        net.capture_alt()
         if getattr(self, "_pipe", None) is None:
-            dev_in = net.static_in
-            self._pipe = {"copy": torch.cuda.Stream(), "stage": [torch.empty_like(dev_in), torch.empty_like(dev_in)],
+            self._pipe = {"copy": torch.cuda.Stream(), "out": torch.cuda.Stream(),
                           "staged": [torch.cuda.Event(), torch.cuda.Event()], "consumed": [torch.cuda.Event(), torch.cuda.Event()],
-                          "used": [False, False]}
+                          "computed": torch.cuda.Event(), "read_back": torch.cuda.Event(), "used": [False, False], "any": False}
         P = self._pipe
+        inputs, graphs = (net.static_in, net.static_in_alt), (net.graph, net.graph_alt)
         start = torch.cuda.Event()
         start.record(cur)
         P["copy"].wait_event(start)                     # copies of this call start after the work already enqueued
-        out_name = self.specs[-1].name
+        logits_dev = net.buffers[self.specs[-1].name]
         for i, (xb, yb) in enumerate(zip(host_batches, host_logits)):
             b = i & 1
             with torch.cuda.stream(P["copy"]):
                 if P["used"][b]:
-                    P["copy"].wait_event(P["consumed"][b])          # the staging buffer was read by its previous batch
-                P["stage"][b].copy_(xb, non_blocking=True)
+                    P["copy"].wait_event(P["consumed"][b])          # the graph that read this input buffer has finished
+                inputs[b].copy_(xb, non_blocking=True)               # pinned host -> the graph's own (padded-row) input
                 P["staged"][b].record(P["copy"])
             cur.wait_event(P["staged"][b])
-            net.static_in.copy_(P["stage"][b], non_blocking=True)
+            if P["any"]:
+                cur.wait_event(P["read_back"])                       # the previous logits have left the (shared) output buffer
+            graphs[b].replay()
             P["consumed"][b].record(cur)
+            P["computed"].record(cur)
             P["used"][b] = True
-            net.graph.replay()
-            yb.copy_(net.buffers[out_name], non_blocking=True)
+            with torch.cuda.stream(P["out"]):                        # the read-back overlaps the next batch's kernels
+                P["out"].wait_event(P["computed"])
+                yb.copy_(logits_dev, non_blocking=True)
+                P["read_back"].record(P["out"])
+            P["any"] = True
+        cur.wait_event(P["read_back"])                  # "synchronise the current stream" covers the last read-back too
 
     def run_inference(self, images: torch.Tensor) -> torch.Tensor:
         """int8 [batch, 3, H, W] -> INT32 logits [batch, num_classes] (the FC accumulators, as the reference keeps them)."""

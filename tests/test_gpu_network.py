@@ -197,3 +197,30 @@ def test_resnet_inference_engine_roundtrip(tmp_path):
     idx, prob = eng.get_top_k(torch.from_numpy(got).cuda(), k=3)
     assert idx.shape == (B, 3) and np.all(prob[:, 0] >= prob[:, 1])
     assert eng.benchmark(3)["images_per_s"] > 0
+
+
+def test_pipelined_serving_loop_matches_single_batches():
+    """run_inference_pipelined (two alternating graphs, copies on side streams) returns, for every host batch, the logits
+    run_inference gives for that batch alone - also when the ring of pinned buffers is shorter than the number of batches in
+    flight allows (each buffer reused every second step) and when the loop is called twice."""
+    import torch
+    from resnet_accel_b200 import layers as L
+    B, n = 4, 5
+    eng = L.ResNetInference(batch=B, image=64, num_classes=50)
+    eng.load_synthetic(70.0, chain_scales=True)
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randint(-128, 128, (B, 3, 64, 64), dtype=torch.int8, generator=g).pin_memory() for _ in range(n)]
+    want = [eng.run_inference(x).cpu().numpy().copy() for x in xs]
+    assert any(not np.array_equal(want[0], w) for w in want[1:])          # the batches really differ
+    for _ in range(2):
+        ys = [torch.zeros((B, 50), dtype=torch.int32).pin_memory() for _ in range(n)]
+        eng.run_inference_pipelined(xs, ys)
+        torch.cuda.current_stream().synchronize()
+        for i in range(n):
+            assert np.array_equal(ys[i].numpy(), want[i]), i
+    # a ring of two pinned buffers, refilled by the host between calls (as bench.py does)
+    ring_x = [xs[0].clone().pin_memory(), xs[1].clone().pin_memory()]
+    ring_y = [torch.zeros((B, 50), dtype=torch.int32).pin_memory() for _ in range(2)]
+    eng.run_inference_pipelined([ring_x[i & 1] for i in range(4)], [ring_y[i & 1] for i in range(4)])
+    torch.cuda.current_stream().synchronize()
+    assert np.array_equal(ring_y[0].numpy(), want[0]) and np.array_equal(ring_y[1].numpy(), want[1])

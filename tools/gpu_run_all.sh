@@ -2,9 +2,7 @@
 # full GPU suite + headline bench (one box)
 mkdir -p gpurun_out/r2
 O=gpurun_out/r2
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench_resnet18.json 2> $O/bench_resnet18.err; echo "resnet18 rc=$?"; tail -2 $O/bench_resnet18.err
 python -c "
 import json;d=json.load(open('$O/bench_resnet18.json'));print(d['value'],d['ms_per_step'],d.get('e2e',{}).get('value'),d.get('bit_exact'))"
-ACCEL_B200_LIB=$PWD/tools/probe/libaccel_head.so timeout 600 python bench.py --steps 20 --warmup 5 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read());print('head lib:',d['value'],d['ms_per_step'])"
