@@ -232,6 +232,12 @@ ACCEL_API int accel_add_residual_i8(const int8_t* main_, const int8_t* res, int8
                           float s_out, accel_stream_t stream);
 /* relu_int8 / relu6_int8 / relu_int32, in place (golden_models.cpp:278-283, :323-330, :298-303).  relu6: upper clamp
  * int8(6.0f / scale), truncated as the reference computes it. */
+/* out[pl][y][x] = in[pl][2y][2x] for `planes` int8 image planes of h x w (rows in_pitch / out_pitch bytes apart): the
+ * pixels a 1x1 / stride 2 / pad 0 convolution reads (conv2d_int8_im2col, golden_models.cpp:883-933, stride handling;
+ * ResNet-50 downsample branches), so that the convolution itself runs as a stride-1 pointwise one.  Output planes are
+ * ceil(h/2) x ceil(w/2); bytes of an output row beyond that are left alone. */
+ACCEL_API int accel_subsample2_i8(const int8_t* in, int64_t planes, int32_t h, int32_t w, int32_t in_pitch, int8_t* out,
+                                  int32_t out_pitch, accel_stream_t stream);
 ACCEL_API int accel_relu_i8(int8_t* data, int64_t n, accel_stream_t stream);
 ACCEL_API int accel_relu6_i8(int8_t* data, int64_t n, float scale, accel_stream_t stream);
 ACCEL_API int accel_relu_i32(int32_t* data, int64_t n, accel_stream_t stream);

@@ -82,6 +82,7 @@ SYMBOLS = {
     "accel_row_absmax_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
     "accel_requant_i32_i8": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I32, _P, _P]),
     "accel_add_residual_i8": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, _P]),
+    "accel_subsample2_i8": (C.c_int, [_P, _I64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "accel_relu_i8": (C.c_int, [_P, _I64, _P]),
     "accel_relu6_i8": (C.c_int, [_P, _I64, _F, _P]),
     "accel_relu_i32": (C.c_int, [_P, _I64, _P]),

@@ -417,8 +417,10 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
                 const accel_out_layout* lay, cudaStream_t st, const accel_plan* plan_ds = nullptr,
                 const accel_epilogue* epi_ds = nullptr, void* out_ds = nullptr) {
   const WsState& W = plan->ws;
-  if (g_no_ws || !W.ready || W.taps != 9 || g->ksize != 3 || (g->stride != 1 && g->stride != 2) || g->pad != 1 || g->batch <= 0)
-    return kWsNotApplicable;
+  // pointwise: 1x1 / stride 1 / pad 0 (one tap, no halo rows, Z1 only)
+  const bool pw = W.ready && W.taps == 1 && g->ksize == 1 && g->stride == 1 && g->pad == 0 && !plan_ds;
+  if (g_no_ws || !W.ready || g->batch <= 0) return kWsNotApplicable;
+  if (!pw && (W.taps != 9 || g->ksize != 3 || (g->stride != 1 && g->stride != 2) || g->pad != 1)) return kWsNotApplicable;
   if (g->c_in != W.c_in || epi->n_channels != W.c_out) return kWsNotApplicable;
   if (!(epi->flags & ACCEL_OUT_I8) || epi->chan_absmax) return kWsNotApplicable;
   const int stride = g->stride;
@@ -426,7 +428,7 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   // stride 2 with streamed weights (Cin > 128): every tile re-reads the filter from L2, so the tile is made as large as
   // TMEM allows (below).  ACCEL_WS_S2_NARROW keeps the 64-pixel tiles (layer4.0 of ResNet-18: 168 us fused, against
   // 125 us on the gather kernels).
-  const bool s2_wide = stride == 2 && W.n_chunks > accel::kWsMaxWSlots && !g_ws_s2_narrow;
+  const bool s2_wide = stride == 2 && W.n_chunks > accel::kWsRing9 && !g_ws_s2_narrow;
   if (plan_ds) {
     const WsState& D = plan_ds->ws;
     if (stride != 2 || !D.ready || D.taps != 1 || D.c_in != W.c_in || D.c_out != W.c_out || !epi_ds || !out_ds) return kWsNotApplicable;
@@ -466,18 +468,20 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   int best_r = 1, best_cost = INT_MAX;
   for (int r = 1; r <= (stride == 2 && !s2_wide ? 64 : 128) / P; ++r) {       // stride 2: N <= 64 (three accumulators per set)
     const int cost = (Ho + r - 1) / r * r;
-    const int copies = accel::kWsCk * (stride == 2 ? 2 * r + 1 : r + 2) * (P >> 4);      // 16-byte loader copies per stage
+    const int copies = accel::kWsCk * (stride == 2 ? 2 * r + 1 : (pw ? r : r + 2)) * (P >> 4);      // 16-byte loader copies per stage
     if (copies > accel::kWsLoadThreads * accel::kWsLoadOps) break;
     if (cost <= best_cost) { best_cost = cost; best_r = r; }
   }
   p.R = best_r; p.N = p.R * P;
   p.stride = stride; p.Ho = Ho; p.Wo = Wo;
 
-  p.rows_in = stride == 2 ? 2 * p.R + 1 : p.R + 2;
+  p.rows_in = stride == 2 ? 2 * p.R + 1 : (pw ? p.R : p.R + 2);
+  p.pw = pw ? 1 : 0; p.ypad = pw ? 0 : 1;
+  p.w_src_stride = pw ? accel::kWsTapBytes : accel::kWsChunkBytes;
   p.has_ds = plan_ds ? 1 : 0;
   p.acc_single = (s2_wide && plan_ds) ? 1 : 0;
   p.v_col = p.acc_single ? 256 : 128;
-  p.w_chunk_bytes = accel::kWsChunkBytes + (plan_ds ? accel::kWsTapBytes : 0);
+  p.w_chunk_bytes = pw ? accel::kWsTapBytes : accel::kWsChunkBytes + (plan_ds ? accel::kWsTapBytes : 0);
   p.n_chunks = W.n_chunks; p.n_groups = W.n_groups; p.c_out = W.c_out;
   p.tiles_per_image = (Ho + p.R - 1) / p.R;
   // 16-pixel rows with <= 7 valid pixels (layer4 of ResNet-18): two images side by side in every staged row
@@ -488,8 +492,10 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   const int64_t n_tiles = static_cast<int64_t>(p.twin ? (g->batch + 1) / 2 : g->batch) * p.tiles_per_image;
   if (n_tiles > INT_MAX) return kWsNotApplicable;
   p.n_tiles = static_cast<int32_t>(n_tiles);
-  p.w_resident = W.n_chunks <= accel::kWsMaxWSlots ? 1 : 0;
-  p.w_slots = p.w_resident ? W.n_chunks : accel::kWsMaxWSlots;
+  // 3x3: 36 KB per chunk - resident up to Cin 128, else a ring of four slots; 1x1: 4 KB per chunk - resident up to Cin 1024
+  const int ring = pw ? 16 : accel::kWsRing9, resident_max = pw ? accel::kWsMaxWSlots : accel::kWsRing9;
+  p.w_resident = W.n_chunks <= resident_max ? 1 : 0;
+  p.w_slots = p.w_resident ? W.n_chunks : ring;
   p.a_box_bytes = accel::kWsCk * p.rows_in * P;
   p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
   const int fixed = 1024 /* alignment slack */ + accel::kWsSmemBar + p.w_slots * p.w_chunk_bytes;
@@ -524,7 +530,10 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
     p.wblob2 = plan_ds->ws.blob;
     p.epi2 = *epi_ds;
     p.out2 = static_cast<int8_t*>(out_ds);
-    std::memcpy(p.masks2, plan_ds->ws.masks, sizeof(p.masks2));
+    if (plan_ds->ws.n_chunks > accel::kWsMaxChunks2 || plan_ds->ws.n_groups > accel::kWsMaxGroups2) return kWsNotApplicable;
+    for (int gi = 0; gi < plan_ds->ws.n_groups; ++gi)
+      for (int j = 0; j < plan_ds->ws.n_chunks; ++j)
+        p.masks2[gi * accel::kWsMaxChunks2 + j] = plan_ds->ws.masks[gi * accel::kWsMaxChunks + j];
   }
   const int n_items = p.dual ? (p.n_tiles + 1) / 2 : p.n_tiles;
   int per_group = sm_count() / p.n_groups;
@@ -1228,6 +1237,25 @@ int accel_requant_i32_i8(const int32_t* acc, int8_t* out, int64_t n_outer, int64
   if (!chan_scale) return fail(ACCEL_INVALID_CONFIG, "chan_scale required");
   accel::requant_i32_i8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       acc, out, n_outer, n_chan, n_inner, chan_scale, bias, relu, sat_count);
+  CU(cudaGetLastError());
+  return ACCEL_OK;
+}
+
+int accel_subsample2_i8(const int8_t* in, int64_t planes, int32_t h, int32_t w, int32_t in_pitch, int8_t* out, int32_t out_pitch,
+                        accel_stream_t stream) {
+  if (planes <= 0 || h <= 0 || w <= 0) return ACCEL_OK;
+  if (!in || !out) return fail(ACCEL_INVALID_CONFIG, "null buffer");
+  const int Ho = (h + 1) / 2, Wo = (w + 1) / 2;
+  if (in_pitch < w || out_pitch < Wo) return fail(ACCEL_INVALID_CONFIG, "row pitch shorter than the row");
+  const int quads = (Wo + 3) / 4;
+  const bool vec = !(in_pitch & 7) && !(out_pitch & 3) && 8 * quads <= in_pitch && !(reinterpret_cast<uintptr_t>(in) & 7) &&
+                   !(reinterpret_cast<uintptr_t>(out) & 3);
+  if (vec)
+    accel::subsample2_i8_vec_kernel<<<grid_for(planes * Ho * quads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, out, planes, in_pitch, h, Ho, Wo, out_pitch);
+  else
+    accel::subsample2_i8_kernel<<<grid_for(planes * Ho * Wo, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, out, planes, in_pitch, h, Ho, Wo, out_pitch);
   CU(cudaGetLastError());
   return ACCEL_OK;
 }

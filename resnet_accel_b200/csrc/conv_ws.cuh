@@ -42,12 +42,14 @@ constexpr int kWsCo = 128;                         // output channels per group 
 constexpr int kWsCk = 32;                          // input channels per chunk (one MMA K)
 constexpr int kWsTapBytes = kWsCo * kWsCk;         // 4096
 constexpr int kWsChunkBytes = 9 * kWsTapBytes;     // 36864
-constexpr int kWsMaxChunks = 16;                   // Cin <= 512
-constexpr int kWsMaxGroups = 8;                    // Cout <= 1024
-constexpr int kWsMaxWSlots = 4;                    // resident: Cin <= 128; else a ring of this many chunk slots
+constexpr int kWsMaxChunks = 64;                   // Cin <= 2048
+constexpr int kWsMaxGroups = 16;                   // Cout <= 2048
+constexpr int kWsMaxChunks2 = 16, kWsMaxGroups2 = 8;      // the fused 1x1 / stride 2 branch (masks2): Cin <= 512, Cout <= 1024
+constexpr int kWsRing9 = 4;                        // 3x3: weights resident when Cin <= 128, else a ring of this many 36 KB chunk slots
+constexpr int kWsMaxWSlots = 32;                   // weight slots (1x1: 4 KB chunks - resident up to Cin 1024, else a ring)
 constexpr int kWsMaxASlots = 16;
 constexpr int kWsAccCols = 256;                    // per accumulator set: Z1 [0, N), U [N-2, 2N)
-constexpr int kWsSmemBar = 1024;                   // barriers + TMEM slot in front of the operand areas
+constexpr int kWsSmemBar = 2048;                   // barriers (132 x 8 bytes) + TMEM slot in front of the operand areas
 
 struct WsParams {
   int32_t C, H, W, B;          // input geometry (output has the same H, W)
@@ -87,7 +89,10 @@ struct WsParams {
   const uint8_t* wblob2;       // [group][chunk][4096]
   accel_epilogue epi2;
   int8_t* out2;
-  uint16_t masks2[kWsMaxGroups * kWsMaxChunks];
+  uint16_t masks2[kWsMaxGroups2 * kWsMaxChunks2];
+  // pointwise mode (1x1 / stride 1 / pad 0: the bottleneck convolutions of ResNet-50): one tap, no halo rows (ypad = 0), Z1
+  // only - the epilogue takes U as zero; the weight blob is [group][chunk][4096] (w_src_stride = 4096)
+  int32_t pw, ypad, w_src_stride;
 };
 struct WsLaunch {
   alignas(64) CUtensorMap tmap;
@@ -295,9 +300,13 @@ struct WsChunk {           // one 16-pixel chunk of this thread's channel
   int64_t off;             // element offset of the chunk in the output / residual tensor
 };
 __device__ __forceinline__ void ws_chunk_load(const WsParams& p, uint32_t acc, const WsChunk& c, uint32_t (&z)[16], uint32_t (&u)[16]) {
-  if (p.dbg & 256) return;      // developer aid: no TMEM loads (stage isolation)
   tmem_ld16(acc + c.p0, z);
-  tmem_ld16(acc + p.u_off + 1 + c.p0, u);
+  if (p.pw) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) u[e] = 0u;
+  } else {
+    tmem_ld16(acc + p.u_off + 1 + c.p0, u);
+  }
 }
 template <int RESMODE, bool SAT, bool FAST>
 __device__ __forceinline__ void ws_chunk_finish(const WsParams& p, const WsChunk& c, const uint32_t (&z)[16], const uint32_t (&u)[16],
@@ -318,7 +327,7 @@ __device__ __forceinline__ void ws_chunk_finish(const WsParams& p, const WsChunk
     }
     o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
-  if (c.lane_ok && !(p.dbg & 512)) stg128(p.out + c.off, o);
+  if (c.lane_ok) stg128(p.out + c.off, o);
 }
 
 // this warp's k-th chunk of a tile: chunk pairs alternate between the two warp sets (32 contiguous bytes per thread)
@@ -350,7 +359,7 @@ __device__ __forceinline__ void ws_epi_prefetch(const WsParams& p, const WsEpiGe
     rpre[k] = make_uint4(0u, 0u, 0u, 0u);
     if constexpr (RESMODE != 0) {
       WsChunk c;
-      if (ws_chunk_at(p, g, k, c) && c.lane_ok && !(p.dbg & 512)) rpre[k] = ldg128(p.epi.residual + c.off);
+      if (ws_chunk_at(p, g, k, c) && c.lane_ok) rpre[k] = ldg128(p.epi.residual + c.off);
     }
   }
 }
@@ -470,7 +479,12 @@ __device__ __forceinline__ uint32_t ws_epi_loop_twin(const WsParams& p, const Ws
         const int64_t off_a = obase + static_cast<int64_t>(y0 + i) * p.out_pitch, off_b = off_a + p.image_stride;
         uint32_t z[16], u[16];
         tmem_ld16(acc + 16 * i, z);
-        tmem_ld16(acc + p.u_off + 1 + 16 * i, u);
+        if (p.pw) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) u[e] = 0u;
+        } else {
+          tmem_ld16(acc + p.u_off + 1 + 16 * i, u);
+        }
         uint4 rb = make_uint4(0u, 0u, 0u, 0u);
         if constexpr (RESMODE != 0) {
           if (ok_a) { const uint2 t = ldg64(p.epi.residual + off_a); rb.x = t.x; rb.y = t.y; }
@@ -652,9 +666,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     er.warp_has_ch = dual ? (q * 16 < p.c_out) : (static_cast<int>(g) * kWsCo + q * 32 < p.c_out);
     er.acc_full = acc_full; er.acc_empty = acc_empty;
     uint32_t sat = 0;
-    if (p.dbg & 16) {
-      // developer aid: no accumulator hand-over at all (the issuer skips it too)
-    } else if constexpr (MODE == kWsModeS2) {
+    if constexpr (MODE == kWsModeS2) {
       WsEpiConst kc2 = kc;
       if (p.has_ds) {
         kc2.sf = ch_ok ? p.epi2.chan_scale[co] : 0.f;
@@ -697,12 +709,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       const uint32_t xl0 = static_cast<uint32_t>(bdesc0) + (a_addr >> 4), a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
       const uint32_t a_slots = static_cast<uint32_t>(p.a_slots), w_slots = static_cast<uint32_t>(p.w_slots);
       const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (p.dbg & 2) != 0, fence = (p.dbg & 8) != 0;
+      const bool pw = p.pw != 0;
       const bool one_set = MODE == kWsModeS2 && p.acc_single;
       constexpr bool alias = !TWIN;
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0, st_i = 0;
       for (uint32_t it = item0; it < n_items; it += item_step, ++n) {
         const uint32_t ab = one_set ? 0u : (n & 1u);
-        if (!(p.dbg & 16)) mbar_wait(&acc_empty[ab], (one_set ? (n & 1u) : ((n >> 1) & 1u)) ^ 1u);
+        mbar_wait(&acc_empty[ab], (one_set ? (n & 1u) : ((n >> 1) & 1u)) ^ 1u);
         tc_fence_after();
         const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
         for (uint32_t sub = 0; sub < n_sub; ++sub) {
@@ -730,15 +743,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
             tc_fence_after();
             const uint32_t wl = wl0 + wslot * w_step, xl = xl0 + as * a_step;
             if (!no_mma) {
-              if (j == 0) {
+              if (pw) {             // one tap into Z1; the first chunk overwrites (its weights are zeros when it has no block)
+                if (leader && (j == 0 || (p.masks[g * kWsMaxChunks + j] & 1u)))
+                  mma_i8_ss(z1, (static_cast<uint64_t>(I.a_hi) << 32) | wl, (static_cast<uint64_t>(I.b_hi) << 32) | xl, I.idesc, j == 0 ? 0u : 1u);
+              } else if (j == 0) {
                 ws_issue_chunk<true, alias>(I, z1, wl, xl, 0x1FFu, has_ds);
               } else {
                 const uint32_t mask = p.masks[g * kWsMaxChunks + j];
-                const bool ds = has_ds && (p.masks2[g * kWsMaxChunks + j] & 1u);
+                const bool ds = has_ds && (p.masks2[g * kWsMaxChunks2 + j] & 1u);
                 ws_issue_chunk<false, alias>(I, z1, wl, xl, mask, ds);
               }
             }
-            if (p.dbg & 128) mbar_arrive(&a_empty[as]); else
             if (leader) mma_commit(&a_empty[as]);
             if (++as == a_slots) { as = 0; aph ^= 1u; }
             if (!w_resident) {
@@ -747,7 +762,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
             }
           }
         }
-        if (leader && !(p.dbg & 16)) mma_commit(&acc_full[ab]);
+        if (leader) mma_commit(&acc_full[ab]);
         if (tl && leader && n == 0) tl[6] = clock64();                  // 6: first item issued
       }
       if (tl && leader) { tl[7] = clock64(); tl[12] = n; }              // 7: issuer done, 12: items
@@ -800,10 +815,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
         int nb[kOps];
 #pragma unroll
         for (int k = 0; k < kOps; ++k) {
-          const int yy = p.stride * y0 - 1 + (yrow[k] & 0xffff);
+          const int yy = p.stride * y0 - p.ypad + (yrow[k] & 0xffff);
           const bool ok = yy >= 0 && yy < p.H && nbytes[k] > 0 && ((yrow[k] >> 16) == 0 || have_b);
           nb[k] = ok ? nbytes[k] : min(nbytes[k], 0);
-          go[k] = ok ? static_cast<uint32_t>(goff[k] + (p.stride * y0 - 1) * p.in_pitch) : 0u;
+          go[k] = ok ? static_cast<uint32_t>(goff[k] + (p.stride * y0 - p.ypad) * p.in_pitch) : 0u;
         }
         const int8_t* src0 = p.x + static_cast<int64_t>(img) * p.C * p.H * p.in_pitch;
         for (uint32_t j = 0; j < n_chunks; ++j) {
@@ -833,7 +848,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     // =================================================================== weight loader (bulk copies)
     if (elect_one()) {
       uint32_t ws = 0, wph = 0;
-      const uint8_t* wsrc = p.wblob + static_cast<size_t>(g) * n_chunks * kWsChunkBytes;
+      const uint8_t* wsrc = p.wblob + static_cast<size_t>(g) * n_chunks * static_cast<size_t>(p.w_src_stride);
       const uint32_t my_items = item0 < n_items ? (n_items - item0 + item_step - 1) / item_step : 0u;
       uint32_t passes = 0;                       // resident: one pass over the chunks; streamed: one per pixel tile
       if (p.w_resident) passes = my_items ? 1u : 0u;
@@ -851,10 +866,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
           }
           uint64_t* bar = &w_full[wslot];
           mbar_arrive_expect_tx(bar, static_cast<uint32_t>(p.w_chunk_bytes));
-          const uint8_t* src = wsrc + static_cast<size_t>(j) * kWsChunkBytes;
+          const uint8_t* src = wsrc + static_cast<size_t>(j) * static_cast<size_t>(p.w_src_stride);
           uint8_t* dst = smem + kWsSmemBar + wslot * static_cast<uint32_t>(p.w_chunk_bytes);
+          if (p.pw) {
+            bulk_g2s(dst, src, kWsTapBytes, bar);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 3; ++i) bulk_g2s(dst + i * (kWsChunkBytes / 3), src + i * (kWsChunkBytes / 3), kWsChunkBytes / 3, bar);
+            for (int i = 0; i < 3; ++i) bulk_g2s(dst + i * (kWsChunkBytes / 3), src + i * (kWsChunkBytes / 3), kWsChunkBytes / 3, bar);
+          }
           if (p.has_ds)
             bulk_g2s(dst + kWsChunkBytes, p.wblob2 + (static_cast<size_t>(g) * n_chunks + j) * kWsTapBytes, kWsTapBytes, bar);
         }

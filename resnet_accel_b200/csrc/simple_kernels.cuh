@@ -257,6 +257,42 @@ __global__ void relu_i8_kernel(int8_t* __restrict__ d, int64_t n, int32_t hi) {
     d[i] = static_cast<int8_t>(v);
   }
 }
+// Every second pixel of every second row of `planes` image planes: what a stride-2 / pad-0 1x1 convolution reads
+// (conv2d_int8_im2col with stride 2, golden_models.cpp:883-933; the ResNet-50 downsample branches).  The row padding of
+// the output is not touched (it stays zero).
+__global__ void subsample2_i8_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int64_t planes, int32_t in_pitch,
+                                     int32_t H, int32_t Ho, int32_t Wo, int32_t out_pitch) {
+  const int64_t n = planes * Ho * Wo;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / Wo;
+    const int xo = static_cast<int>(i - row * Wo);
+    const int64_t pl = row / Ho;
+    const int yo = static_cast<int>(row - pl * Ho);
+    out[(pl * Ho + yo) * out_pitch + xo] = in[(pl * H + 2 * yo) * static_cast<int64_t>(in_pitch) + 2 * xo];
+  }
+}
+// same, four output pixels per thread from one aligned 8-byte load (rows 8-byte aligned and long enough: checked on the host)
+__global__ void subsample2_i8_vec_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int64_t planes, int32_t in_pitch,
+                                         int32_t H, int32_t Ho, int32_t Wo, int32_t out_pitch) {
+  const int q_per_row = (Wo + 3) >> 2;
+  const int64_t n = planes * Ho * q_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / q_per_row;
+    const int q = static_cast<int>(i - row * q_per_row);
+    const int64_t pl = row / Ho;
+    const int yo = static_cast<int>(row - pl * Ho);
+    const uint2 v = *reinterpret_cast<const uint2*>(in + (pl * H + 2 * yo) * static_cast<int64_t>(in_pitch) + 8 * q);
+    const uint32_t even = __byte_perm(v.x, v.y, 0x6420);
+    int8_t* o = out + (pl * Ho + yo) * out_pitch + 4 * q;
+    if (4 * q + 4 <= Wo) {
+      *reinterpret_cast<uint32_t*>(o) = even;
+    } else {
+      for (int b = 0; 4 * q + b < Wo; ++b) o[b] = static_cast<int8_t>(even >> (8 * b));
+    }
+  }
+}
 __global__ void relu_i32_kernel(int32_t* __restrict__ d, int64_t n) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)

@@ -218,6 +218,7 @@ class BsrNetwork:
             else:   # rows padded to 16 bytes: the next layer streams them with 16-byte cp.async
                 self.buffers[sp.name] = ops.alloc_padded((batch, sp.c_out, sp.h_out, sp.w_out))
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.sub_buffers: Dict[str, torch.Tensor] = {}     # inputs of 1x1 / stride-2 convolutions after 2x sub-sampling
         self.static_in: Optional[torch.Tensor] = None
         # a 3x3 / stride 2 convolution and the 1x1 / stride 2 downsample of the same tensor run as one call
         self.fused_ds: Dict[str, str] = {}
@@ -285,13 +286,21 @@ class BsrNetwork:
                               relu=sp.relu, relu_ds=dsp.relu, out=out, out_ds=self.buffers[dsp.name], sat_count=self.sat)
             elif sp.kind == "conv":
                 L = self.layers[sp.name]
+                stride = sp.stride
+                if sp.k == 1 and sp.stride == 2 and sp.pad == 0:
+                    # a 1x1 / stride 2 convolution (ResNet-50 downsample) reads every second pixel of every second row: take
+                    # those first, then it is a stride-1 pointwise convolution and runs on the weight-stationary kernel
+                    if sp.name not in self.sub_buffers:
+                        self.sub_buffers[sp.name] = ops.alloc_padded((src.shape[0], sp.c_in, sp.h_out, sp.w_out))
+                    src = ops.subsample2_int8(src, out=self.sub_buffers[sp.name])
+                    stride = 1
                 if sp.residual:
                     # conv -> requant -> + identity -> ReLU on the int8 sum
-                    L.plan.conv(src, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=L.sf, bias=L.bias, relu=False,
+                    L.plan.conv(src, sp.k, stride, sp.pad, sp.c_out, "i8", chan_scale=L.sf, bias=L.bias, relu=False,
                                 residual=t[sp.residual], res_scales=(L.s_out, self.scale_of[sp.residual], L.s_out), out=out,
                                 sat_count=self.sat, relu_out=True)
                 else:
-                    L.plan.conv(src, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=L.sf, bias=L.bias,
+                    L.plan.conv(src, sp.k, stride, sp.pad, sp.c_out, "i8", chan_scale=L.sf, bias=L.bias,
                                 relu=sp.relu, out=out, sat_count=self.sat)
             elif sp.kind == "maxpool":
                 ops.maxpool_i8(src, sp.k, sp.stride, sp.pad, out=out)

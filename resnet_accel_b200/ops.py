@@ -312,7 +312,8 @@ class BsrPlan:
                 residual = r2
         e, keep = self._epilogue(out_kind, c_out, chan_scale, bias, relu, residual, res_scales, sat_count, chan_absmax,
                                  relu_out)
-        if ksize == 3 and stride in (1, 2) and pad == 1 and out_kind == "i8" and chan_absmax is None and W <= 62:
+        if out_kind == "i8" and chan_absmax is None and W <= 62 and (
+                (ksize == 3 and stride in (1, 2) and pad == 1) or (ksize == 1 and stride == 1 and pad == 0)):
             self._prepare_conv_ws(Cin, c_out, ksize)
         g = ConvGeom(B, Cin, H, W, ksize, stride, pad, in_pitch)
         P = max(Ho * Wo, 1)
@@ -528,6 +529,26 @@ def add_residual_i8(a: torch.Tensor, b: torch.Tensor, s_main: float, s_res: floa
     a, b = a.contiguous(), b.contiguous()
     out = torch.empty_like(a)
     check(_lib.lib().accel_add_residual_i8(_ptr(a), _ptr(b), _ptr(out), a.numel(), s_main, s_res, s_out, _stream()))
+    return out
+
+
+def subsample2_int8(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``x[:, :, ::2, ::2]`` of an int8 NCHW tensor (dense or padded rows) into a padded-row tensor: the input a 1x1 / stride 2
+    convolution really reads, so that it can run as a stride-1 pointwise convolution (csrc/conv_ws.cuh)."""
+    if x.dtype != torch.int8 or x.dim() != 4 or not x.is_cuda:
+        raise AcceleratorError(_lib.INVALID_CONFIG, "Activations must be a 4-D INT8 CUDA tensor (NCHW)")
+    pitch = _row_pitch(x)
+    if pitch is None:
+        x = x.contiguous()
+        pitch = x.shape[3]
+    B, Cn, H, W = x.shape
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    if out is None:
+        out = alloc_padded((B, Cn, Ho, Wo))
+    op = _row_pitch(out)
+    if op is None or tuple(out.shape) != (B, Cn, Ho, Wo) or out.dtype != torch.int8:
+        raise AcceleratorError(_lib.INVALID_CONFIG, "output must be int8 NCHW [B, C, ceil(H/2), ceil(W/2)], dense or with padded rows")
+    check(_lib.lib().accel_subsample2_i8(_ptr(x), B * Cn, H, W, pitch, _ptr(out), op, _stream()))
     return out
 
 

@@ -219,3 +219,88 @@ def test_conv_ws_stride2_alone():
     _s2_case(9, 128, 28, 28, 128, 0.3, seed=6, with_ds=False)
     _s2_case(3, 256, 14, 14, 200, 0.3, seed=7, with_ds=False)     # streamed weights: whole-image tiles, two accumulator sets
     _s2_case(2, 160, 12, 24, 64, 0.5, seed=8, with_ds=False)
+
+
+def _pw_case(B, Cin, H, W, Cout, density, seed, residual=False, relu=True, relu_out=False, res_scales=(0.05, 0.02, 0.04)):
+    """1x1 / stride 1 / pad 0 on the weight-stationary kernel (pointwise mode) vs the C oracle."""
+    import torch
+    from resnet_accel_b200 import _lib, ops
+    from resnet_accel_b200.ops import BsrPlan
+    rng = np.random.default_rng(seed)
+    Wm = rng.integers(-128, 128, (Cout, Cin)).astype(np.int8)
+    nbr, nbc = -(-Cout // 14), -(-Cin // 14)
+    keep = rng.random((nbr, nbc)) < density
+    keep[:, : min(3, nbc)] = False                   # the first 32-channel chunk holds no block: it still initialises the accumulator
+    Wm = Wm * np.repeat(np.repeat(keep, 14, 0), 14, 1)[:Cout, :Cin].astype(np.int8)
+    bsr = O.build_bsr_14x14_int8_direct(Wm)
+    x = rng.integers(-128, 128, (B, Cin, H, W), dtype=np.int8)
+    bias = rng.integers(-1000, 1000, Cout, dtype=np.int32)
+    sf = rng.uniform(1e-4, 2e-3, Cout).astype(np.float32)
+    res = rng.integers(-128, 128, (B, Cout, H, W), dtype=np.int8) if residual else None
+    plan = BsrPlan(bsr["indptr"], bsr["indices"], bsr["data"], n_block_cols=bsr["num_block_cols"])
+    xd = ops.alloc_padded(x.shape)
+    xd.copy_(torch.from_numpy(x).cuda())
+    base_in = xd._base if xd._base is not None else xd
+    if base_in.shape[-1] > W:
+        base_in[..., W:] = 77                          # garbage in the row padding of the input must not matter
+    rd = None
+    if residual:
+        rd = ops.alloc_padded(res.shape)
+        rd.copy_(torch.from_numpy(res).cuda())
+    out = ops.alloc_padded((B, Cout, H, W))
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    before = _lib.lib().accel_debug_counter(0)
+    plan.conv(xd, 1, 1, 0, Cout, out_kind="i8", chan_scale=sf, bias=bias, relu=relu, residual=rd, res_scales=res_scales,
+              sat_count=cnt, relu_out=relu_out, out=out)
+    torch.cuda.synchronize()
+    assert _lib.lib().accel_debug_counter(0) == before + 1, "the weight-stationary kernel did not run"
+    ref, sat = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, 1, 1, 0, bias=bias, relu=relu, sf=sf,
+                                       residual=res, res_scales=res_scales)
+    if relu_out:
+        ref = np.maximum(ref, 0)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert int(cnt.item()) == sat
+    base = out._base if out._base is not None else out
+    assert int(base[..., W:].abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,density,residual", [
+    (2, 64, 56, 56, 64, 0.5, False),          # ResNet-50 layer1.0.conv1: <= 64 channels, paired tiles
+    (2, 64, 56, 56, 256, 0.3, True),          # layer1.x.conv3 with the identity added
+    (3, 256, 56, 56, 64, 0.3, False),         # layer1.1.conv1
+    (3, 512, 28, 28, 128, 0.3, False),        # layer2: 32-pixel rows
+    (4, 1024, 14, 14, 256, 0.3, False),       # layer3: weights resident at Cin 1024 (32 chunks)
+    (4, 256, 14, 14, 1000, 0.3, True),        # a channel count that is no multiple of 128
+    (5, 2048, 7, 7, 512, 0.2, False),         # layer4: two images per staged row, weights streamed (64 chunks), odd batch
+    (4, 512, 7, 7, 2048, 0.3, True),          # layer4.x.conv3: 16 channel groups
+    (40, 96, 28, 28, 160, 0.4, False),        # many tiles per CTA, 3 chunks
+])
+def test_conv_ws_pointwise_vs_oracle(B, Cin, H, W, Cout, density, residual):
+    _pw_case(B, Cin, H, W, Cout, density, seed=B + Cin + H + Cout, residual=residual, relu=not residual, relu_out=residual)
+
+
+def test_subsample2_and_strided_pointwise():
+    """x[:, :, ::2, ::2] on the GPU, and a 1x1 / stride 2 convolution = the pointwise kernel on the sub-sampled input."""
+    import torch
+    from resnet_accel_b200 import ops
+    from resnet_accel_b200.ops import BsrPlan
+    rng = np.random.default_rng(77)
+    for shape in ((3, 5, 14, 14), (2, 64, 57, 55), (2, 32, 8, 32)):
+        x = torch.from_numpy(rng.integers(-128, 128, shape, dtype=np.int8)).cuda()
+        xp = ops.alloc_padded(shape)
+        xp.copy_(x)
+        for src in (x, xp):
+            got = ops.subsample2_int8(src)
+            assert torch.equal(got, x[:, :, ::2, ::2])
+            base = got._base if got._base is not None else got
+            assert int(base[..., got.shape[-1]:].abs().sum().item()) == 0
+    B, Cin, H, W, Cout = 2, 256, 28, 28, 512
+    Wm = rng.integers(-128, 128, (Cout, Cin)).astype(np.int8)
+    bsr = O.build_bsr_14x14_int8_direct(Wm)
+    x = rng.integers(-128, 128, (B, Cin, H, W), dtype=np.int8)
+    sf = rng.uniform(1e-4, 1e-3, Cout).astype(np.float32)
+    plan = BsrPlan(bsr["indptr"], bsr["indices"], bsr["data"], n_block_cols=bsr["num_block_cols"])
+    xs = ops.subsample2_int8(torch.from_numpy(x).cuda())
+    got = plan.conv(xs, 1, 1, 0, Cout, out_kind="i8", chan_scale=sf).cpu().numpy()
+    ref, _ = c_oracle.conv_bsr_layer(x, bsr["indptr"], bsr["indices"], bsr["data"], Cout, 1, 2, 0, sf=sf)
+    assert np.array_equal(got, ref)
