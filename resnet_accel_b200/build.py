@@ -35,20 +35,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra: list | None = None) -> str:
+    """out / extra: developer builds (another output path, extra nvcc flags such as -DACCEL_DEV=1)."""
+    if out is None and not force and not needs_build():
         return LIB
+    out = out or LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "--fmad=false",
            "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out] + list(extra or []) + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _out = sys.argv[sys.argv.index("-o") + 1] if "-o" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out, extra=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -75,7 +75,7 @@ struct WsParams {
   int32_t chan_stride;         // H * out_pitch
   int32_t x_store_end;         // pixels of a row that are stored (W rounded up to 16)
   int64_t image_stride;        // c_out * chan_stride
-  int32_t dbg;                 // developer aid: bit 0 = epilogue does no work, bit 1 = issuer issues no MMAs
+  int32_t dbg;                 // developer aid (compiled in with -DACCEL_DEV=1 only): bit 0 = epilogue does no work, bit 1 = issuer issues no MMAs
   long long* timeline;         // developer aid: 16 clock64 stamps per CTA when non-null (accel_debug_set_timeline)
   uint16_t masks[kWsMaxGroups * kWsMaxChunks];
   // stride-2 mode (3x3 / stride 2 / pad 1, optionally fused with the 1x1 / stride 2 convolution that reads the same input:
@@ -94,11 +94,22 @@ struct WsParams {
   // only - the epilogue takes U as zero; the weight blob is [group][chunk][4096] (w_src_stride = 4096)
   int32_t pw, ypad, w_src_stride;
 };
+// Developer aids (stage-isolation flags, clock stamps) sit inside the loader / issuer / epilogue loops: they are compiled out
+// unless the library is built with -DACCEL_DEV=1 (tools/ws_timeline.py, tools/ws_probe.py need that build).
+#ifndef ACCEL_DEV
+#define ACCEL_DEV 0
+#endif
+#ifndef ACCEL_WS_FENCE
+#define ACCEL_WS_FENCE 0        // 1: fence.proxy.async per activation stage on the issuer side, always (ACCEL_DBG_FLAGS bit 3 turns it on at run time)
+#endif
+struct WsParams;
+__device__ __forceinline__ int ws_dbg(const WsParams& p);
 struct WsLaunch {
   alignas(64) CUtensorMap tmap;
   WsParams p;
 };
 
+__device__ __forceinline__ int ws_dbg(const WsParams& p) { return ACCEL_DEV ? p.dbg : 0; }
 __host__ __device__ constexpr uint32_t idesc_i8_bmn(uint32_t M, uint32_t N) {
   return (2u << 4) | (1u << 7) | (1u << 10) | (0u << 15) /* A K-major */ | (1u << 16) /* B MN-major */ | ((N >> 3) << 17) |
          ((M >> 4) << 24);
@@ -445,10 +456,10 @@ __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRo
     eg.y0 = static_cast<int>(tc - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
     eg.obase = static_cast<int64_t>(img) * p.image_stride + static_cast<int64_t>(r.co) * p.chan_stride;
     uint4 rpre[kWsMaxMyChunks];
-    if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_prefetch<RESMODE>(p, eg, rpre);      // residual bytes: before the MMAs are done
+    if (r.warp_has_ch && !(ws_dbg(p) & 1)) ws_epi_prefetch<RESMODE>(p, eg, rpre);      // residual bytes: before the MMAs are done
     mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
     tc_fence_after();
-    if (r.warp_has_ch && !(p.dbg & 1)) ws_epi_tile<RESMODE, SAT, FAST>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, rpre, sat);
+    if (r.warp_has_ch && !(ws_dbg(p) & 1)) ws_epi_tile<RESMODE, SAT, FAST>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, rpre, sat);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&r.acc_empty[ab]);
@@ -471,7 +482,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop_twin(const WsParams& p, const Ws
     const int64_t obase = static_cast<int64_t>(img_a) * p.image_stride + static_cast<int64_t>(r.co) * p.chan_stride;
     mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
     tc_fence_after();
-    if (r.warp_has_ch && !(p.dbg & 1)) {
+    if (r.warp_has_ch && !(ws_dbg(p) & 1)) {
       for (int k = 0; k < kWsMaxMyChunks; ++k) {
         const int i = 2 * (r.half + 2 * (k >> 1)) + (k & 1);         // chunk = staged row i of the tile
         if (i >= r.n_c16) break;
@@ -528,7 +539,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop_s2(const WsParams& p, const WsEp
     const int64_t obase = static_cast<int64_t>(img) * p.image_stride + static_cast<int64_t>(r.co) * p.chan_stride;
     mbar_wait(&r.acc_full[ab], p.acc_single ? (n & 1u) : ((n >> 1) & 1u));
     tc_fence_after();
-    if (r.warp_has_ch && !(p.dbg & 1)) {
+    if (r.warp_has_ch && !(ws_dbg(p) & 1)) {
       for (int k = 0; k < kWsMaxMyChunks; ++k) {
         const int i = 2 * (r.half + 2 * (k >> 1)) + (k & 1);
         if (i >= r.n_c16) break;
@@ -619,7 +630,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
 
   // The next kernel on the stream may take over SMs as CTAs of this grid retire (its prologue and resident weight
   // load then overlap our tail); everything here that reads what the previous kernel wrote sits behind griddep_wait().
-  long long* tl = p.timeline ? p.timeline + static_cast<size_t>(blockIdx.x) * 128 : nullptr;
+  long long* const tl = (ACCEL_DEV && p.timeline) ? p.timeline + static_cast<size_t>(blockIdx.x) * 128 : nullptr;
   if (tl && threadIdx.x == 0) { tl[0] = clock64(); long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); tl[14] = g; }   // 0: CTA entry (14: ns)
   griddep_launch();
   if (threadIdx.x == 0) {
@@ -708,7 +719,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       const uint32_t wl0 = static_cast<uint32_t>(adesc0) + (w_addr >> 4), w_step = static_cast<uint32_t>(p.w_chunk_bytes) >> 4;
       const uint32_t xl0 = static_cast<uint32_t>(bdesc0) + (a_addr >> 4), a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
       const uint32_t a_slots = static_cast<uint32_t>(p.a_slots), w_slots = static_cast<uint32_t>(p.w_slots);
-      const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (p.dbg & 2) != 0, fence = (p.dbg & 8) != 0;
+      const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (ws_dbg(p) & 2) != 0, fence = ((p.dbg & 8) != 0) || ACCEL_WS_FENCE;
       const bool pw = p.pw != 0;
       const bool one_set = MODE == kWsModeS2 && p.acc_single;
       constexpr bool alias = !TWIN;

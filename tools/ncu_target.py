@@ -36,11 +36,12 @@ if "conv" in which:
         res = ops.alloc_padded((batch, sp.c_out, sp.h_out, sp.w_out))
         res.copy_(torch.randint(-128, 128, (batch, sp.c_out, sp.h_out, sp.w_out), dtype=torch.int8, device="cuda"))
         out = ops.alloc_padded((batch, sp.c_out, sp.h_out, sp.w_out))
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")        # the network runner counts saturations: same variant
         for _ in range(reps):
             if sp.residual:
                 y = lay.plan.conv(x, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=lay.sf, residual=res,
-                                  res_scales=(0.05, 0.05, 0.05), relu_out=True, out=out)
+                                  res_scales=(0.05, 0.05, 0.05), relu_out=True, out=out, sat_count=cnt)
             else:
-                y = lay.plan.conv(x, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=lay.sf, relu=True, out=out)
+                y = lay.plan.conv(x, sp.k, sp.stride, sp.pad, sp.c_out, "i8", chan_scale=lay.sf, relu=True, out=out, sat_count=cnt)
         torch.cuda.synchronize()
 print("ok")
