@@ -119,6 +119,16 @@ WsKernelFn ws_kernel_pick(bool sat, bool fast) {
 }
 WsKernelFn ws_kernel_ptr(int mode, int resmode, bool sat, bool fast) {
   if (mode == accel::kWsModeS2) return resmode == 0 ? ws_kernel_pick<accel::kWsModeS2, 0>(sat, fast) : nullptr;
+  if (mode == accel::kWsModePw || mode == accel::kWsModeTwinPw) {      // pointwise: no residual / the integer residual add / the general divide
+    const bool tw = mode == accel::kWsModeTwinPw;
+    switch (resmode) {
+      case 0: return tw ? ws_kernel_pick<accel::kWsModeTwinPw, 0>(sat, fast) : ws_kernel_pick<accel::kWsModePw, 0>(sat, fast);
+      case 1: return tw ? ws_kernel_pick<accel::kWsModeTwinPw, 1>(sat, fast) : ws_kernel_pick<accel::kWsModePw, 1>(sat, fast);
+      case 2: return tw ? ws_kernel_pick<accel::kWsModeTwinPw, 2>(sat, fast) : ws_kernel_pick<accel::kWsModePw, 2>(sat, fast);
+      case 3: return tw ? ws_kernel_pick<accel::kWsModeTwinPw, 3>(sat, fast) : ws_kernel_pick<accel::kWsModePw, 3>(sat, fast);
+      default: return tw ? ws_kernel_pick<accel::kWsModeTwinPw, 4>(sat, fast) : ws_kernel_pick<accel::kWsModePw, 4>(sat, fast);
+    }
+  }
   if (mode == accel::kWsModeTwin) {
     switch (resmode) {
       case 0: return ws_kernel_pick<accel::kWsModeTwin, 0>(sat, fast);
@@ -163,7 +173,7 @@ void set_kernel_attrs() {
     if (g_attr_err == cudaSuccess)
       g_attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPersist);
   }
-  for (int m = 0; m < 3; ++m)
+  for (int m = 0; m < 5; ++m)
     for (int r = 0; r < 5; ++r)
       for (int t = 0; t < 4; ++t)
         if (const void* f = ws_kernel_fn(m, r, (t & 1) != 0, (t & 2) != 0))
@@ -541,7 +551,8 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   if (per_group < 1) return kWsNotApplicable;
   const int smem = fixed + p.a_slots * p.a_stage_bytes;
   const int resmode = !epi->residual ? 0 : (p.res_fast == 3 ? 4 : (p.res_fast == 2 ? 3 : (p.res_fast == 1 ? 1 : 2)));
-  const int mode = stride == 2 ? accel::kWsModeS2 : (p.twin ? accel::kWsModeTwin : accel::kWsModeS1);
+  const int mode = stride == 2 ? accel::kWsModeS2
+                               : (p.twin ? (p.pw ? accel::kWsModeTwinPw : accel::kWsModeTwin) : (p.pw ? accel::kWsModePw : accel::kWsModeS1));
   // conversion-free epilogue: the caller promised |accumulator + bias| < 2^22 (both launches of a fused stride-2 pair must)
   const bool fast = !g_no_fast_epi && epi->acc_bound > 0 && epi->acc_bound < (1 << 22) && resmode == 4 && !plan_ds;
   WsKernelFn kfn = ws_kernel_ptr(mode, resmode, epi->sat_count != nullptr, fast);

@@ -48,6 +48,7 @@ constexpr int kWsMaxChunks2 = 16, kWsMaxGroups2 = 8;      // the fused 1x1 / str
 constexpr int kWsRing9 = 4;                        // 3x3: weights resident when Cin <= 128, else a ring of this many 36 KB chunk slots
 constexpr int kWsMaxWSlots = 32;                   // weight slots (1x1: 4 KB chunks - resident up to Cin 1024, else a ring)
 constexpr int kWsMaxASlots = 16;
+constexpr uint32_t kWsFenceGroup = 4;               // activation stages one issuer-side proxy fence may cover
 constexpr int kWsAccCols = 256;                    // per accumulator set: Z1 [0, N), U [N-2, 2N)
 constexpr int kWsSmemBar = 2048;                   // barriers (132 x 8 bytes) + TMEM slot in front of the operand areas
 
@@ -100,7 +101,7 @@ struct WsParams {
 #define ACCEL_DEV 0
 #endif
 #ifndef ACCEL_WS_FENCE
-#define ACCEL_WS_FENCE 0        // 1: fence.proxy.async per activation stage on the issuer side, always (ACCEL_DBG_FLAGS bit 3 turns it on at run time)
+#define ACCEL_WS_FENCE 0        // issuer-side fence.proxy.async between the cp.async stages and the MMAs: 0 none, 1 one per stage, 2 one per group of arrived stages
 #endif
 struct WsParams;
 __device__ __forceinline__ int ws_dbg(const WsParams& p);
@@ -310,9 +311,10 @@ struct WsChunk {           // one 16-pixel chunk of this thread's channel
   bool lane_ok;            // this thread stores it
   int64_t off;             // element offset of the chunk in the output / residual tensor
 };
+template <bool PW>
 __device__ __forceinline__ void ws_chunk_load(const WsParams& p, uint32_t acc, const WsChunk& c, uint32_t (&z)[16], uint32_t (&u)[16]) {
   tmem_ld16(acc + c.p0, z);
-  if (p.pw) {
+  if constexpr (PW) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) u[e] = 0u;
   } else {
@@ -374,24 +376,24 @@ __device__ __forceinline__ void ws_epi_prefetch(const WsParams& p, const WsEpiGe
     }
   }
 }
-template <int RESMODE, bool SAT, bool FAST>
+template <int RESMODE, bool SAT, bool FAST, bool PW>
 __device__ __forceinline__ void ws_epi_tile(const WsParams& p, uint32_t acc, const WsEpiGeom& g, const WsEpiConst& kc,
                                             const uint4 (&rpre)[kWsMaxMyChunks], uint32_t& sat) {
   uint32_t za[16], ua[16], zb[16], ub[16];
   WsChunk ca, cb;
   bool has_a = ws_chunk_at(p, g, 0, ca), has_b = false;
-  if (has_a) ws_chunk_load(p, acc, ca, za, ua);
+  if (has_a) ws_chunk_load<PW>(p, acc, ca, za, ua);
 #pragma unroll
   for (int k = 0; k < kWsMaxMyChunks; k += 2) {
     if (!has_a) break;
     tmem_ld_wait();
     has_b = ws_chunk_at(p, g, k + 1, cb);
-    if (has_b) ws_chunk_load(p, acc, cb, zb, ub);
+    if (has_b) ws_chunk_load<PW>(p, acc, cb, zb, ub);
     if (ca.live) ws_chunk_finish<RESMODE, SAT, FAST>(p, ca, za, ua, rpre[k], kc, sat);
     if (!has_b) break;
     tmem_ld_wait();
     has_a = k + 2 < kWsMaxMyChunks && ws_chunk_at(p, g, k + 2, ca);
-    if (has_a) ws_chunk_load(p, acc, ca, za, ua);
+    if (has_a) ws_chunk_load<PW>(p, acc, ca, za, ua);
     if (cb.live) ws_chunk_finish<RESMODE, SAT, FAST>(p, cb, zb, ub, rpre[k + 1], kc, sat);
   }
   tmem_ld_wait();
@@ -442,7 +444,7 @@ struct WsEpiRole {
   uint64_t* acc_full;
   uint64_t* acc_empty;
 };
-template <int RESMODE, bool SAT, bool FAST>
+template <int RESMODE, bool SAT, bool FAST, bool PW>
 __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, int lane) {
   uint32_t sat = 0, n = 0;
   for (uint32_t it = r.item0; it < r.n_items; it += r.item_step, ++n) {
@@ -459,7 +461,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRo
     if (r.warp_has_ch && !(ws_dbg(p) & 1)) ws_epi_prefetch<RESMODE>(p, eg, rpre);      // residual bytes: before the MMAs are done
     mbar_wait(&r.acc_full[ab], (n >> 1) & 1u);
     tc_fence_after();
-    if (r.warp_has_ch && !(ws_dbg(p) & 1)) ws_epi_tile<RESMODE, SAT, FAST>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, rpre, sat);
+    if (r.warp_has_ch && !(ws_dbg(p) & 1)) ws_epi_tile<RESMODE, SAT, FAST, PW>(p, r.tmem_acc + ab * kWsAccCols, eg, kc, rpre, sat);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&r.acc_empty[ab]);
@@ -467,7 +469,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop(const WsParams& p, const WsEpiRo
   return sat;
 }
 
-template <int RESMODE, bool SAT, bool FAST>
+template <int RESMODE, bool SAT, bool FAST, bool PW>
 __device__ __forceinline__ uint32_t ws_epi_loop_twin(const WsParams& p, const WsEpiRole& r, const WsEpiConst& kc, int lane) {
   uint32_t sat = 0, n = 0;
   const uint64_t keep64 = p.W >= 8 ? ~0ull : ((1ull << (8 * p.W)) - 1ull);
@@ -490,7 +492,7 @@ __device__ __forceinline__ uint32_t ws_epi_loop_twin(const WsParams& p, const Ws
         const int64_t off_a = obase + static_cast<int64_t>(y0 + i) * p.out_pitch, off_b = off_a + p.image_stride;
         uint32_t z[16], u[16];
         tmem_ld16(acc + 16 * i, z);
-        if (p.pw) {
+        if constexpr (PW) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) u[e] = 0u;
         } else {
@@ -596,10 +598,13 @@ __device__ __forceinline__ void ws_issue_chunk(const WsIssue& I, uint32_t z1, ui
 // One instantiation per (tile mode, residual mode, saturation counting): every launch runs exactly one epilogue variant, so
 // the others cost it neither registers nor instruction-cache space (measured: the twin paths inside one big kernel slowed
 // the layer1 convolutions from 63 to 84 us).  MODE 0 = stride 1, 1 = stride 2 (+ fused 1x1), 2 = twin tiles.
-constexpr int kWsModeS1 = 0, kWsModeS2 = 1, kWsModeTwin = 2;
+// MODE 3 / 4 = the pointwise (1x1 / stride 1 / pad 0) forms of 0 / 2: compile-time as well - a run-time flag inside the
+// issuer and epilogue loops of the 3x3 kernels costs them several per cent (same-box A/B).
+constexpr int kWsModeS1 = 0, kWsModeS2 = 1, kWsModeTwin = 2, kWsModePw = 3, kWsModeTwinPw = 4;
 template <int MODE, int RESMODE, bool SAT, bool FAST>
 __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_constant__ WsLaunch L) {
-  constexpr bool TWIN = MODE == kWsModeTwin;
+  constexpr bool TWIN = MODE == kWsModeTwin || MODE == kWsModeTwinPw;
+  constexpr bool PW = MODE == kWsModePw || MODE == kWsModeTwinPw;
   extern __shared__ uint8_t smem_dyn[];
   const WsParams& p = L.p;
   // operand areas need 1024-byte alignment (swizzle atoms): align the dynamic window by hand
@@ -688,9 +693,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       }
       sat = ws_epi_loop_s2<SAT, FAST>(p, er, kc, kc2, lane);
     } else if constexpr (TWIN) {
-      sat = ws_epi_loop_twin<RESMODE, SAT, FAST>(p, er, kc, lane);
+      sat = ws_epi_loop_twin<RESMODE, SAT, FAST, PW>(p, er, kc, lane);
     } else {
-      sat = ws_epi_loop<RESMODE, SAT, FAST>(p, er, kc, lane);
+      sat = ws_epi_loop<RESMODE, SAT, FAST, PW>(p, er, kc, lane);
     }
     if (tl && threadIdx.x == 0) tl[3] = clock64();                     // 3: epilogue loop done (warp 0)
     if (sat_on) {
@@ -719,11 +724,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       const uint32_t wl0 = static_cast<uint32_t>(adesc0) + (w_addr >> 4), w_step = static_cast<uint32_t>(p.w_chunk_bytes) >> 4;
       const uint32_t xl0 = static_cast<uint32_t>(bdesc0) + (a_addr >> 4), a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
       const uint32_t a_slots = static_cast<uint32_t>(p.a_slots), w_slots = static_cast<uint32_t>(p.w_slots);
-      const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (ws_dbg(p) & 2) != 0, fence = ((p.dbg & 8) != 0) || ACCEL_WS_FENCE;
-      const bool pw = p.pw != 0;
+      const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (ws_dbg(p) & 2) != 0, fence = ACCEL_WS_FENCE == 1 || (ACCEL_DEV && (p.dbg & 8) != 0);
       const bool one_set = MODE == kWsModeS2 && p.acc_single;
       constexpr bool alias = !TWIN;
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0, st_i = 0;
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0, st_i = 0, fenced = 0;
       for (uint32_t it = item0; it < n_items; it += item_step, ++n) {
         const uint32_t ab = one_set ? 0u : (n & 1u);
         mbar_wait(&acc_empty[ab], (one_set ? (n & 1u) : ((n >> 1) & 1u)) ^ 1u);
@@ -741,20 +745,36 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
               mbar_wait(&w_full[ws], wph);
             }
             if (tl && leader && n == 0 && sub == 0 && j == 0) tl[4] = clock64();   // 4: issuer has the first weights
-            mbar_wait(&a_full[as], aph);
+            // The stage was written by cp.async (generic proxy) and is read by tcgen05.mma (async proxy): the PTX memory model
+            // asks for a fence.proxy.async between the mbarrier wait that makes the writes visible and the MMAs.
+            // One fence per stage on this thread costs 2 - 3 us per convolution (layer1 58.2 -> 60.3, layer2 34.6 -> 36.9,
+            // layer3 33.4 -> 36.0 us): the issuer is the critical thread.  So one fence covers every stage that has ALREADY
+            // arrived: after the blocking wait for this stage, up to kWsFenceGroup - 1 following ring slots are tested without
+            // blocking (mbarrier.test_wait), then a single fence orders all of them; their own turn skips wait and fence.
+            if constexpr (ACCEL_WS_FENCE == 2) {
+              if (fenced == 0u) {
+                mbar_wait(&a_full[as], aph);
+                uint32_t s2 = as, p2 = aph;
+                fenced = 1u;
+                for (uint32_t k = 1; k < kWsFenceGroup; ++k) {
+                  if (++s2 == a_slots) { s2 = 0; p2 ^= 1u; }
+                  if (s2 == as || !mbar_test(&a_full[s2], p2)) break;
+                  ++fenced;
+                }
+                fence_proxy_async_smem();
+              }
+              --fenced;
+            } else {
+              mbar_wait(&a_full[as], aph);
+              if (fence) fence_proxy_async_smem();
+            }
             if (tl && st_i >= 32 && st_i < 64) tl[64 + (st_i - 32)] = clock64();      // issuer saw stage st_i
             ++st_i;
             if (tl && leader && n == 0 && sub == 0 && j == 0) tl[5] = clock64();   // 5: issuer has the first activation stage
-            // The stage was written by cp.async (generic proxy) and is read by tcgen05.mma (async proxy).  A proxy fence per
-            // stage on the consumer side was measured: +2 to +3 us on every convolution (layer1 58.2 -> 60.3,
-            // layer2 34.6 -> 36.9, layer3 33.4 -> 36.0 us).  Default off, as in CUTLASS's sm100 cp.async mainloop where
-            // cp.async.mbarrier.arrive + the consumer's mbarrier wait is the whole hand-over; ACCEL_DBG_FLAGS bit 3 turns
-            // it on (tests/test_gpu_conv_ws.py soaks both settings against the gather kernels).
-            if (fence && leader) fence_proxy_async_smem();
             tc_fence_after();
             const uint32_t wl = wl0 + wslot * w_step, xl = xl0 + as * a_step;
             if (!no_mma) {
-              if (pw) {             // one tap into Z1; the first chunk overwrites (its weights are zeros when it has no block)
+              if constexpr (PW) {   // one tap into Z1; the first chunk overwrites (its weights are zeros when it has no block)
                 if (leader && (j == 0 || (p.masks[g * kWsMaxChunks + j] & 1u)))
                   mma_i8_ss(z1, (static_cast<uint64_t>(I.a_hi) << 32) | wl, (static_cast<uint64_t>(I.b_hi) << 32) | xl, I.idesc, j == 0 ? 0u : 1u);
               } else if (j == 0) {
@@ -879,7 +899,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
           mbar_arrive_expect_tx(bar, static_cast<uint32_t>(p.w_chunk_bytes));
           const uint8_t* src = wsrc + static_cast<size_t>(j) * static_cast<size_t>(p.w_src_stride);
           uint8_t* dst = smem + kWsSmemBar + wslot * static_cast<uint32_t>(p.w_chunk_bytes);
-          if (p.pw) {
+          if constexpr (PW) {
             bulk_g2s(dst, src, kWsTapBytes, bar);
           } else {
 #pragma unroll

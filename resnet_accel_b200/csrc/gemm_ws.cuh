@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kGwThreads, 1) gemm_ws_kernel(const __grid_con
       mbar_wait(&acc_full[ab], (n >> 1) & 1u);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_base + ab * kGwRows + half * 128;
-      if (!(p.dbg & 1) && m0 < p.M && __any_sync(0xffffffffu, ch_ok)) {
+      if (!(ACCEL_DEV && (p.dbg & 1)) && m0 < p.M && __any_sync(0xffffffffu, ch_ok)) {
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int64_t mc = m0 + cc * 32;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kGwThreads, 1) gemm_ws_kernel(const __grid_con
           tc_fence_after();
           const uint32_t wl = d_lo0 | (((stage0 + s * kStageBytes) >> 4) & 0x3FFFu);
           const uint32_t xl = d_lo0 | (((stage0 + s * kStageBytes + kGwBoxBytes) >> 4) & 0x3FFFu);
-          if (!(p.dbg & 2)) {
+          if (!(ACCEL_DEV && (p.dbg & 2))) {
 #pragma unroll
             for (uint32_t k = 0; k < kGwKc / 32; ++k)
               mma_i8_ss_cg<CG>(d, (static_cast<uint64_t>(d_hi) << 32) | (wl + 2u * k), (static_cast<uint64_t>(d_hi) << 32) | (xl + 2u * k),

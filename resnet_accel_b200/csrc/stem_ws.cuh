@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const uint32_t n_items = static_cast<uint32_t>(p.n_items);
 
-  long long* const tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;
+  long long* const tl = (ACCEL_DEV && p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;      // -DACCEL_DEV=1 builds only
 #define STEM_STAMP(KIND, ROW) if (tl && (ROW) >= 32u && (ROW) < 96u) tl[(KIND) * 64 + ((ROW) - 32u)] = clock64();
   griddep_launch();
   if (threadIdx.x == 0) {
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
       uint32_t pr;
       int yp0, r0, r1;
       stem_item(p, it, pr, yp0, r0, r1);
-      if (p.dbg & 1) {                              // developer aid: hand the accumulators straight back
+      if (ACCEL_DEV && (p.dbg & 1)) {                              // developer aid: hand the accumulators straight back
         for (int yc = r0; yc <= r1; ++yc) STEM_ROW((void)acc)
         continue;
       }
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_ws_kernel(const __grid_con
             const uint64_t be = (static_cast<uint64_t>(b_hi) << 32) | e_lo, bo = (static_cast<uint64_t>(b_hi) << 32) | (e_lo + 256u);
             const uint64_t be1 = (static_cast<uint64_t>(b_hi) << 32) | (e_lo + 512u), bo1 = (static_cast<uint64_t>(b_hi) << 32) | (e_lo + 768u);
             auto wt = [&](int kw) { return (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + kw * (kWsTapBytes >> 4)); };
-            if (!(p.dbg & 2)) {
+            if (!(ACCEL_DEV && (p.dbg & 2))) {
               // conv pixel x lives in column 2 + x.  Unshifted chunks: shift 0 -> +2, shift -2 -> +4.  Chunks shifted right by
               // one pixel: shift -1 -> +2, shift +1 -> +0.  The first MMA overwrites [2, 130); columns 0, 1, 130, 131 are never read.
               mma_i8_ss(z + 2, wt(3), be, idesc, 0u);      // E,  kw 3, shift  0

@@ -18,4 +18,9 @@ python tools/stem_probe.py > $O/plain_stem.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:stem_ws_kernel -s 4 -c 1 -f -o $O/ncu_stem python tools/stem_probe.py > $O/ncu_stem.log 2>&1; echo "stem rc=$?"
 env WHICH=gemm SPARSITY=70 REPS=3 python tools/ncu_target.py > $O/plain_gemm.log 2>&1 && \
 env WHICH=gemm SPARSITY=70 REPS=3 ncu --set full --clock-control none --import-source on -k regex:gemm_ws_kernel -s 1 -c 1 -f -o $O/ncu_gemm4096 python tools/ncu_target.py > $O/ncu_gemm.log 2>&1; echo "gemm rc=$?"
-ls -la $O/*.ncu-rep
+# summaries here on the box (the reports are 16 MB each; gpurun brings back at most 64 MiB)
+for r in $O/ncu_*.ncu-rep; do
+  python tools/ncu_top.py $r --top 30 > ${r%.ncu-rep}.txt 2>&1
+done
+for r in $O/ncu_*.ncu-rep; do case $r in *layer1.0.conv1*|*stem*) ;; *) rm -f $r ;; esac; done
+ls -la $O/ncu_*

@@ -42,7 +42,7 @@ for r in rd:
 tot = sum(d["gpu__time_duration.sum"] for d in per.values()) or 1.0
 if not a.forwards:
     a.forwards = int(sum(d["launches"] for n, d in per.items() if "avgpool_i8" in n)) or 1
-ours = re.compile(r"conv_ws_kernel|stem_ws_kernel|bsr_tcp_kernel|bsr_tc_kernel")
+ours = re.compile(r"conv_ws_kernel|stem_ws_kernel|gemm_ws_kernel|bsr_tcp_kernel|bsr_tc_kernel")
 os.makedirs("profiles", exist_ok=True)
 with open(f"profiles/{a.tag}_launches.md", "w") as f:
     f.write(f"# ncu launch list ({a.tag}): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
