@@ -48,7 +48,6 @@ constexpr int kWsMaxChunks2 = 16, kWsMaxGroups2 = 8;      // the fused 1x1 / str
 constexpr int kWsRing9 = 4;                        // 3x3: weights resident when Cin <= 128, else a ring of this many 36 KB chunk slots
 constexpr int kWsMaxWSlots = 32;                   // weight slots (1x1: 4 KB chunks - resident up to Cin 1024, else a ring)
 constexpr int kWsMaxASlots = 16;
-constexpr uint32_t kWsFenceGroup = 4;               // activation stages one issuer-side proxy fence may cover
 constexpr int kWsAccCols = 256;                    // per accumulator set: Z1 [0, N), U [N-2, 2N)
 constexpr int kWsSmemBar = 2048;                   // barriers (132 x 8 bytes) + TMEM slot in front of the operand areas
 
@@ -101,7 +100,7 @@ struct WsParams {
 #define ACCEL_DEV 0
 #endif
 #ifndef ACCEL_WS_FENCE
-#define ACCEL_WS_FENCE 0        // issuer-side fence.proxy.async between the cp.async stages and the MMAs: 0 none, 1 one per stage, 2 one per group of arrived stages
+#define ACCEL_WS_FENCE 0        // issuer-side fence.proxy.async between the cp.async stages and the MMAs: 0 none, 1 one per stage (see the issuer)
 #endif
 struct WsParams;
 __device__ __forceinline__ int ws_dbg(const WsParams& p);
@@ -727,7 +726,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (ws_dbg(p) & 2) != 0, fence = ACCEL_WS_FENCE == 1 || (ACCEL_DEV && (p.dbg & 8) != 0);
       const bool one_set = MODE == kWsModeS2 && p.acc_single;
       constexpr bool alias = !TWIN;
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0, st_i = 0, fenced = 0;
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0, st_i = 0;
       for (uint32_t it = item0; it < n_items; it += item_step, ++n) {
         const uint32_t ab = one_set ? 0u : (n & 1u);
         mbar_wait(&acc_empty[ab], (one_set ? (n & 1u) : ((n >> 1) & 1u)) ^ 1u);
@@ -745,29 +744,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
               mbar_wait(&w_full[ws], wph);
             }
             if (tl && leader && n == 0 && sub == 0 && j == 0) tl[4] = clock64();   // 4: issuer has the first weights
-            // The stage was written by cp.async (generic proxy) and is read by tcgen05.mma (async proxy): the PTX memory model
-            // asks for a fence.proxy.async between the mbarrier wait that makes the writes visible and the MMAs.
-            // One fence per stage on this thread costs 2 - 3 us per convolution (layer1 58.2 -> 60.3, layer2 34.6 -> 36.9,
-            // layer3 33.4 -> 36.0 us): the issuer is the critical thread.  So one fence covers every stage that has ALREADY
-            // arrived: after the blocking wait for this stage, up to kWsFenceGroup - 1 following ring slots are tested without
-            // blocking (mbarrier.test_wait), then a single fence orders all of them; their own turn skips wait and fence.
-            if constexpr (ACCEL_WS_FENCE == 2) {
-              if (fenced == 0u) {
-                mbar_wait(&a_full[as], aph);
-                uint32_t s2 = as, p2 = aph;
-                fenced = 1u;
-                for (uint32_t k = 1; k < kWsFenceGroup; ++k) {
-                  if (++s2 == a_slots) { s2 = 0; p2 ^= 1u; }
-                  if (s2 == as || !mbar_test(&a_full[s2], p2)) break;
-                  ++fenced;
-                }
-                fence_proxy_async_smem();
-              }
-              --fenced;
-            } else {
-              mbar_wait(&a_full[as], aph);
-              if (fence) fence_proxy_async_smem();
-            }
+            // The stage was written by cp.async (generic proxy) and is read by tcgen05.mma (async proxy).  Read strictly, the PTX
+            // memory model asks for a fence.proxy.async between the mbarrier wait that makes the writes visible and the MMAs
+            // (ADVICE r1).  Measured on one box (whole ResNet-18, batch 256): no fence 262.1 k img/s, one fence per stage here
+            // 255.2 k (-2.6 %: this thread is the critical one), one fence per group of up to four already-arrived stages
+            // (mbarrier.test_wait look-ahead) 245.2 k - the look-ahead code costs more than the fences it saves.  A run-time
+            // switch inside this loop costs 6 % by itself, so the choice is made at build time: ACCEL_WS_FENCE = 0 (default: the
+            // hand-over is cp.async.mbarrier.arrive + this wait + tcgen05.fence::after_thread_sync; every parity test, the
+            // bit_exact check of bench.py and the soak in tests/test_gpu_conv_ws.py run this way) or 1 (-DACCEL_WS_FENCE=1).
+            mbar_wait(&a_full[as], aph);
+            if (fence) fence_proxy_async_smem();
             if (tl && st_i >= 32 && st_i < 64) tl[64 + (st_i - 32)] = clock64();      // issuer saw stage st_i
             ++st_i;
             if (tl && leader && n == 0 && sub == 0 && j == 0) tl[5] = clock64();   // 5: issuer has the first activation stage
