@@ -70,6 +70,7 @@ bool g_no_persist = std::getenv("ACCEL_NO_PERSIST") != nullptr;   // developer s
 long long g_ws_launches = 0;         // accel_debug_counter(0)
 bool g_ws_s2_narrow = std::getenv("ACCEL_WS_S2_NARROW") != nullptr;   // developer switch: 64-pixel stride-2 tiles even with streamed weights
 bool g_no_pdl = std::getenv("ACCEL_NO_PDL") != nullptr;            // developer switch: plain stream-ordered launches
+int g_ws_tma = std::getenv("ACCEL_WS_TMA") ? std::atoi(std::getenv("ACCEL_WS_TMA")) : 3;      // developer switch, conv_ws activation stages by TMA: 0 never (LDGSTS), 1 for 64-byte rows, 2 also 32-byte, 3 (default) also 16-byte rows
 bool g_no_twin = std::getenv("ACCEL_NO_TWIN") != nullptr;          // developer switch: one image per tile even for 7-pixel rows
 bool g_no_ws = std::getenv("ACCEL_NO_WS") != nullptr;              // developer switch: never take the weight-stationary conv path
 int g_stem_rows = std::getenv("ACCEL_STEM_ROWS") ? std::atoi(std::getenv("ACCEL_STEM_ROWS")) : 0;      // developer switch: pooled rows per stem item
@@ -533,6 +534,22 @@ int try_conv_ws(const accel_plan* plan, const int8_t* input, const accel_conv_ge
   p.x_store_end = w16;
   p.image_stride = lay->image_stride;
   std::memcpy(p.masks, W.masks, sizeof(p.masks));
+  // Activation stages by TMA tensor tiles (everything but the twin tiles, whose 8-byte half rows are below TMA's 16-byte box
+  // minimum).  Same-box A/B, whole ResNet-18 at batch 256: LDGSTS loaders 261.3 k img/s, TMA for 64-byte rows 268.7 k (layer1
+  // 64 -> 56 us, layer2.0 + downsample 81 -> 66 us), also for 32-byte rows 271.5 k (layer2 45 -> 42 us), also for 16-byte rows
+  // 272.8 k.  tools/ws_timeline.py had shown the two loader warps latency-bound on their own instruction stream (~100
+  // instructions per 8 KB stage, 790 cycles alone and ~1100 next to the epilogue warps); the TMA unit needs ~4 cycles per box row
+  // whatever the SM's warps are doing.
+  p.use_tma = 0;
+  if (!p.twin && ((g_ws_tma >= 1 && P == 64) || (g_ws_tma >= 2 && P == 32) || (g_ws_tma >= 3 && P == 16))) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(Wd), static_cast<uint64_t>(g->c_in), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(g->batch)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(in_pitch) * H, static_cast<uint64_t>(in_pitch),
+                                 static_cast<uint64_t>(in_pitch) * H * g->c_in};
+    const uint32_t box[4] = {static_cast<uint32_t>(P), static_cast<uint32_t>(accel::kWsCk), static_cast<uint32_t>(p.rows_in), 1u};
+    const CUtensorMapSwizzle sw = P == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (P == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (p.rows_in <= 256 && encode_tmap(&L.tmap, input, 4, dims, strides, box, sw)) p.use_tma = 1;
+  }
   p.dbg = g_dbg_flags;
   p.timeline = g_timeline;
   p.dual = (W.c_out <= 64 && stride == 1) ? 1 : 0;
@@ -644,6 +661,7 @@ void accel_debug_set_timeline(long long* dev_buffer) {
   const char* f = std::getenv("ACCEL_DBG_FLAGS");
   g_dbg_flags = f ? std::atoi(f) : 0;
   g_no_fast_epi = std::getenv("ACCEL_NO_FAST_EPI") != nullptr;
+  g_ws_tma = std::getenv("ACCEL_WS_TMA") ? std::atoi(std::getenv("ACCEL_WS_TMA")) : 3;
   g_stem_rows = std::getenv("ACCEL_STEM_ROWS") ? std::atoi(std::getenv("ACCEL_STEM_ROWS")) : 0;
 }
 

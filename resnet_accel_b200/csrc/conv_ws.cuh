@@ -93,6 +93,9 @@ struct WsParams {
   // pointwise mode (1x1 / stride 1 / pad 0: the bottleneck convolutions of ResNet-50): one tap, no halo rows (ypad = 0), Z1
   // only - the epilogue takes U as zero; the weight blob is [group][chunk][4096] (w_src_stride = 4096)
   int32_t pw, ypad, w_src_stride;
+  // activation stages by TMA tensor tiles instead of LDGSTS (one elected thread; the tensor map of WsLaunch describes the NCHW input with
+  // the dimensions ordered (x, c, y, n): box [P][32 channels][rows_in][1], swizzle atom = one image row of 8 channels)
+  int32_t use_tma;
 };
 // Developer aids (stage-isolation flags, clock stamps) sit inside the loader / issuer / epilogue loops: they are compiled out
 // unless the library is built with -DACCEL_DEV=1 (tools/ws_timeline.py, tools/ws_probe.py need that build).
@@ -145,6 +148,9 @@ __global__ void ws_scatter_kernel(const int8_t* __restrict__ blocks, const int32
   }
 }
 
+__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ int pin(int v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ uint64_t pin64(uint64_t v) { asm volatile("" : "+l"(v)); return v; }
 __device__ __forceinline__ uint4 ldg128(const void* p) {
   uint4 v;
   asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -638,7 +644,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
   if (tl && threadIdx.x == 0) { tl[0] = clock64(); long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); tl[14] = g; }   // 0: CTA entry (14: ns)
   griddep_launch();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWsMaxASlots; ++s) { mbar_init(&a_full[s], kWsLoadThreads); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kWsMaxASlots; ++s) { mbar_init(&a_full[s], p.use_tma ? 1 : kWsLoadThreads); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kWsMaxChunks; ++s) mbar_init(&w_full[s], 1);
     for (int s = 0; s < kWsMaxWSlots; ++s) mbar_init(&w_empty[s], 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kWsEpiWarps); }
@@ -795,6 +801,33 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     griddep_wait();          // the activations are the previous kernel's output
     const int lt = static_cast<int>(threadIdx.x) - kWsWarpLoad * 32;           // 0..63
     if (tl && lt == 0) tl[8] = clock64();                              // 8: loaders past griddepcontrol.wait
+    if (!TWIN && p.use_tma) {
+      // One TMA tensor tile per stage: rows / columns / channels outside the image are zero-filled by the unit (that is the
+      // convolution padding).  The unit retires about one box row (P bytes) per 4 cycles, whatever the SM's warps are doing:
+      // for 64-byte rows (ResNet-18 layer1: 128 rows per 8 KB stage) that is faster than the two LDGSTS warps, whose ~100
+      // instructions per stage compete with the epilogue warps for issue slots; for 16 / 32-byte rows it is slower.
+      if (warp == kWsWarpLoad && elect_one()) {
+        uint32_t as = 0, aph = 0;
+        const uint32_t a_slots_ = static_cast<uint32_t>(p.a_slots), a_stage_ = static_cast<uint32_t>(p.a_stage_bytes);
+        const uint32_t box_bytes = static_cast<uint32_t>(p.a_box_bytes);
+        for (uint32_t it = item0; it < n_items; it += item_step) {
+          const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
+          for (uint32_t sub = 0; sub < n_sub; ++sub) {
+            const uint32_t tt = dual ? 2u * it + sub : it;
+            const uint32_t img = fdiv(tt, p.d_tpi);
+            const int y0 = static_cast<int>(tt - img * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
+            const int ybase = p.stride * y0 - p.ypad;
+            for (uint32_t j = 0; j < n_chunks; ++j) {
+              mbar_wait(&a_empty[as], aph ^ 1u);
+              mbar_arrive_expect_tx(&a_full[as], box_bytes);
+              tma_load_4d(a_addr + as * a_stage_, &L.tmap, 0, static_cast<int>(j * kWsCk), ybase, static_cast<int>(img), &a_full[as]);
+              if (++as == a_slots_) { as = 0; aph ^= 1u; }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else {
     const int x16s = p.P >> 4, rows = p.rows_in;
     const int n_ops = kWsCk * rows * (p.twin ? 2 : x16s);
     constexpr int kOps = TWIN ? kWsLoadOps + 1 : kWsLoadOps;      // twin tiles: 576 eight-byte copies per stage
@@ -817,31 +850,52 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       if (TWIN) yrow[k] |= xq << 16;                                // image B of the pair may not exist (odd batch)
     }
     uint32_t as = 0, aph = 0, st_l = 0;
-    const int64_t chunk_stride = static_cast<int64_t>(kWsCk) * p.H * p.in_pitch;
+    // The two loader warps are latency-bound on their own instruction stream (tools/ws_timeline.py, loads only, layer1: 433 +
+    // 277 cycles to issue the two stages of a tile, 712 cycles of per-tile set-up between tiles): everything a tile needs is
+    // kept in registers, and a tile whose staged rows all lie inside the image (all but the first and last of an image) takes
+    // the per-copy offsets and sizes as they were computed once per launch.
+    // pin(): an opaque register copy.  Left alone, ptxas re-reads these kernel parameters from the constant bank inside the tile
+    // loop (LDC / LDCU), and the parameter block is 4 KB of masks that the issuer walks - those loads miss the constant cache.
+    const int stride_ = pin(p.stride), ypad_ = pin(p.ypad), H_ = pin(p.H), pitch_ = pin(p.in_pitch), R_ = pin(p.R);
+    const uint32_t tpi_ = pin(static_cast<uint32_t>(p.tiles_per_image)), B_ = pin(static_cast<uint32_t>(p.B));
+    const uint32_t a_slots_ = pin(static_cast<uint32_t>(p.a_slots)), a_stage_ = pin(static_cast<uint32_t>(p.a_stage_bytes));
+    FastDiv d_tpi_ = p.d_tpi;
+    d_tpi_.d = pin(d_tpi_.d); d_tpi_.mul = pin(d_tpi_.mul); d_tpi_.shr = pin(d_tpi_.shr);
+    const int8_t* const x_ = reinterpret_cast<const int8_t*>(pin64(reinterpret_cast<uint64_t>(p.x)));
+    const int64_t image_bytes = static_cast<int64_t>(pin64(static_cast<uint64_t>(static_cast<int64_t>(p.C) * H_ * pitch_)));
+    const int64_t chunk_stride = static_cast<int64_t>(pin64(static_cast<uint64_t>(static_cast<int64_t>(kWsCk) * H_ * pitch_)));
     for (uint32_t it = item0; it < n_items; it += item_step) {
       const uint32_t n_sub = (dual && 2u * it + 1u < n_tiles) ? 2u : 1u;
       for (uint32_t sub = 0; sub < n_sub; ++sub) {
         const uint32_t tt = dual ? 2u * it + sub : it;
-        const uint32_t ti = fdiv(tt, p.d_tpi);                      // image (twin: image pair) of the tile
+        const uint32_t ti = fdiv(tt, d_tpi_);                       // image (twin: image pair) of the tile
         const uint32_t img = TWIN ? 2u * ti : ti;
-        const int y0 = static_cast<int>(tt - ti * static_cast<uint32_t>(p.tiles_per_image)) * p.R;
-        const bool have_b = img + 1u < static_cast<uint32_t>(p.B);
+        const int y0 = static_cast<int>(tt - ti * tpi_) * R_;
+        const bool have_b = img + 1u < B_;
+        const int ybase = stride_ * y0 - ypad_;                     // first staged input row of the tile
+        const int tile_off = ybase * pitch_;                        // >= 0 whenever that row is inside the image
+        const bool interior = ybase >= 0 && ybase + rows <= H_ && (!TWIN || have_b);       // CTA-uniform
         // per tile: which of this thread's copies read an input row inside the image (the others zero-fill: 0 bytes
         // from offset 0), so that the per-stage loop is one LDGSTS and one address add per copy
         uint32_t go[kOps];
         int nb[kOps];
+        if (interior) {
 #pragma unroll
-        for (int k = 0; k < kOps; ++k) {
-          const int yy = p.stride * y0 - p.ypad + (yrow[k] & 0xffff);
-          const bool ok = yy >= 0 && yy < p.H && nbytes[k] > 0 && ((yrow[k] >> 16) == 0 || have_b);
-          nb[k] = ok ? nbytes[k] : min(nbytes[k], 0);
-          go[k] = ok ? static_cast<uint32_t>(goff[k] + (p.stride * y0 - p.ypad) * p.in_pitch) : 0u;
+          for (int k = 0; k < kOps; ++k) { go[k] = static_cast<uint32_t>(goff[k]); nb[k] = nbytes[k]; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kOps; ++k) {
+            const int yy = ybase + (yrow[k] & 0xffff);
+            const bool ok = yy >= 0 && yy < H_ && nbytes[k] > 0 && ((yrow[k] >> 16) == 0 || have_b);
+            nb[k] = ok ? nbytes[k] : min(nbytes[k], 0);
+            go[k] = ok ? static_cast<uint32_t>(goff[k] + tile_off) : 0u;
+          }
         }
-        const int8_t* src0 = p.x + static_cast<int64_t>(img) * p.C * p.H * p.in_pitch;
+        const int8_t* src0 = x_ + static_cast<int64_t>(img) * image_bytes + (interior ? tile_off : 0);
         for (uint32_t j = 0; j < n_chunks; ++j) {
           mbar_wait(&a_empty[as], aph ^ 1u);
           if (tl && lt == 0 && st_l >= 32 && st_l < 64) tl[16 + (st_l - 32)] = clock64();     // loader got the slot of stage st_l
-          const uint32_t dst0 = a_addr + as * static_cast<uint32_t>(p.a_stage_bytes);
+          const uint32_t dst0 = a_addr + as * a_stage_;
 #pragma unroll
           for (int k = 0; k < kOps; ++k)
             if (nb[k] >= 0) {
@@ -855,11 +909,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
           cp_async_mbar_arrive(&a_full[as]);
           if (tl && lt == 0 && st_l >= 32 && st_l < 64) tl[96 + (st_l - 32)] = clock64();     // loader issued stage st_l
           ++st_l;
-          if (++as == static_cast<uint32_t>(p.a_slots)) { as = 0; aph ^= 1u; }
+          if (++as == a_slots_) { as = 0; aph ^= 1u; }
         }
       }
     }
     if (tl && lt == 0) tl[9] = clock64();                              // 9: loaders done
+    }
   }
   else {
     // =================================================================== weight loader (bulk copies)

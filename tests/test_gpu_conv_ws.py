@@ -129,6 +129,25 @@ def test_conv_ws_many_tiles_persistent():
     _case(24, 256, 14, 14, 128, 0.3, seed=12)
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "3"])
+def test_conv_ws_activation_loaders(mode, monkeypatch):
+    """The activation stages arrive by TMA tensor tiles (default, ACCEL_WS_TMA=3) or by the LDGSTS loader warps (0; 1 = TMA for
+    64-byte rows only): same bytes either way, for every row width, the stride-2 / fused-downsample and the pointwise modes."""
+    from resnet_accel_b200 import _lib
+    monkeypatch.setenv("ACCEL_WS_TMA", mode)
+    _lib.lib().accel_debug_set_timeline(None)
+    try:
+        _case(3, 64, 56, 56, 64, 0.3, seed=31)                       # 64-byte rows, paired M = 64 tiles
+        _case(3, 128, 28, 28, 128, 0.3, seed=32, residual=False, relu=True, relu_out=False)      # 32-byte rows
+        _case(20, 256, 14, 14, 256, 0.3, seed=33)                    # 16-byte rows, streamed weights
+        _case(2, 64, 13, 37, 200, 0.4, seed=34)                      # ragged rows and channels
+        _case(2, 64, 30, 62, 70, 0.2, seed=35)                       # widest row
+        _case(5, 512, 7, 7, 512, 0.3, seed=36)                       # twin tiles: always the LDGSTS loaders
+    finally:
+        monkeypatch.delenv("ACCEL_WS_TMA")
+        _lib.lib().accel_debug_set_timeline(None)
+
+
 def test_conv_ws_dense_layout_and_fallback():
     """W % 16 == 0 tensors are accepted without padding; unaligned tensors fall back to the gather kernels."""
     import torch

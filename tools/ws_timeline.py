@@ -47,5 +47,5 @@ for name in os.environ.get("LAYER", "layer1.0.conv1,layer2.1.conv1,layer3.1.conv
     c0 = t[0]
     L_, I_, J_ = c0[16:48] - c0[0], c0[64:96] - c0[0], c0[96:128] - c0[0]
     print("   stage: loader got slot / loader issued / issuer saw data   | issue - slot, data - issue  (cycles since entry, CTA 0)")
-    for i in range(0, 32, 2):
+    for i in range(0, 32, int(os.environ.get("TL_STEP", 2))):
         print(f"   {32+i:4d}: {L_[i]:8d} {J_[i]:8d} {I_[i]:8d}   | {J_[i]-L_[i]:6d} {I_[i]-J_[i]:6d}")
