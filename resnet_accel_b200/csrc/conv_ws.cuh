@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
       const uint32_t wl0 = static_cast<uint32_t>(adesc0) + (w_addr >> 4), w_step = static_cast<uint32_t>(p.w_chunk_bytes) >> 4;
       const uint32_t xl0 = static_cast<uint32_t>(bdesc0) + (a_addr >> 4), a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
       const uint32_t a_slots = static_cast<uint32_t>(p.a_slots), w_slots = static_cast<uint32_t>(p.w_slots);
-      const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (ws_dbg(p) & 2) != 0, fence = ACCEL_WS_FENCE == 1 || (ACCEL_DEV && (p.dbg & 8) != 0);
+      const bool w_resident = p.w_resident != 0, has_ds = p.has_ds != 0, no_mma = (ws_dbg(p) & 2) != 0, fence = TWIN || ACCEL_WS_FENCE == 1 || (ACCEL_DEV && (p.dbg & 8) != 0);
       const bool one_set = MODE == kWsModeS2 && p.acc_single;
       constexpr bool alias = !TWIN;
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, n = 0, st_i = 0;
@@ -750,14 +750,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
               mbar_wait(&w_full[ws], wph);
             }
             if (tl && leader && n == 0 && sub == 0 && j == 0) tl[4] = clock64();   // 4: issuer has the first weights
-            // The stage was written by cp.async (generic proxy) and is read by tcgen05.mma (async proxy).  Read strictly, the PTX
-            // memory model asks for a fence.proxy.async between the mbarrier wait that makes the writes visible and the MMAs
-            // (ADVICE r1).  Measured on one box (whole ResNet-18, batch 256): no fence 262.1 k img/s, one fence per stage here
-            // 255.2 k (-2.6 %: this thread is the critical one), one fence per group of up to four already-arrived stages
-            // (mbarrier.test_wait look-ahead) 245.2 k - the look-ahead code costs more than the fences it saves.  A run-time
-            // switch inside this loop costs 6 % by itself, so the choice is made at build time: ACCEL_WS_FENCE = 0 (default: the
-            // hand-over is cp.async.mbarrier.arrive + this wait + tcgen05.fence::after_thread_sync; every parity test, the
-            // bit_exact check of bench.py and the soak in tests/test_gpu_conv_ws.py run this way) or 1 (-DACCEL_WS_FENCE=1).
+            // Proxy fence.  Stages that arrive by TMA are written and read in the async proxy: nothing to order.  The twin
+            // tiles are still written by cp.async (generic proxy) and read by tcgen05.mma (async proxy); read strictly, the PTX memory
+            // model asks for a fence.proxy.async between the mbarrier wait that makes those writes visible and the MMAs, so the twin
+            // kernels issue one per stage here (compile-time: TWIN).  What it costs was measured when every layer still used cp.async
+            // (whole ResNet-18, batch 256, one box): no fence 262.1 k img/s, one per stage 255.2 k (-2.6 %), one per group of up to four
+            // arrived stages (mbarrier.test_wait look-ahead) 245.2 k; a run-time switch inside this loop costs 6 % by itself.  The
+            // developer path that loads non-twin stages with cp.async (ACCEL_WS_TMA=0) is fenced only in -DACCEL_WS_FENCE=1 builds.
             mbar_wait(&a_full[as], aph);
             if (fence) fence_proxy_async_smem();
             if (tl && st_i >= 32 && st_i < 64) tl[64 + (st_i - 32)] = clock64();      // issuer saw stage st_i
