@@ -836,8 +836,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_ws_kernel(const __grid_con
     for (int k = 0; k < kOps; ++k) {
       const int o = lt + kWsLoadThreads * k;
       // twin: xq = which image of the pair (8 bytes each inside the 16-byte row), else the 16-byte column of the row
-      const int xq = TWIN ? (o & 1) : o % x16s, y = TWIN ? (o >> 1) % rows : (o / x16s) % rows,
-                c = TWIN ? (o >> 1) / rows : o / (x16s * rows);
+      // twin: 16 consecutive lanes take the two images of eight consecutive channels of one row = 128 contiguous bytes of the
+      // stage (row-fastest lanes put every store of a warp on the same four banks: 3.5 M bank conflicts per launch under ncu)
+      const int tq = o >> 1;
+      const int xq = TWIN ? (o & 1) : o % x16s, y = TWIN ? (tq >> 3) % rows : (o / x16s) % rows,
+                c = TWIN ? ((tq & 7) | (((tq >> 3) / rows) << 3)) : o / (x16s * rows);
       uint32_t so = static_cast<uint32_t>(y) * p.row_stride + static_cast<uint32_t>(c * p.P + xq * (TWIN ? 8 : 16));
       if (p.b_layout == 4u) so ^= ((so >> 7) & 3u) << 4;           // 64-byte swizzle
       else if (p.b_layout == 6u) so ^= ((so >> 7) & 1u) << 4;      // 32-byte swizzle
